@@ -1,0 +1,375 @@
+// contract.cu — host launcher of the contraction engine behind eb200_contract and every BLAS-like
+// entry point. Replaces the device einsum_generic_algorithm launcher
+// (reference: libs/Einsums/TensorAlgebra/include/Einsums/TensorAlgebra/Backends/GPUTensorAlgebra.hpp:200-342).
+#include "contract.cuh"
+#include "contract_kernels.cuh"
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+#include <cstdlib>
+
+namespace eb200 {
+namespace {
+
+int grid_for(int64_t total, int threads, int per_sm = 8) {
+    int64_t need = (total + threads - 1) / threads;
+    int64_t cap = (int64_t)sm_count() * per_sm;
+    return (int)std::max<int64_t>(1, std::min(need, cap));
+}
+
+template <typename K> int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) EB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return EB200_OK;
+}
+
+// stream-ordered scratch for split partials: no synchronisation, freed after the finalize kernel
+int ws_alloc(void **p, size_t bytes, cudaStream_t s) {
+    EB_CUDA(cudaMallocAsync(p, bytes, s));
+    return EB200_OK;
+}
+
+template <typename T> int launch_scale(cudaStream_t s, const Grp &t, void *C, const double beta[2], eb200_contract_desc &d) {
+    ScaleArgs a;
+    a.t = t;
+    a.C = C;
+    a.beta[0] = beta[0];
+    a.beta[1] = beta[1];
+    if (t.tot == 0) return EB200_OK;
+    scale_tensor<T><<<grid_for(t.tot, 256), 256, 0, s>>>(a);
+    EB_POST_LAUNCH("scale_tensor");
+    d.launches++;
+    return EB200_OK;
+}
+
+template <typename T>
+int launch_finalize(cudaStream_t s, const Grp &gb, const Grp &gm, const Grp &gn, const void *ws, void *C, const double alpha[2],
+                    const double beta[2], int splits, eb200_contract_desc &d) {
+    FinalizeArgs a;
+    a.gb = gb; a.gm = gm; a.gn = gn;
+    a.ws = ws; a.C = C;
+    a.alpha[0] = alpha[0]; a.alpha[1] = alpha[1];
+    a.beta[0] = beta[0];   a.beta[1] = beta[1];
+    a.splits = splits;
+    int64_t total = gb.tot * gm.tot * gn.tot;
+    splitk_finalize<T><<<grid_for(total, 256), 256, 0, s>>>(a);
+    EB_POST_LAUNCH("splitk_finalize");
+    d.launches++;
+    return EB200_OK;
+}
+
+// ---------------------------------------------------------------- tile kernels
+struct TileChoice { int bm, bn, bk, per_sm; };
+
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, int MINB>
+int launch_mma_cfg(cudaStream_t s, TileArgs &args, dim3 grid) {
+    const bool ak = args.p.a_kmajor, bk = args.p.b_kmajor;
+#define EB_MMA_CASE(AK, BKM)                                                                          \
+    {                                                                                                 \
+        using Cfg = TileCfg<BM, BN, BK, WM, WN, STAGES, AK, BKM>;                                     \
+        auto kern = tile_mma_f64<BM, BN, BK, WM, WN, STAGES, AK, BKM, MINB>;                          \
+        int  rc = set_smem(kern, Cfg::SMEM);                                                          \
+        if (rc) return rc;                                                                            \
+        kern<<<grid, Cfg::NT, Cfg::SMEM, s>>>(args);                                                  \
+    }
+    if (ak && bk) EB_MMA_CASE(true, true)
+    else if (ak && !bk) EB_MMA_CASE(true, false)
+    else if (!ak && bk) EB_MMA_CASE(false, true)
+    else EB_MMA_CASE(false, false)
+#undef EB_MMA_CASE
+    EB_POST_LAUNCH("tile_mma_f64");
+    return EB200_OK;
+}
+
+int g_mma_config = 0; // 0 = auto; 1 = 128x128 (1 CTA/SM); 2 = 128x64 (2 CTA/SM). Tuning hook (EB200_MMA_CONFIG).
+std::once_flag g_cfg_once;
+
+template <typename T, bool CA, bool CB> int launch_simt(cudaStream_t s, TileArgs &args, dim3 grid) {
+    tile_simt<T, CA, CB><<<grid, 256, 0, s>>>(args);
+    EB_POST_LAUNCH("tile_simt");
+    return EB200_OK;
+}
+template <typename T> int launch_simt_conj(cudaStream_t s, TileArgs &args, dim3 grid) {
+    if constexpr (Scalar<T>::is_complex) {
+        if (args.conj_a && args.conj_b) return launch_simt<T, true, true>(s, args, grid);
+        if (args.conj_a) return launch_simt<T, true, false>(s, args, grid);
+        if (args.conj_b) return launch_simt<T, false, true>(s, args, grid);
+    }
+    return launch_simt<T, false, false>(s, args, grid);
+}
+
+template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const double beta_eff[2]) {
+    TileArgs args;
+    args.p = p;
+    args.A = p.swapped ? d.B.data : d.A.data;
+    args.B = p.swapped ? d.A.data : d.B.data;
+    args.C = d.C.data;
+    args.ws = nullptr;
+    args.alpha[0] = d.alpha[0]; args.alpha[1] = d.alpha[1];
+    args.beta[0] = beta_eff[0]; args.beta[1] = beta_eff[1];
+    args.conj_a = d.conj_a; args.conj_b = d.conj_b;
+
+    const bool mma = (p.family == EB200_KF_TILE_MMA);
+    int bm, bn, bk, ctas_per_sm;
+    std::call_once(g_cfg_once, [] {
+        const char *e = getenv("EB200_MMA_CONFIG");
+        if (e) g_mma_config = atoi(e);
+    });
+    int cfg = 0;
+    if (mma) {
+        cfg = g_mma_config ? g_mma_config : 1;
+        if (cfg == 2) { bm = 128; bn = 64; bk = 16; ctas_per_sm = 2; }
+        else { cfg = 1; bm = 128; bn = 128; bk = 16; ctas_per_sm = 1; }
+    } else { bm = 64; bn = 64; bk = 8; ctas_per_sm = 4; }
+
+    const int64_t tm = (p.m.tot + bm - 1) / bm, tn = (p.n.tot + bn - 1) / bn;
+    if (tm * tn > 0x7fffffffLL || p.b.tot > 65535)
+        return fail(EB200_ERR_UNSUPPORTED, "contract: tile grid too large (%lld x %lld tiles, %lld batches)", (long long)tm, (long long)tn,
+                    (long long)p.b.tot);
+    args.tiles_m = (int)tm;
+    args.tiles_n = (int)tn;
+
+    // split-K when the output alone cannot fill the machine
+    const int64_t tiles = tm * tn * p.b.tot;
+    const int64_t KT = (p.k.tot + bk - 1) / bk;
+    int           splits = 1;
+    if (d.split_k > 0) splits = d.split_k;
+    else {
+        const int64_t target = (int64_t)sm_count() * ctas_per_sm;
+        if (tiles * 2 <= target) splits = (int)std::min<int64_t>(target / tiles, std::max<int64_t>(1, KT / 8));
+    }
+    splits = (int)std::max<int64_t>(1, std::min<int64_t>(splits, KT));
+    if (splits > 65535) splits = 65535;
+    args.splits = splits;
+    d.split_k = splits;
+
+    void *ws = nullptr;
+    if (splits > 1) {
+        size_t bytes = (size_t)splits * p.b.tot * p.m.tot * p.n.tot * sizeof(T);
+        int    rc = ws_alloc(&ws, bytes, s);
+        if (rc) return rc;
+        args.ws = ws;
+    }
+    dim3 grid((unsigned)(tm * tn), (unsigned)splits, (unsigned)p.b.tot);
+    int  rc;
+    if (mma) {
+        if constexpr (std::is_same_v<T, double>) {
+            if (cfg == 2) rc = launch_mma_cfg<128, 64, 16, 32, 32, 3, 2>(s, args, grid);
+            else rc = launch_mma_cfg<128, 128, 16, 64, 32, 4, 1>(s, args, grid);
+        } else {
+            rc = fail(EB200_ERR_UNSUPPORTED, "tile_mma is FP64 only");
+        }
+    } else {
+        rc = launch_simt_conj<T>(s, args, grid);
+    }
+    if (rc) return rc;
+    d.launches++;
+    if (splits > 1) {
+        rc = launch_finalize<T>(s, p.b, p.m, p.n, ws, d.C.data, d.alpha, beta_eff, splits, d);
+        if (rc) return rc;
+        EB_CUDA(cudaFreeAsync(ws, s));
+    }
+    return EB200_OK;
+}
+
+// ---------------------------------------------------------------- streaming reductions
+template <typename T, int NN, bool CA, bool CB> int launch_reduce_nn(cudaStream_t s, bool row, ReduceArgs &a, dim3 grid) {
+    if (row) {
+        row_reduce<T, NN, 4, CA, CB><<<grid, 256, 0, s>>>(a);
+        EB_POST_LAUNCH("row_reduce");
+    } else {
+        col_reduce<T, NN, 2, CA, CB><<<grid, 256, 0, s>>>(a);
+        EB_POST_LAUNCH("col_reduce");
+    }
+    return EB200_OK;
+}
+template <typename T, bool CA, bool CB> int launch_reduce_c(cudaStream_t s, bool row, ReduceArgs &a, dim3 grid) {
+    int nn = (int)a.n.tot;
+    if (nn <= 1) return launch_reduce_nn<T, 1, CA, CB>(s, row, a, grid);
+    if (nn <= 2) return launch_reduce_nn<T, 2, CA, CB>(s, row, a, grid);
+    if (nn <= 4) return launch_reduce_nn<T, 4, CA, CB>(s, row, a, grid);
+    return launch_reduce_nn<T, 8, CA, CB>(s, row, a, grid);
+}
+template <typename T> int launch_reduce(cudaStream_t s, bool row, ReduceArgs &a, dim3 grid) {
+    if constexpr (Scalar<T>::is_complex) {
+        if (a.conj_a && a.conj_b) return launch_reduce_c<T, true, true>(s, row, a, grid);
+        if (a.conj_a) return launch_reduce_c<T, true, false>(s, row, a, grid);
+        if (a.conj_b) return launch_reduce_c<T, false, true>(s, row, a, grid);
+    }
+    return launch_reduce_c<T, false, false>(s, row, a, grid);
+}
+
+template <typename T> int run_reduce(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const double beta_eff[2]) {
+    ReduceArgs a;
+    a.rows = p.rows; a.n = p.n; a.k = p.k;
+    a.A = p.swapped ? d.B.data : d.A.data;
+    a.B = p.swapped ? d.A.data : d.B.data;
+    a.C = d.C.data;
+    a.ws = nullptr;
+    a.alpha[0] = d.alpha[0]; a.alpha[1] = d.alpha[1];
+    a.beta[0] = beta_eff[0]; a.beta[1] = beta_eff[1];
+    a.conj_a = p.swapped ? d.conj_b : d.conj_a;
+    a.conj_b = p.swapped ? d.conj_a : d.conj_b;
+
+    const bool    row = (p.family != EB200_KF_COLREDUCE);
+    const int64_t R = p.rows.tot, K = p.k.tot;
+    const int64_t rows_per_block = row ? 4 : 256 * 2;
+    const int64_t row_blocks = (R + rows_per_block - 1) / rows_per_block;
+    if (row_blocks > 0x7fffffffLL) return fail(EB200_ERR_UNSUPPORTED, "contract: too many rows for the reduction grid");
+    int splits = 1;
+    if (d.split_k > 0) splits = d.split_k;
+    else {
+        const int64_t target = (int64_t)sm_count() * 8;
+        const int64_t min_k_per_split = row ? 4096 : 64;
+        if (row_blocks < target) splits = (int)std::min<int64_t>((target + row_blocks - 1) / row_blocks, std::max<int64_t>(1, K / min_k_per_split));
+    }
+    splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(splits, K), 65535));
+    a.splits = splits;
+    d.split_k = splits;
+    void *ws = nullptr;
+    if (splits > 1) {
+        int rc = ws_alloc(&ws, (size_t)splits * R * p.n.tot * sizeof(T), s);
+        if (rc) return rc;
+        a.ws = ws;
+    }
+    dim3 grid((unsigned)row_blocks, (unsigned)splits, 1);
+    int  rc = launch_reduce<T>(s, row, a, grid);
+    if (rc) return rc;
+    d.launches++;
+    if (splits > 1) {
+        Grp none;
+        memset(&none, 0, sizeof(none));
+        none.tot = 1;
+        rc = launch_finalize<T>(s, none, p.rows, p.n, ws, d.C.data, d.alpha, beta_eff, splits, d);
+        if (rc) return rc;
+        EB_CUDA(cudaFreeAsync(ws, s));
+    }
+    return EB200_OK;
+}
+
+// ---------------------------------------------------------------- elementwise
+template <typename T, bool CA, bool CB> int launch_elem(cudaStream_t s, ElemArgs &a) {
+    elementwise<T, CA, CB><<<grid_for(a.t.tot, 256, 16), 256, 0, s>>>(a);
+    EB_POST_LAUNCH("elementwise");
+    return EB200_OK;
+}
+template <typename T> int run_elementwise(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const double beta_eff[2]) {
+    ElemArgs a;
+    a.t = p.t;
+    a.A = d.A.data; a.B = d.B.data; a.C = d.C.data;
+    a.alpha[0] = d.alpha[0]; a.alpha[1] = d.alpha[1];
+    a.beta[0] = beta_eff[0]; a.beta[1] = beta_eff[1];
+    int rc;
+    if constexpr (Scalar<T>::is_complex) {
+        if (d.conj_a && d.conj_b) rc = launch_elem<T, true, true>(s, a);
+        else if (d.conj_a) rc = launch_elem<T, true, false>(s, a);
+        else if (d.conj_b) rc = launch_elem<T, false, true>(s, a);
+        else rc = launch_elem<T, false, false>(s, a);
+    } else {
+        rc = launch_elem<T, false, false>(s, a);
+    }
+    if (rc) return rc;
+    d.launches++;
+    return EB200_OK;
+}
+
+// Whole-C group with C's own axes (every axis separately, repeated indices included): used when
+// C = beta*C has to touch elements the contraction does not enumerate (C with a repeated index).
+int full_c_group(const eb200_contract_desc &d, Grp &g) {
+    memset(&g, 0, sizeof(g));
+    g.tot = 1;
+    // sort axes by stride, merge contiguous
+    struct Ax { int64_t ext, st; };
+    std::vector<Ax> ax;
+    for (int a = 0; a < d.C.rank; a++) {
+        int64_t e = d.extent[d.C.index[a]];
+        if (e == 1) continue;
+        ax.push_back({e, d.C.stride[a]});
+    }
+    std::stable_sort(ax.begin(), ax.end(), [](const Ax &x, const Ax &y) { return std::llabs(x.st) < std::llabs(y.st); });
+    for (size_t i = 0; i + 1 < ax.size();) {
+        if (ax[i + 1].st == ax[i].st * ax[i].ext) {
+            ax[i].ext *= ax[i + 1].ext;
+            ax.erase(ax.begin() + i + 1);
+        } else i++;
+    }
+    if ((int)ax.size() > MAXG) return fail(EB200_ERR_UNSUPPORTED, "contract: C has more than %d non-mergeable axes", MAXG);
+    for (auto &x : ax) {
+        g.ext[g.n] = x.ext;
+        g.s[ROLE_C][g.n] = x.st;
+        g.n++;
+        g.tot *= x.ext;
+    }
+    return EB200_OK;
+}
+
+template <typename T> int contract_typed(cudaStream_t s, eb200_contract_desc &d) {
+    Plan p;
+    int  rc = make_plan(d, p, sm_count());
+    if (rc) return rc;
+    d.kernel_used = p.family;
+    d.launches = 0;
+    if (p.family == EB200_KF_NONE) return EB200_OK;
+    if (!d.C.data) return fail(EB200_ERR_INVALID_ARGUMENT, "contract: C.data is NULL");
+
+    double beta_eff[2] = {d.beta[0], Scalar<T>::is_complex ? d.beta[1] : 0.0};
+    const bool beta_is_one = (beta_eff[0] == 1.0 && beta_eff[1] == 0.0);
+    if (p.family == EB200_KF_SCALE_ONLY || p.c_has_repeat) {
+        // reference semantics: C->zero() / *C *= beta on the WHOLE tensor (GPUTensorAlgebra.hpp:273-277)
+        if (!beta_is_one) {
+            Grp g;
+            rc = full_c_group(d, g);
+            if (rc) return rc;
+            rc = launch_scale<T>(s, g, d.C.data, beta_eff, d);
+            if (rc) return rc;
+        }
+        if (p.family == EB200_KF_SCALE_ONLY) return EB200_OK;
+        beta_eff[0] = 1.0;
+        beta_eff[1] = 0.0;
+    }
+    if (!d.A.data || !d.B.data) return fail(EB200_ERR_INVALID_ARGUMENT, "contract: A.data or B.data is NULL");
+    switch (p.family) {
+    case EB200_KF_TILE_MMA:
+    case EB200_KF_TILE_SIMT: return run_tile<T>(s, p, d, beta_eff);
+    case EB200_KF_ROWREDUCE:
+    case EB200_KF_COLREDUCE:
+    case EB200_KF_FULLREDUCE: return run_reduce<T>(s, p, d, beta_eff);
+    case EB200_KF_ELEMENTWISE: return run_elementwise<T>(s, p, d, beta_eff);
+    default: return fail(EB200_ERR_UNSUPPORTED, "contract: no kernel family for this descriptor");
+    }
+}
+
+} // namespace
+
+int contract_dispatch(cudaStream_t s, eb200_contract_desc &d) {
+    if (d.A.dtype != d.C.dtype || d.B.dtype != d.C.dtype)
+        return fail(EB200_ERR_UNSUPPORTED, "contract: mixed element types (C=%d A=%d B=%d) are not supported by this build", d.C.dtype, d.A.dtype,
+                    d.B.dtype);
+    switch (d.C.dtype) {
+    case EB200_F32: return contract_typed<float>(s, d);
+    case EB200_F64: return contract_typed<double>(s, d);
+    case EB200_C64: return contract_typed<float2>(s, d);
+    case EB200_C128: return contract_typed<double2>(s, d);
+    default: return fail(EB200_ERR_INVALID_ARGUMENT, "contract: bad dtype %d", d.C.dtype);
+    }
+}
+
+} // namespace eb200
+
+extern "C" {
+
+int eb200_contract(void *stream, eb200_contract_desc *desc) {
+    if (!desc) return eb200::fail(EB200_ERR_INVALID_ARGUMENT, "eb200_contract: desc is NULL");
+    return eb200::contract_dispatch(eb200::as_stream(stream), *desc);
+}
+
+int eb200_contract_plan(eb200_contract_desc *desc) {
+    if (!desc) return eb200::fail(EB200_ERR_INVALID_ARGUMENT, "eb200_contract_plan: desc is NULL");
+    eb200::Plan p;
+    int         rc = eb200::make_plan(*desc, p, 148);
+    if (rc) return rc;
+    desc->kernel_used = p.family;
+    return EB200_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,643 @@
+// contract_kernels.cuh — device kernels of the contraction engine (sm_100a).
+//
+//   tile_mma_f64     C tile = A tile x B tile on the FP64 tensor pipe (DMMA.8x8x4 via
+//                    mma.sync.m8n8k4.f64; tcgen05 has no f64 kind), operands gathered straight from
+//                    their native index order into padded shared memory by a multi-stage cp.async
+//                    pipeline — the index permutation is fused into the loads (transpose-free TTGT).
+//   tile_simt        same tiling on the FMA pipes for f32 / complex.
+//   row_reduce       streaming kernel for contractions with <= 8 output columns per row and the
+//                    contracted direction contiguous in A (gemv 'T'-like, Fock J/K, dot).
+//   col_reduce       same, row direction contiguous in A (gemv 'N'-like).
+//   elementwise      no contracted index (outer / direct / broadcast products).
+//   splitk_finalize  fixed-order sum of split partials + alpha/beta epilogue (deterministic).
+//   scale_tensor     C = beta*C over C's full extent (beta == 0 writes zeros without reading).
+#pragma once
+#include "plan.cuh"
+
+namespace eb200 {
+
+// ------------------------------------------------------------------------------------------
+// small PTX helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 8-byte async copy global->shared; src_bytes == 0 zero-fills the destination
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+struct TileArgs {
+    Plan          p;
+    const void   *A;
+    const void   *B;
+    void         *C;
+    void         *ws;        // split-K partials [split][batch][M][N] (C's type), or nullptr
+    double        alpha[2];
+    double        beta[2];
+    int32_t       splits;    // >= 1
+    int32_t       tiles_m, tiles_n;
+    int32_t       conj_a, conj_b;
+};
+
+// ------------------------------------------------------------------------------------------
+// FP64 tensor-pipe tile kernel
+// ------------------------------------------------------------------------------------------
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool A_KMAJOR, bool B_KMAJOR> struct TileCfg {
+    static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
+    static constexpr int NT      = WARPS_M * WARPS_N * 32;
+    static constexpr int PAD     = 4; // pitch == 4 (mod 16) doubles: conflict-free DMMA fragment loads
+    static constexpr int A_PITCH = A_KMAJOR ? (BK + PAD) : (BM + PAD);
+    static constexpr int B_PITCH = B_KMAJOR ? (BK + PAD) : (BN + PAD);
+    static constexpr int A_ELEMS = A_KMAJOR ? BM * A_PITCH : BK * A_PITCH;
+    static constexpr int B_ELEMS = B_KMAJOR ? BN * B_PITCH : BK * B_PITCH;
+    static constexpr int RING    = STAGES + 1;
+    static constexpr size_t SMEM = (size_t)STAGES * (A_ELEMS + B_ELEMS) * 8 + (size_t)(2 * BM + 2 * BN) * 8 + (size_t)RING * BK * 2 * 8;
+};
+
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool A_KMAJOR, bool B_KMAJOR, int MINB>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) tile_mma_f64(const __grid_constant__ TileArgs args) {
+    using Cfg = TileCfg<BM, BN, BK, WM, WN, STAGES, A_KMAJOR, B_KMAJOR>;
+    constexpr int NT = Cfg::NT;
+    constexpr int FM = WM / 8, FN = WN / 8;
+    static_assert(BK % 4 == 0 && (BM * BK) % NT == 0 && (BN * BK) % NT == 0, "tile shape");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double  *As    = reinterpret_cast<double *>(smem_raw);
+    double  *Bs    = As + STAGES * Cfg::A_ELEMS;
+    int64_t *moffA = reinterpret_cast<int64_t *>(Bs + STAGES * Cfg::B_ELEMS);
+    int64_t *moffC = moffA + BM;
+    int64_t *noffB = moffC + BM;
+    int64_t *noffC = noffB + BN;
+    int64_t *koffA = noffC + BN;            // [RING][BK]
+    int64_t *koffB = koffA + Cfg::RING * BK; // [RING][BK]
+
+    const Plan &p   = args.p;
+    const int   tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int   wm0 = (warp % Cfg::WARPS_M) * WM, wn0 = (warp / Cfg::WARPS_M) * WN;
+
+    // grouped rasterisation: consecutive CTAs share A/B slabs in L2
+    int tile_m, tile_n;
+    {
+        constexpr int GROUP = 8;
+        int id = blockIdx.x, per_group = GROUP * args.tiles_n;
+        int g = id / per_group, first = g * GROUP;
+        int gsize = min(args.tiles_m - first, GROUP);
+        int in_g = id - g * per_group;
+        tile_m = first + in_g % gsize;
+        tile_n = in_g / gsize;
+    }
+    const int     split = blockIdx.y;
+    const int64_t batch = blockIdx.z;
+
+    int64_t baseA, baseB, baseC;
+    grp_offset3(p.b, batch, baseA, baseB, baseC);
+    const double *A = reinterpret_cast<const double *>(args.A) + baseA;
+    const double *B = reinterpret_cast<const double *>(args.B) + baseB;
+
+    const int64_t Mtot = p.m.tot, Ntot = p.n.tot, Ktot = p.k.tot;
+    const int     KT = (int)((Ktot + BK - 1) / BK);
+    const int     ks0 = (int)((int64_t)KT * split / args.splits), ks1 = (int)((int64_t)KT * (split + 1) / args.splits);
+    const int     nsteps = ks1 - ks0;
+
+    for (int i = tid; i < BM; i += NT) {
+        int64_t m = (int64_t)tile_m * BM + i, oa = OFF_INVALID, oc = OFF_INVALID;
+        if (m < Mtot) grp_offset2(p.m, m, ROLE_A, ROLE_C, oa, oc);
+        moffA[i] = oa;
+        moffC[i] = oc;
+    }
+    for (int i = tid; i < BN; i += NT) {
+        int64_t n = (int64_t)tile_n * BN + i, ob = OFF_INVALID, oc = OFF_INVALID;
+        if (n < Ntot) grp_offset2(p.n, n, ROLE_B, ROLE_C, ob, oc);
+        noffB[i] = ob;
+        noffC[i] = oc;
+    }
+    auto compute_koff = [&](int step /*local*/) {
+        // one entry per thread, BK threads
+        int     slot = step % Cfg::RING;
+        int64_t k = (int64_t)(ks0 + step) * BK + tid, oa = OFF_INVALID, ob = OFF_INVALID;
+        if (k < Ktot) grp_offset2(p.k, k, ROLE_A, ROLE_B, oa, ob);
+        koffA[slot * BK + tid] = oa;
+        koffB[slot * BK + tid] = ob;
+    };
+    if (tid < BK)
+        for (int s = 0; s < STAGES && s < nsteps; s++) compute_koff(s);
+    __syncthreads();
+
+    auto load_stage = [&](int step /*local*/) {
+        const int      buf  = step % STAGES;
+        const int      slot = step % Cfg::RING;
+        const uint32_t as = smem_u32(As + buf * Cfg::A_ELEMS), bs = smem_u32(Bs + buf * Cfg::B_ELEMS);
+#pragma unroll
+        for (int j = 0; j < BM * BK / NT; j++) {
+            int e = tid + j * NT, ml, kl;
+            if constexpr (A_KMAJOR) { kl = e % BK; ml = e / BK; }
+            else { ml = e % BM; kl = e / BM; }
+            int64_t  om = moffA[ml], ok = koffA[slot * BK + kl];
+            bool     v = (om != OFF_INVALID) && (ok != OFF_INVALID);
+            uint32_t dst = as + 8u * (A_KMAJOR ? ml * Cfg::A_PITCH + kl : kl * Cfg::A_PITCH + ml);
+            cp_async8(dst, v ? (const void *)(A + om + ok) : (const void *)A, v ? 8 : 0);
+        }
+#pragma unroll
+        for (int j = 0; j < BN * BK / NT; j++) {
+            int e = tid + j * NT, nl, kl;
+            if constexpr (B_KMAJOR) { kl = e % BK; nl = e / BK; }
+            else { nl = e % BN; kl = e / BN; }
+            int64_t  on = noffB[nl], ok = koffB[slot * BK + kl];
+            bool     v = (on != OFF_INVALID) && (ok != OFF_INVALID);
+            uint32_t dst = bs + 8u * (B_KMAJOR ? nl * Cfg::B_PITCH + kl : kl * Cfg::B_PITCH + nl);
+            cp_async8(dst, v ? (const void *)(B + on + ok) : (const void *)B, v ? 8 : 0);
+        }
+    };
+
+    double acc[FM][FN][2];
+#pragma unroll
+    for (int i = 0; i < FM; i++)
+#pragma unroll
+        for (int j = 0; j < FN; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nsteps) load_stage(s);
+        cp_async_commit();
+    }
+
+    const int fr = lane >> 2, fk = lane & 3; // fragment row (m or n) and k within the k4 step
+    for (int it = 0; it < nsteps; it++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        if (it + STAGES - 1 < nsteps) load_stage(it + STAGES - 1);
+        cp_async_commit();
+        if (tid < BK && it + STAGES < nsteps) compute_koff(it + STAGES);
+
+        const double *a_s = As + (it % STAGES) * Cfg::A_ELEMS;
+        const double *b_s = Bs + (it % STAGES) * Cfg::B_ELEMS;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double a[FM], b[FN];
+#pragma unroll
+            for (int i = 0; i < FM; i++) {
+                int m = wm0 + 8 * i + fr, k = kk + fk;
+                a[i] = a_s[A_KMAJOR ? m * Cfg::A_PITCH + k : k * Cfg::A_PITCH + m];
+            }
+#pragma unroll
+            for (int j = 0; j < FN; j++) {
+                int n = wn0 + 8 * j + fr, k = kk + fk;
+                b[j] = b_s[B_KMAJOR ? n * Cfg::B_PITCH + k : k * Cfg::B_PITCH + n];
+            }
+#pragma unroll
+            for (int i = 0; i < FM; i++)
+#pragma unroll
+                for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // ---- epilogue: C fragment (row = lane/4, cols = 2*(lane%4)+{0,1}) straight from registers
+    if (args.splits == 1) {
+        double      *C = reinterpret_cast<double *>(args.C) + baseC;
+        const double alpha = args.alpha[0], beta = args.beta[0];
+        const bool   has_beta = beta != 0.0;
+#pragma unroll
+        for (int i = 0; i < FM; i++) {
+            int64_t om = moffC[wm0 + 8 * i + fr];
+            if (om == OFF_INVALID) continue;
+#pragma unroll
+            for (int j = 0; j < FN; j++) {
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    int64_t on = noffC[wn0 + 8 * j + 2 * fk + c];
+                    if (on == OFF_INVALID) continue;
+                    double *dst = C + om + on;
+                    double  v = alpha * acc[i][j][c];
+                    if (has_beta) v = fma(beta, *dst, v);
+                    *dst = v;
+                }
+            }
+        }
+    } else {
+        double *ws = reinterpret_cast<double *>(args.ws) + (((int64_t)split * p.b.tot + batch) * Mtot) * Ntot;
+#pragma unroll
+        for (int i = 0; i < FM; i++) {
+            int64_t m = (int64_t)tile_m * BM + wm0 + 8 * i + fr;
+            if (m >= Mtot) continue;
+#pragma unroll
+            for (int j = 0; j < FN; j++) {
+                int64_t n = (int64_t)tile_n * BN + wn0 + 8 * j + 2 * fk;
+                if (n < Ntot) ws[m * Ntot + n] = acc[i][j][0];
+                if (n + 1 < Ntot) ws[m * Ntot + n + 1] = acc[i][j][1];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// FMA-pipe tile kernel (f32, complex, and f64 for cross-checks): 64x64x8 tile, 4x4 per thread
+// ------------------------------------------------------------------------------------------
+template <typename T, bool CONJ_A, bool CONJ_B> __global__ void __launch_bounds__(256) tile_simt(const __grid_constant__ TileArgs args) {
+    constexpr int BM = 64, BN = 64, BK = 8, NT = 256;
+    __shared__ T       As[BK][BM + 1];
+    __shared__ T       Bs[BK][BN + 1];
+    __shared__ int64_t moffA[BM], moffC[BM], noffB[BN], noffC[BN];
+
+    const Plan &p = args.p;
+    const int   tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int   tile_m = blockIdx.x % args.tiles_m, tile_n = blockIdx.x / args.tiles_m;
+    const int   split = blockIdx.y;
+    const int64_t batch = blockIdx.z;
+
+    int64_t baseA, baseB, baseC;
+    grp_offset3(p.b, batch, baseA, baseB, baseC);
+    const T *A = reinterpret_cast<const T *>(args.A) + baseA;
+    const T *B = reinterpret_cast<const T *>(args.B) + baseB;
+
+    const int64_t Mtot = p.m.tot, Ntot = p.n.tot, Ktot = p.k.tot;
+    const int     KT = (int)((Ktot + BK - 1) / BK);
+    const int     ks0 = (int)((int64_t)KT * split / args.splits), ks1 = (int)((int64_t)KT * (split + 1) / args.splits);
+
+    for (int i = tid; i < BM; i += NT) {
+        int64_t m = (int64_t)tile_m * BM + i, oa = OFF_INVALID, oc = OFF_INVALID;
+        if (m < Mtot) grp_offset2(p.m, m, ROLE_A, ROLE_C, oa, oc);
+        moffA[i] = oa; moffC[i] = oc;
+    }
+    for (int i = tid; i < BN; i += NT) {
+        int64_t n = (int64_t)tile_n * BN + i, ob = OFF_INVALID, oc = OFF_INVALID;
+        if (n < Ntot) grp_offset2(p.n, n, ROLE_B, ROLE_C, ob, oc);
+        noffB[i] = ob; noffC[i] = oc;
+    }
+    __syncthreads();
+
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = zero_of<T>();
+
+    // loader mapping: 512 elements per operand per step, 2 per thread; lanes run along the
+    // direction that is contiguous in global memory
+    for (int ks = ks0; ks < ks1; ks++) {
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            int e = tid + j * NT, ml, kl;
+            if (p.a_kmajor) { kl = e % BK; ml = e / BK; } else { ml = e % BM; kl = e / BM; }
+            int64_t k = (int64_t)ks * BK + kl, om = moffA[ml];
+            T       v = zero_of<T>();
+            if (k < Ktot && om != OFF_INVALID) v = maybe_conj<CONJ_A>(A[om + grp_offset(p.k, k, ROLE_A)]);
+            As[kl][ml] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            int e = tid + j * NT, nl, kl;
+            if (p.b_kmajor) { kl = e % BK; nl = e / BK; } else { nl = e % BN; kl = e / BN; }
+            int64_t k = (int64_t)ks * BK + kl, on = noffB[nl];
+            T       v = zero_of<T>();
+            if (k < Ktot && on != OFF_INVALID) v = maybe_conj<CONJ_B>(B[on + grp_offset(p.k, k, ROLE_B)]);
+            Bs[kl][nl] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; kk++) {
+            T a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = As[kk][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fma_(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    if (args.splits == 1) {
+        T         *C = reinterpret_cast<T *>(args.C) + baseC;
+        const T    alpha = make_scalar<T>(args.alpha[0], args.alpha[1]), beta = make_scalar<T>(args.beta[0], args.beta[1]);
+        const bool has_beta = !is_zero(beta);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int64_t om = moffC[ty + 16 * i];
+            if (om == OFF_INVALID) continue;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int64_t on = noffC[tx + 16 * j];
+                if (on == OFF_INVALID) continue;
+                T *dst = C + om + on;
+                *dst = axpby_(alpha, acc[i][j], beta, has_beta ? *dst : zero_of<T>(), has_beta);
+            }
+        }
+    } else {
+        T *ws = reinterpret_cast<T *>(args.ws) + (((int64_t)split * p.b.tot + batch) * Mtot) * Ntot;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int64_t m = (int64_t)tile_m * BM + ty + 16 * i;
+            if (m >= Mtot) continue;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int64_t n = (int64_t)tile_n * BN + tx + 16 * j;
+                if (n < Ntot) ws[m * Ntot + n] = acc[i][j];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// split-K / split-reduction finalize: C = beta*C + alpha * sum_s ws[s][row][col]   (fixed order)
+// rows are enumerated by (gb, gm) [gb outer], columns by gn; only ROLE_C strides are used.
+// ------------------------------------------------------------------------------------------
+struct FinalizeArgs {
+    Grp         gb, gm, gn;
+    const void *ws;
+    void       *C;
+    double      alpha[2], beta[2];
+    int32_t     splits;
+};
+
+template <typename T> __global__ void __launch_bounds__(256) splitk_finalize(const __grid_constant__ FinalizeArgs a) {
+    const int64_t rows = a.gb.tot * a.gm.tot, cols = a.gn.tot, total = rows * cols;
+    const T       alpha = make_scalar<T>(a.alpha[0], a.alpha[1]), beta = make_scalar<T>(a.beta[0], a.beta[1]);
+    const bool    has_beta = !is_zero(beta);
+    const T      *ws = reinterpret_cast<const T *>(a.ws);
+    T            *C = reinterpret_cast<T *>(a.C);
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (int64_t)gridDim.x * blockDim.x) {
+        int64_t row = x / cols, col = x - row * cols;
+        int64_t bi = row / a.gm.tot, mi = row - bi * a.gm.tot;
+        T       s = zero_of<T>();
+        for (int sp = 0; sp < a.splits; sp++) s = add_(s, ws[(int64_t)sp * total + x]);
+        int64_t off = grp_offset(a.gb, bi, ROLE_C) + grp_offset(a.gm, mi, ROLE_C) + grp_offset(a.gn, col, ROLE_C);
+        C[off] = axpby_(alpha, s, beta, has_beta ? C[off] : zero_of<T>(), has_beta);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// streaming reductions
+// ------------------------------------------------------------------------------------------
+struct ReduceArgs {
+    Grp         rows, n, k;   // rows: (A,B,C) strides; n: (B,C); k: (A,B)
+    const void *A;
+    const void *B;
+    void       *C;
+    void       *ws;           // partials [split][rows.tot][n.tot] when splits > 1
+    double      alpha[2], beta[2];
+    int32_t     splits;
+    int32_t     conj_a, conj_b;
+};
+
+// row_reduce: block = RB consecutive rows x one K segment. Lanes run along k (contiguous in A).
+// Each B value is loaded once and reused by the RB rows, so B traffic is 1/RB of A traffic.
+template <typename T, int NN, int RB, bool CONJ_A, bool CONJ_B>
+__global__ void __launch_bounds__(256) row_reduce(const __grid_constant__ ReduceArgs a) {
+    constexpr int NT = 256, NW = NT / 32, UNR = 4;
+    __shared__ T  red[NW][RB * NN];
+    const int     tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t R = a.rows.tot, K = a.k.tot;
+    const int     ncols = (int)a.n.tot;
+    const int64_t r0 = (int64_t)blockIdx.x * RB;
+    const int     split = blockIdx.y;
+    const int64_t k_begin = K * split / a.splits, k_end = K * (split + 1) / a.splits;
+
+    const T *A = reinterpret_cast<const T *>(a.A);
+    const T *B = reinterpret_cast<const T *>(a.B);
+
+    int64_t rowA[RB], rowB[RB];
+    bool    same_b = true; // B does not depend on the row (no batch index): share the B loads
+#pragma unroll
+    for (int j = 0; j < RB; j++) {
+        int64_t r = r0 + j, oa = 0, ob = 0, oc = 0;
+        if (r < R) grp_offset3(a.rows, r, oa, ob, oc);
+        rowA[j] = (r < R) ? oa : OFF_INVALID;
+        rowB[j] = ob;
+        if (ob != 0) same_b = false;
+    }
+    int64_t colB[NN];
+#pragma unroll
+    for (int c = 0; c < NN; c++) colB[c] = (c < ncols) ? grp_offset(a.n, c, ROLE_B) : 0;
+
+    T acc[RB][NN];
+#pragma unroll
+    for (int j = 0; j < RB; j++)
+#pragma unroll
+        for (int c = 0; c < NN; c++) acc[j][c] = zero_of<T>();
+
+    const int64_t e0 = a.k.n > 0 ? a.k.ext[0] : 1;
+    for (int64_t kb = k_begin + (int64_t)tid * 1; kb < k_end; kb += (int64_t)NT * UNR) {
+        int64_t oa[UNR], ob[UNR];
+        bool    ok[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            int64_t k = kb + (int64_t)u * NT;
+            ok[u] = k < k_end;
+            oa[u] = ob[u] = 0;
+            if (ok[u]) {
+                if (a.k.n == 1) {
+                    oa[u] = k * a.k.s[ROLE_A][0];
+                    ob[u] = k * a.k.s[ROLE_B][0];
+                } else {
+                    grp_offset2(a.k, k, ROLE_A, ROLE_B, oa[u], ob[u]);
+                }
+            }
+        }
+        (void)e0;
+        T av[UNR][RB];
+#pragma unroll
+        for (int u = 0; u < UNR; u++)
+#pragma unroll
+            for (int j = 0; j < RB; j++) av[u][j] = (ok[u] && rowA[j] != OFF_INVALID) ? A[rowA[j] + oa[u]] : zero_of<T>();
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            if (!ok[u]) continue;
+            if (same_b) {
+#pragma unroll
+                for (int c = 0; c < NN; c++) {
+                    if (c >= ncols) break;
+                    T bv = maybe_conj<CONJ_B>(B[ob[u] + colB[c]]);
+#pragma unroll
+                    for (int j = 0; j < RB; j++) acc[j][c] = fma_(maybe_conj<CONJ_A>(av[u][j]), bv, acc[j][c]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < RB; j++) {
+                    if (rowA[j] == OFF_INVALID) continue;
+#pragma unroll
+                    for (int c = 0; c < NN; c++) {
+                        if (c >= ncols) break;
+                        T bv = maybe_conj<CONJ_B>(B[rowB[j] + ob[u] + colB[c]]);
+                        acc[j][c] = fma_(maybe_conj<CONJ_A>(av[u][j]), bv, acc[j][c]);
+                    }
+                }
+            }
+        }
+    }
+    (void)lane;
+    // block reduction, fixed order
+#pragma unroll
+    for (int j = 0; j < RB; j++)
+#pragma unroll
+        for (int c = 0; c < NN; c++) {
+            T v = warp_sum(acc[j][c]);
+            if (lane == 0) red[warp][j * NN + c] = v;
+        }
+    __syncthreads();
+    if (tid < RB * NN) {
+        int     j = tid / NN, c = tid % NN;
+        int64_t r = r0 + j;
+        if (r < R && c < ncols) {
+            T s = zero_of<T>();
+#pragma unroll
+            for (int w = 0; w < NW; w++) s = add_(s, red[w][tid]);
+            if (a.splits == 1) {
+                const T    alpha = make_scalar<T>(a.alpha[0], a.alpha[1]), beta = make_scalar<T>(a.beta[0], a.beta[1]);
+                const bool has_beta = !is_zero(beta);
+                T         *dst = reinterpret_cast<T *>(a.C) + grp_offset(a.rows, r, ROLE_C) + grp_offset(a.n, c, ROLE_C);
+                *dst = axpby_(alpha, s, beta, has_beta ? *dst : zero_of<T>(), has_beta);
+            } else {
+                reinterpret_cast<T *>(a.ws)[((int64_t)split * R + r) * ncols + c] = s;
+            }
+        }
+    }
+}
+
+// col_reduce: threads run along rows (contiguous in A); each thread owns RT rows and walks a K segment.
+template <typename T, int NN, int RT, bool CONJ_A, bool CONJ_B>
+__global__ void __launch_bounds__(256) col_reduce(const __grid_constant__ ReduceArgs a) {
+    constexpr int NT = 256;
+    const int     tid = threadIdx.x;
+    const int64_t R = a.rows.tot, K = a.k.tot;
+    const int     ncols = (int)a.n.tot;
+    const int     split = blockIdx.y;
+    const int64_t k_begin = K * split / a.splits, k_end = K * (split + 1) / a.splits;
+    const T      *A = reinterpret_cast<const T *>(a.A);
+    const T      *B = reinterpret_cast<const T *>(a.B);
+
+    int64_t rowA[RT], rowB[RT];
+#pragma unroll
+    for (int j = 0; j < RT; j++) {
+        int64_t r = (int64_t)blockIdx.x * NT * RT + (int64_t)j * NT + tid, oa = 0, ob = 0, oc = 0;
+        if (r < R) grp_offset3(a.rows, r, oa, ob, oc);
+        rowA[j] = (r < R) ? oa : OFF_INVALID;
+        rowB[j] = ob;
+    }
+    int64_t colB[NN];
+#pragma unroll
+    for (int c = 0; c < NN; c++) colB[c] = (c < ncols) ? grp_offset(a.n, c, ROLE_B) : 0;
+
+    T acc[RT][NN];
+#pragma unroll
+    for (int j = 0; j < RT; j++)
+#pragma unroll
+        for (int c = 0; c < NN; c++) acc[j][c] = zero_of<T>();
+
+    // uniform incremental walk over the K multi-index
+    int64_t idx[MAXG], offA = 0, offB = 0;
+    {
+        int64_t x = k_begin;
+        for (int i = 0; i < MAXG; i++) {
+            idx[i] = 0;
+            if (i < a.k.n) {
+                int64_t q = x / a.k.ext[i];
+                idx[i] = x - q * a.k.ext[i];
+                offA += idx[i] * a.k.s[ROLE_A][i];
+                offB += idx[i] * a.k.s[ROLE_B][i];
+                x = q;
+            }
+        }
+    }
+    for (int64_t k = k_begin; k < k_end; k++) {
+        T av[RT];
+#pragma unroll
+        for (int j = 0; j < RT; j++) av[j] = (rowA[j] != OFF_INVALID) ? maybe_conj<CONJ_A>(A[rowA[j] + offA]) : zero_of<T>();
+#pragma unroll
+        for (int c = 0; c < NN; c++) {
+            if (c >= ncols) break;
+#pragma unroll
+            for (int j = 0; j < RT; j++) {
+                T bv = maybe_conj<CONJ_B>(B[rowB[j] + offB + colB[c]]);
+                acc[j][c] = fma_(av[j], bv, acc[j][c]);
+            }
+        }
+        // advance
+        offA += a.k.s[ROLE_A][0];
+        offB += a.k.s[ROLE_B][0];
+        if (++idx[0] == a.k.ext[0]) {
+#pragma unroll
+            for (int i = 0; i < MAXG - 1; i++) {
+                if (i < a.k.n && idx[i] == a.k.ext[i]) {
+                    offA -= idx[i] * a.k.s[ROLE_A][i];
+                    offB -= idx[i] * a.k.s[ROLE_B][i];
+                    idx[i] = 0;
+                    if (i + 1 < a.k.n) {
+                        idx[i + 1]++;
+                        offA += a.k.s[ROLE_A][i + 1];
+                        offB += a.k.s[ROLE_B][i + 1];
+                    }
+                }
+            }
+        }
+    }
+    const T    alpha = make_scalar<T>(a.alpha[0], a.alpha[1]), beta = make_scalar<T>(a.beta[0], a.beta[1]);
+    const bool has_beta = !is_zero(beta);
+#pragma unroll
+    for (int j = 0; j < RT; j++) {
+        int64_t r = (int64_t)blockIdx.x * NT * RT + (int64_t)j * NT + tid;
+        if (r >= R) continue;
+#pragma unroll
+        for (int c = 0; c < NN; c++) {
+            if (c >= ncols) break;
+            if (a.splits == 1) {
+                T *dst = reinterpret_cast<T *>(a.C) + grp_offset(a.rows, r, ROLE_C) + grp_offset(a.n, c, ROLE_C);
+                *dst = axpby_(alpha, acc[j][c], beta, has_beta ? *dst : zero_of<T>(), has_beta);
+            } else {
+                reinterpret_cast<T *>(a.ws)[((int64_t)split * R + r) * ncols + c] = acc[j][c];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// elementwise (no contracted index) and whole-tensor scaling
+// ------------------------------------------------------------------------------------------
+struct ElemArgs {
+    Grp         t; // all target indices, inner-first by C stride; strides (A,B,C)
+    const void *A;
+    const void *B;
+    void       *C;
+    double      alpha[2], beta[2];
+};
+
+template <typename T, bool CONJ_A, bool CONJ_B> __global__ void __launch_bounds__(256) elementwise(const __grid_constant__ ElemArgs a) {
+    const T      *A = reinterpret_cast<const T *>(a.A);
+    const T      *B = reinterpret_cast<const T *>(a.B);
+    T            *C = reinterpret_cast<T *>(a.C);
+    const T       alpha = make_scalar<T>(a.alpha[0], a.alpha[1]), beta = make_scalar<T>(a.beta[0], a.beta[1]);
+    const bool    has_beta = !is_zero(beta);
+    const int64_t total = a.t.tot;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (int64_t)gridDim.x * blockDim.x) {
+        int64_t oa, ob, oc;
+        grp_offset3(a.t, x, oa, ob, oc);
+        T v = mul_(maybe_conj<CONJ_A>(A[oa]), maybe_conj<CONJ_B>(B[ob]));
+        C[oc] = axpby_(alpha, v, beta, has_beta ? C[oc] : zero_of<T>(), has_beta);
+    }
+}
+
+struct ScaleArgs {
+    Grp    t; // ROLE_C strides only
+    void  *C;
+    double beta[2];
+};
+template <typename T> __global__ void __launch_bounds__(256) scale_tensor(const __grid_constant__ ScaleArgs a) {
+    T            *C = reinterpret_cast<T *>(a.C);
+    const T       beta = make_scalar<T>(a.beta[0], a.beta[1]);
+    const bool    zero = is_zero(beta);
+    const int64_t total = a.t.tot;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (int64_t)gridDim.x * blockDim.x) {
+        int64_t oc = grp_offset(a.t, x, ROLE_C);
+        C[oc] = zero ? zero_of<T>() : mul_(beta, C[oc]);
+    }
+}
+
+} // namespace eb200

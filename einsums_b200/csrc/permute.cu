@@ -1,0 +1,252 @@
+// permute.cu — tensor transpose C[perm] = beta*C + alpha*op(A) for any rank and any axis order.
+// Replaces tensor_algebra::detail::gpu_permute (LibreTT plan+execute,
+// reference libs/Einsums/TensorAlgebra/src/DevicePermute.hip:20-59) and permute_kernel
+// (TensorAlgebra/Backends/DevicePermute.hpp:34-73), plus eb200_copy_strided for the layout-changing
+// copies of Tensor/Backends/DeviceTensor.hpp:295-402.
+//
+// Method: axes are sorted by A stride and merged where A and C agree on contiguity; then
+//   * if the fastest axis of A is also the fastest axis of C -> row kernel (both sides coalesced,
+//     16-byte accesses when alignment allows);
+//   * otherwise -> 2-D tile transpose through padded shared memory over the plane spanned by
+//     (fastest axis of A, fastest axis of C); both the read and the write are coalesced, all other
+//     axes are decoded once per tile.
+#include "plan.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace eb200 {
+namespace {
+
+struct PermArgs {
+    Grp         rest;   // remaining axes: strides ROLE_A / ROLE_C
+    int64_t     ea, sa_a, sc_a; // axis "a": fastest in A   (extent, A stride, C stride)
+    int64_t     ec, sa_c, sc_c; // axis "c": fastest in C
+    const void *A;
+    void       *C;
+    double      alpha[2], beta[2];
+    int64_t     tiles_a, tiles_c;
+};
+
+template <typename T, bool CONJ> __device__ __forceinline__ T perm_out(T alpha, T a, T beta, T *dst, bool has_beta) {
+    T v = mul_(alpha, maybe_conj<CONJ>(a));
+    if (has_beta) v = fma_(beta, *dst, v);
+    return v;
+}
+
+// plane transpose: TILE x TILE elements per block, block = (TILE, ROWS)
+template <typename T, bool CONJ, int TILE, int ROWS> __global__ void __launch_bounds__(TILE *ROWS) permute_tile(const __grid_constant__ PermArgs a) {
+    __shared__ T tile[TILE][TILE + 1];
+    const T     *A = reinterpret_cast<const T *>(a.A);
+    T           *C = reinterpret_cast<T *>(a.C);
+    const T      alpha = make_scalar<T>(a.alpha[0], a.alpha[1]), beta = make_scalar<T>(a.beta[0], a.beta[1]);
+    const bool   has_beta = !is_zero(beta);
+    const int    tx = threadIdx.x, ty = threadIdx.y;
+    const int64_t per_rest = a.tiles_a * a.tiles_c;
+    const int64_t ntiles = per_rest * a.rest.tot;
+
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int64_t rest = t / per_rest, in = t - rest * per_rest;
+        int64_t tc = in / a.tiles_a, ta = in - tc * a.tiles_a;
+        int64_t offA, offC;
+        grp_offset2(a.rest, rest, ROLE_A, ROLE_C, offA, offC);
+        const int64_t a0 = ta * TILE, c0 = tc * TILE;
+        // read: lanes along axis a (contiguous in A), rows along axis c
+        {
+            const int64_t ia = a0 + tx;
+#pragma unroll
+            for (int r = ty; r < TILE; r += ROWS) {
+                int64_t ic = c0 + r;
+                if (ia < a.ea && ic < a.ec) tile[r][tx] = A[offA + ia * a.sa_a + ic * a.sa_c];
+            }
+        }
+        __syncthreads();
+        // write: lanes along axis c (contiguous in C), rows along axis a
+        {
+            const int64_t ic = c0 + tx;
+#pragma unroll
+            for (int r = ty; r < TILE; r += ROWS) {
+                int64_t ia = a0 + r;
+                if (ia < a.ea && ic < a.ec) {
+                    T *dst = C + offC + ia * a.sc_a + ic * a.sc_c;
+                    *dst = perm_out<T, CONJ>(alpha, tile[tx][r], beta, dst, has_beta);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// row kernel: the same axis is fastest on both sides. VEC elements per thread per step.
+template <typename T, bool CONJ, int VEC> __global__ void __launch_bounds__(256) permute_rows(const __grid_constant__ PermArgs a) {
+    const T      *A = reinterpret_cast<const T *>(a.A);
+    T            *C = reinterpret_cast<T *>(a.C);
+    const T       alpha = make_scalar<T>(a.alpha[0], a.alpha[1]), beta = make_scalar<T>(a.beta[0], a.beta[1]);
+    const bool    has_beta = !is_zero(beta);
+    const int64_t chunks_per_row = (a.ea + VEC - 1) / VEC;
+    const int64_t total = chunks_per_row * a.rest.tot;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (int64_t)gridDim.x * blockDim.x) {
+        int64_t row = x / chunks_per_row, ch = x - row * chunks_per_row;
+        int64_t offA, offC;
+        grp_offset2(a.rest, row, ROLE_A, ROLE_C, offA, offC);
+        int64_t i0 = ch * VEC;
+        if constexpr (VEC > 1) {
+            // only launched when sa_a == sc_a == 1, ea % VEC == 0 and everything is VEC-aligned
+            struct alignas(sizeof(T) * VEC) Pack { T v[VEC]; };
+            Pack in = *reinterpret_cast<const Pack *>(A + offA + i0);
+            Pack out;
+            T   *dst = C + offC + i0;
+            if (has_beta) out = *reinterpret_cast<const Pack *>(dst);
+#pragma unroll
+            for (int u = 0; u < VEC; u++) {
+                T v = mul_(alpha, maybe_conj<CONJ>(in.v[u]));
+                if (has_beta) v = fma_(beta, out.v[u], v);
+                out.v[u] = v;
+            }
+            *reinterpret_cast<Pack *>(dst) = out;
+        } else {
+            if (i0 < a.ea) {
+                T *dst = C + offC + i0 * a.sc_a;
+                *dst = perm_out<T, CONJ>(alpha, A[offA + i0 * a.sa_a], beta, dst, has_beta);
+            }
+        }
+    }
+}
+
+struct Axis { int64_t ext, sa, sc; };
+
+template <typename T>
+int permute_impl(void *stream, int rank, const int64_t *dimsA, const int64_t *stridesA, const int *perm, const int64_t *stridesC, T alpha,
+                 const T *A, T beta, T *C, int conj) {
+    if (rank < 0 || rank > EB200_MAX_RANK) return fail(EB200_ERR_RANK, "permute: rank %d outside [0,%d]", rank, EB200_MAX_RANK);
+    if (rank > 0 && (!dimsA || !stridesA || !perm || !stridesC)) return fail(EB200_ERR_INVALID_ARGUMENT, "permute: NULL dims/strides/perm");
+    bool seen[EB200_MAX_RANK] = {false};
+    for (int i = 0; i < rank; i++) {
+        if (perm[i] < 0 || perm[i] >= rank || seen[perm[i]])
+            return fail(EB200_ERR_INVALID_ARGUMENT, "permute: perm is not a permutation of 0..%d (perm[%d]=%d)", rank - 1, i, perm[i]);
+        seen[perm[i]] = true;
+    }
+    std::vector<Axis> ax;
+    for (int i = 0; i < rank; i++) {
+        int     ai = perm[i];
+        int64_t e = dimsA[ai];
+        if (e < 0) return fail(EB200_ERR_DOMAIN, "permute: negative extent %lld on axis %d", (long long)e, ai);
+        if (e == 0) return EB200_OK; // empty tensor: nothing to do
+        if (e == 1) continue;
+        ax.push_back({e, stridesA[ai], stridesC[i]});
+    }
+    if (!A || !C) return fail(EB200_ERR_INVALID_ARGUMENT, "permute: NULL tensor pointer");
+    std::stable_sort(ax.begin(), ax.end(), [](const Axis &x, const Axis &y) { return std::llabs(x.sa) < std::llabs(y.sa); });
+    for (size_t i = 0; i + 1 < ax.size();) {
+        if (ax[i + 1].sa == ax[i].sa * ax[i].ext && ax[i + 1].sc == ax[i].sc * ax[i].ext) {
+            ax[i].ext *= ax[i + 1].ext;
+            ax.erase(ax.begin() + i + 1);
+        } else i++;
+    }
+    if (ax.empty()) ax.push_back({1, 1, 1}); // scalar / all-ones tensor
+
+    PermArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.rest.tot = 1;
+    pa.A = A; pa.C = C;
+    if constexpr (Scalar<T>::is_complex) { pa.alpha[0] = alpha.x; pa.alpha[1] = alpha.y; pa.beta[0] = beta.x; pa.beta[1] = beta.y; }
+    else { pa.alpha[0] = alpha; pa.beta[0] = beta; }
+
+    size_t ia = 0, ic = 0;
+    for (size_t i = 1; i < ax.size(); i++)
+        if (std::llabs(ax[i].sc) < std::llabs(ax[ic].sc)) ic = i;
+    auto push_rest = [&](const Axis &x) -> bool {
+        if (pa.rest.n >= MAXG) return false;
+        pa.rest.ext[pa.rest.n] = x.ext;
+        pa.rest.s[ROLE_A][pa.rest.n] = x.sa;
+        pa.rest.s[ROLE_C][pa.rest.n] = x.sc;
+        pa.rest.n++;
+        pa.rest.tot *= x.ext;
+        return true;
+    };
+    cudaStream_t s = as_stream(stream);
+    const bool   cj = conj && Scalar<T>::is_complex;
+    if (ia == ic) {
+        pa.ea = ax[ia].ext; pa.sa_a = ax[ia].sa; pa.sc_a = ax[ia].sc;
+        for (size_t i = 0; i < ax.size(); i++)
+            if (i != ia && !push_rest(ax[i])) return fail(EB200_ERR_UNSUPPORTED, "permute: more than %d non-mergeable axes", MAXG + 2);
+        constexpr int VEC = 16 / sizeof(T) > 1 ? 16 / sizeof(T) : 1;
+        bool          vec_ok = VEC > 1 && pa.sa_a == 1 && pa.sc_a == 1 && pa.ea % VEC == 0 && ((uintptr_t)A % 16 == 0) && ((uintptr_t)C % 16 == 0);
+        for (int i = 0; i < pa.rest.n && vec_ok; i++)
+            if (pa.rest.s[ROLE_A][i] % VEC || pa.rest.s[ROLE_C][i] % VEC) vec_ok = false;
+        int64_t chunks = ((pa.ea + (vec_ok ? VEC : 1) - 1) / (vec_ok ? VEC : 1)) * pa.rest.tot;
+        int     grid = (int)std::max<int64_t>(1, std::min<int64_t>((chunks + 255) / 256, (int64_t)sm_count() * 16));
+        if (vec_ok) {
+            if (cj) permute_rows<T, true, VEC><<<grid, 256, 0, s>>>(pa);
+            else permute_rows<T, false, VEC><<<grid, 256, 0, s>>>(pa);
+        } else {
+            if (cj) permute_rows<T, true, 1><<<grid, 256, 0, s>>>(pa);
+            else permute_rows<T, false, 1><<<grid, 256, 0, s>>>(pa);
+        }
+        EB_POST_LAUNCH("permute_rows");
+    } else {
+        pa.ea = ax[ia].ext; pa.sa_a = ax[ia].sa; pa.sc_a = ax[ia].sc;
+        pa.ec = ax[ic].ext; pa.sa_c = ax[ic].sa; pa.sc_c = ax[ic].sc;
+        for (size_t i = 0; i < ax.size(); i++)
+            if (i != ia && i != ic && !push_rest(ax[i])) return fail(EB200_ERR_UNSUPPORTED, "permute: more than %d non-mergeable axes", MAXG + 2);
+        constexpr int TILE = 32, ROWS = 8;
+        pa.tiles_a = (pa.ea + TILE - 1) / TILE;
+        pa.tiles_c = (pa.ec + TILE - 1) / TILE;
+        int64_t ntiles = pa.tiles_a * pa.tiles_c * pa.rest.tot;
+        int     grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)sm_count() * 32));
+        dim3    block(TILE, ROWS);
+        if (cj) permute_tile<T, true, TILE, ROWS><<<grid, block, 0, s>>>(pa);
+        else permute_tile<T, false, TILE, ROWS><<<grid, block, 0, s>>>(pa);
+        EB_POST_LAUNCH("permute_tile");
+    }
+    return EB200_OK;
+}
+
+} // namespace
+} // namespace eb200
+
+using namespace eb200;
+
+extern "C" {
+
+int eb200_spermute(void *stream, int rank, const int64_t *dimsA, const int64_t *stridesA, const int *perm, const int64_t *stridesC,
+                   const float *alpha, const float *A, const float *beta, float *C, int conj) {
+    if (!alpha || !beta) return fail(EB200_ERR_INVALID_ARGUMENT, "permute: alpha/beta is NULL");
+    return permute_impl<float>(stream, rank, dimsA, stridesA, perm, stridesC, *alpha, A, *beta, C, conj);
+}
+int eb200_dpermute(void *stream, int rank, const int64_t *dimsA, const int64_t *stridesA, const int *perm, const int64_t *stridesC,
+                   const double *alpha, const double *A, const double *beta, double *C, int conj) {
+    if (!alpha || !beta) return fail(EB200_ERR_INVALID_ARGUMENT, "permute: alpha/beta is NULL");
+    return permute_impl<double>(stream, rank, dimsA, stridesA, perm, stridesC, *alpha, A, *beta, C, conj);
+}
+int eb200_cpermute(void *stream, int rank, const int64_t *dimsA, const int64_t *stridesA, const int *perm, const int64_t *stridesC,
+                   const float *alpha, const float *A, const float *beta, float *C, int conj) {
+    if (!alpha || !beta) return fail(EB200_ERR_INVALID_ARGUMENT, "permute: alpha/beta is NULL");
+    return permute_impl<float2>(stream, rank, dimsA, stridesA, perm, stridesC, *(const float2 *)alpha, (const float2 *)A, *(const float2 *)beta,
+                                (float2 *)C, conj);
+}
+int eb200_zpermute(void *stream, int rank, const int64_t *dimsA, const int64_t *stridesA, const int *perm, const int64_t *stridesC,
+                   const double *alpha, const double *A, const double *beta, double *C, int conj) {
+    if (!alpha || !beta) return fail(EB200_ERR_INVALID_ARGUMENT, "permute: alpha/beta is NULL");
+    return permute_impl<double2>(stream, rank, dimsA, stridesA, perm, stridesC, *(const double2 *)alpha, (const double2 *)A,
+                                 *(const double2 *)beta, (double2 *)C, conj);
+}
+
+int eb200_copy_strided(void *stream, int dtype, int rank, const int64_t *dims, const void *src, const int64_t *src_strides, void *dst,
+                       const int64_t *dst_strides) {
+    int perm[EB200_MAX_RANK];
+    if (rank < 0 || rank > EB200_MAX_RANK) return fail(EB200_ERR_RANK, "copy_strided: rank %d outside [0,%d]", rank, EB200_MAX_RANK);
+    for (int i = 0; i < rank; i++) perm[i] = i;
+    switch (dtype) {
+    case EB200_F32: return permute_impl<float>(stream, rank, dims, src_strides, perm, dst_strides, 1.0f, (const float *)src, 0.0f, (float *)dst, 0);
+    case EB200_F64: return permute_impl<double>(stream, rank, dims, src_strides, perm, dst_strides, 1.0, (const double *)src, 0.0, (double *)dst, 0);
+    case EB200_C64:
+        return permute_impl<float2>(stream, rank, dims, src_strides, perm, dst_strides, make_float2(1.f, 0.f), (const float2 *)src,
+                                    make_float2(0.f, 0.f), (float2 *)dst, 0);
+    case EB200_C128:
+        return permute_impl<double2>(stream, rank, dims, src_strides, perm, dst_strides, make_double2(1., 0.), (const double2 *)src,
+                                     make_double2(0., 0.), (double2 *)dst, 0);
+    default: return fail(EB200_ERR_INVALID_ARGUMENT, "copy_strided: bad dtype %d", dtype);
+    }
+}
+}

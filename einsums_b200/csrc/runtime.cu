@@ -1,0 +1,219 @@
+// runtime.cu — device runtime of libeinsums_b200.so: init/finalize, streams, events, memory.
+// Replaces libs/Einsums/GPUStreams/src/GPUStreams.hip:58-166 and the hipMalloc/hipMemcpy calls in
+// libs/Einsums/Tensor/include/Einsums/Tensor/Backends/DeviceTensor.hpp:33-116 (reference paths).
+#include "common.cuh"
+
+namespace eb200 {
+
+ErrorState &err_state() {
+    static thread_local ErrorState st;
+    return st;
+}
+int64_t &launch_counter() {
+    static thread_local int64_t n = 0;
+    return n;
+}
+
+int fail(int code, const char *fmt, ...) {
+    ErrorState &st = err_state();
+    st.code = code;
+    st.cuda = 0;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(st.msg, sizeof(st.msg), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    ErrorState &st = err_state();
+    st.cuda = (int)e;
+    if (e == cudaErrorMemoryAllocation) st.code = EB200_ERR_OUT_OF_MEMORY;
+    else if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) st.code = EB200_ERR_NO_DEVICE;
+    else st.code = EB200_ERR_CUDA;
+    snprintf(st.msg, sizeof(st.msg), "CUDA error %d (%s) in %s: %s", (int)e, cudaGetErrorName(e), what, cudaGetErrorString(e));
+    // clear the sticky "last error" for non-fatal failures so later calls start clean
+    (void)cudaGetLastError();
+    return st.code;
+}
+
+static int g_sm_count[64] = {0};
+int        sm_count() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (g_sm_count[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        g_sm_count[dev] = n;
+    }
+    return g_sm_count[dev];
+}
+
+} // namespace eb200
+
+using namespace eb200;
+
+extern "C" {
+
+int eb200_version(void) { return EB200_VERSION_MAJOR * 1000 + EB200_VERSION_MINOR; }
+
+const char *eb200_last_error_string(void) { return err_state().msg; }
+int         eb200_last_cuda_error(void) { return err_state().cuda; }
+
+int eb200_device_count(int *count) {
+    if (!count) return fail(EB200_ERR_INVALID_ARGUMENT, "eb200_device_count: count is NULL");
+    int         n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return cuda_fail(e, "cudaGetDeviceCount");
+    }
+    *count = n;
+    return EB200_OK;
+}
+
+int eb200_set_device(int device) {
+    EB_CUDA(cudaSetDevice(device));
+    return EB200_OK;
+}
+
+int eb200_init(int device) {
+    int n = 0;
+    int rc = eb200_device_count(&n);
+    if (rc != EB200_OK) return rc;
+    if (n == 0) return fail(EB200_ERR_NO_DEVICE, "eb200_init: no CUDA device is visible; this backend has no CPU fallback");
+    if (device < 0 || device >= n) return fail(EB200_ERR_INVALID_ARGUMENT, "eb200_init: device %d out of range [0,%d)", device, n);
+    EB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    EB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        return fail(EB200_ERR_UNSUPPORTED, "eb200_init: device %d is sm_%d%d; libeinsums_b200 carries sm_100a code only", device, prop.major,
+                    prop.minor);
+    }
+    EB_CUDA(cudaFree(nullptr)); // same context warm-up the reference does (GPUStreams.hip:60)
+    (void)sm_count();
+    return EB200_OK;
+}
+
+int eb200_finalize(void) {
+    // Unlike the reference (hipDeviceReset, GPUStreams.hip:134) we only drain: other libraries
+    // (torch, NCCL) may share the context.
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess && e != cudaErrorNoDevice) return cuda_fail(e, "cudaDeviceSynchronize");
+    return EB200_OK;
+}
+
+int eb200_stream_create(void **stream) {
+    if (!stream) return fail(EB200_ERR_INVALID_ARGUMENT, "eb200_stream_create: NULL");
+    cudaStream_t s;
+    EB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = (void *)s;
+    return EB200_OK;
+}
+int eb200_stream_destroy(void *stream) {
+    EB_CUDA(cudaStreamDestroy(as_stream(stream)));
+    return EB200_OK;
+}
+int eb200_stream_synchronize(void *stream) {
+    EB_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    return EB200_OK;
+}
+int eb200_device_synchronize(void) {
+    EB_CUDA(cudaDeviceSynchronize());
+    return EB200_OK;
+}
+
+int eb200_event_create(void **event) {
+    if (!event) return fail(EB200_ERR_INVALID_ARGUMENT, "eb200_event_create: NULL");
+    cudaEvent_t e;
+    EB_CUDA(cudaEventCreate(&e));
+    *event = (void *)e;
+    return EB200_OK;
+}
+int eb200_event_destroy(void *event) {
+    EB_CUDA(cudaEventDestroy((cudaEvent_t)event));
+    return EB200_OK;
+}
+int eb200_event_record(void *event, void *stream) {
+    EB_CUDA(cudaEventRecord((cudaEvent_t)event, as_stream(stream)));
+    return EB200_OK;
+}
+int eb200_event_synchronize(void *event) {
+    EB_CUDA(cudaEventSynchronize((cudaEvent_t)event));
+    return EB200_OK;
+}
+int eb200_event_elapsed_ms(void *start, void *stop, float *ms) {
+    if (!ms) return fail(EB200_ERR_INVALID_ARGUMENT, "eb200_event_elapsed_ms: NULL");
+    EB_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+    return EB200_OK;
+}
+
+int eb200_malloc(void **ptr, size_t bytes) {
+    if (!ptr) return fail(EB200_ERR_INVALID_ARGUMENT, "eb200_malloc: NULL");
+    *ptr = nullptr;
+    if (bytes == 0) return EB200_OK;
+    EB_CUDA(cudaMalloc(ptr, bytes));
+    return EB200_OK;
+}
+int eb200_free(void *ptr) {
+    if (!ptr) return EB200_OK;
+    EB_CUDA(cudaFree(ptr));
+    return EB200_OK;
+}
+int eb200_malloc_host(void **ptr, size_t bytes) {
+    if (!ptr) return fail(EB200_ERR_INVALID_ARGUMENT, "eb200_malloc_host: NULL");
+    *ptr = nullptr;
+    if (bytes == 0) return EB200_OK;
+    EB_CUDA(cudaMallocHost(ptr, bytes));
+    return EB200_OK;
+}
+int eb200_free_host(void *ptr) {
+    if (!ptr) return EB200_OK;
+    EB_CUDA(cudaFreeHost(ptr));
+    return EB200_OK;
+}
+int eb200_mem_get_info(size_t *free_bytes, size_t *total_bytes) {
+    size_t f = 0, t = 0;
+    EB_CUDA(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return EB200_OK;
+}
+
+int eb200_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream) {
+    if (bytes == 0) return EB200_OK;
+    EB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, as_stream(stream)));
+    EB_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    return EB200_OK;
+}
+int eb200_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream) {
+    if (bytes == 0) return EB200_OK;
+    EB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
+    EB_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    return EB200_OK;
+}
+int eb200_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream) {
+    if (bytes == 0) return EB200_OK;
+    EB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    return EB200_OK;
+}
+int eb200_memcpy_h2d_async(void *dst, const void *src, size_t bytes, void *stream) {
+    if (bytes == 0) return EB200_OK;
+    EB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, as_stream(stream)));
+    return EB200_OK;
+}
+int eb200_memcpy_d2h_async(void *dst, const void *src, size_t bytes, void *stream) {
+    if (bytes == 0) return EB200_OK;
+    EB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
+    return EB200_OK;
+}
+int eb200_memset_zero(void *dst, size_t bytes, void *stream) {
+    if (bytes == 0) return EB200_OK;
+    EB_CUDA(cudaMemsetAsync(dst, 0, bytes, as_stream(stream)));
+    return EB200_OK;
+}
+
+int64_t eb200_launch_count(void) { return launch_counter(); }
+void    eb200_launch_count_reset(void) { launch_counter() = 0; }
+
+} // extern "C"

@@ -1,0 +1,265 @@
+/*
+ * einsums_b200.h — C ABI of libeinsums_b200.so: the sm_100a device backend for Einsums'
+ * contraction hot path (einsum / permute / linear_algebra::{gemm,gemv,dot,ger,axpy,scal,
+ * direct_product} on DeviceTensor<T,Rank>).
+ *
+ * Every entry point replaces one function of the reference's "flat seam" (the closest thing
+ * Einsums has to an FFI), cited per declaration as file:line relative to the reference tree:
+ *   HBV  = libs/Einsums/hipBLASVendor
+ *   TA   = libs/Einsums/TensorAlgebra/include/Einsums/TensorAlgebra
+ *   T    = libs/Einsums/Tensor/include/Einsums/Tensor
+ *   GS   = libs/Einsums/GPUStreams
+ *
+ * Conventions (same as the reference's vendor layer unless stated):
+ *   - plain pointers and 64-bit sizes; no C++/torch types;
+ *   - BLAS-style entry points have Fortran (column-major) semantics on DEVICE pointers,
+ *     scalars are passed by pointer to HOST memory (read before return);
+ *   - complex numbers are interleaved (re,im) pairs: float[2] / double[2];
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream). Calls only
+ *     enqueue work; they do not synchronise unless documented ("host result");
+ *   - every function returns an eb200_status; on error eb200_last_error_string() (thread
+ *     local) describes it with the same wording class as the reference's exceptions;
+ *   - there is NO CPU fallback: without a usable CUDA device every compute call returns
+ *     EB200_ERR_NO_DEVICE / EB200_ERR_CUDA.
+ */
+#ifndef EINSUMS_B200_H
+#define EINSUMS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EB200_VERSION_MAJOR 0
+#define EB200_VERSION_MINOR 1
+#define EB200_MAX_RANK 12   /* max rank of one tensor in a contraction / permute          */
+#define EB200_MAX_UNIQUE 24 /* max number of distinct indices in one contraction          */
+
+typedef enum eb200_status {
+    EB200_OK = 0,
+    /* maps to std::invalid_argument in the C++ shim (HBV/src/gemm.hip:39-49, gemv.hip:27-33) */
+    EB200_ERR_INVALID_ARGUMENT = 1,
+    /* maps to std::domain_error (HBV/src/gemm.hip:51-80: negative sizes, too-small ld)       */
+    EB200_ERR_DOMAIN = 2,
+    /* maps to einsums::dimension_error (TA/Backends/Dispatch.hpp:125-127, DevicePermute.hpp:121-126) */
+    EB200_ERR_DIMENSION = 3,
+    /* maps to einsums::rank_error / tensor_compat_error                                        */
+    EB200_ERR_RANK = 4,
+    EB200_ERR_UNSUPPORTED = 5,
+    /* cudaErrorMemoryAllocation; maps to hip_exception<hipErrorOutOfMemory> (Errors/Error.hpp:1476-1500) */
+    EB200_ERR_OUT_OF_MEMORY = 6,
+    /* any other CUDA runtime error; eb200_last_cuda_error() returns the cudaError_t           */
+    EB200_ERR_CUDA = 7,
+    EB200_ERR_NO_DEVICE = 8,
+    EB200_ERR_NOT_INITIALIZED = 9
+} eb200_status;
+
+/* element types (value of eb200_contract_desc::dtype etc.) */
+typedef enum eb200_dtype { EB200_F32 = 0, EB200_F64 = 1, EB200_C64 = 2, EB200_C128 = 3 } eb200_dtype;
+
+/* AlgorithmChoice as reported by the reference's analyser (TA/Detail/Utilities.hpp:26-34).
+ * eb200_contract reports which device kernel family actually ran through
+ * eb200_contract_desc::kernel_used using the values below 100; */
+typedef enum eb200_algorithm {
+    EB200_ALG_GENERIC = 0,
+    EB200_ALG_DOT = 1,
+    EB200_ALG_DIRECT = 2,
+    EB200_ALG_GER = 3,
+    EB200_ALG_GEMV = 4,
+    EB200_ALG_GEMM = 5,
+    EB200_ALG_INDETERMINATE = 6
+} eb200_algorithm;
+
+/* device kernel families of the contraction engine (eb200_contract_desc::kernel_used) */
+typedef enum eb200_kernel_family {
+    EB200_KF_NONE = 0,        /* nothing launched (zero-size)                                  */
+    EB200_KF_TILE_MMA = 1,    /* tiled tensor-pipe kernel (FP64 DMMA) with fused index gathers */
+    EB200_KF_TILE_SIMT = 2,   /* tiled FMA kernel (f32 / complex) with fused index gathers     */
+    EB200_KF_ROWREDUCE = 3,   /* streaming reduction: few outputs per row of A (gemv-like)     */
+    EB200_KF_COLREDUCE = 4,   /* streaming reduction, target index contiguous in A (gemv-T)    */
+    EB200_KF_FULLREDUCE = 5,  /* dot-like: everything is contracted                             */
+    EB200_KF_ELEMENTWISE = 6, /* no contracted index: outer / direct / broadcast products      */
+    EB200_KF_SCALE_ONLY = 7   /* empty contraction space: C = beta*C only                       */
+} eb200_kernel_family;
+
+/* ------------------------------------------------------------------------------------------
+ * Runtime: replaces GS/src/GPUStreams.hip:58-136 (initialize/finalize), :145-166 (stream_wait),
+ * GS/include/Einsums/GPUStreams/GPUStreams.hpp:194-280 (get_stream & friends) and
+ * libs/Einsums/GPUMemory (GPUAllocator: hipMalloc under a budget).
+ * ---------------------------------------------------------------------------------------- */
+int eb200_version(void);
+/* Selects `device` for the calling thread, verifies it is sm_100, warms the context. */
+int eb200_init(int device);
+int eb200_finalize(void);
+int eb200_device_count(int *count);
+int eb200_set_device(int device);
+const char *eb200_last_error_string(void);
+int eb200_last_cuda_error(void);
+
+int eb200_stream_create(void **stream);
+int eb200_stream_destroy(void *stream);
+int eb200_stream_synchronize(void *stream); /* gpu::stream_wait()                              */
+int eb200_device_synchronize(void);         /* gpu::device_synchronize()                       */
+
+/* events, so that callers without the CUDA runtime can time on the launching stream */
+int eb200_event_create(void **event);
+int eb200_event_destroy(void *event);
+int eb200_event_record(void *event, void *stream);
+int eb200_event_synchronize(void *event);
+int eb200_event_elapsed_ms(void *start, void *stop, float *ms);
+
+/* T/Backends/DeviceTensor.hpp:62-116 (ctor: hipMalloc) and :33-60 (dtor) */
+int eb200_malloc(void **ptr, size_t bytes);
+int eb200_free(void *ptr);
+int eb200_malloc_host(void **ptr, size_t bytes); /* pinned host memory (PINNED mode)           */
+int eb200_free_host(void *ptr);
+int eb200_mem_get_info(size_t *free_bytes, size_t *total_bytes);
+/* contiguous copies; *_async variants only enqueue */
+int eb200_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int eb200_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int eb200_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
+int eb200_memcpy_h2d_async(void *dst, const void *src, size_t bytes, void *stream);
+int eb200_memcpy_d2h_async(void *dst, const void *src, size_t bytes, void *stream);
+int eb200_memset_zero(void *dst, size_t bytes, void *stream);
+
+/* Strided device->device copy with layout change: dst[sum i_k*dst_strides[k]] =
+ * src[sum i_k*src_strides[k]] over `dims` (element strides). Replaces the copy_to_tensor
+ * kernels of T/Backends/DeviceTensor.hpp:295-402 and DeviceTensorView.hpp:59 (view <- tensor,
+ * host column-major -> device row-major conversion after a raw upload).                     */
+int eb200_copy_strided(void *stream, int dtype, int rank, const int64_t *dims, const void *src,
+                       const int64_t *src_strides, void *dst, const int64_t *dst_strides);
+
+/* ------------------------------------------------------------------------------------------
+ * BLAS-like flat seam. Column-major, device pointers, 64-bit sizes.
+ * eb200_Xgemm replaces blas::hip::Xgemm            HBV/src/gemm.hip:82-154 (checks :23-80)
+ * eb200_Xgemv replaces blas::hip::Xgemv            HBV/src/gemv.hip:57-122 (checks :27-55)
+ * eb200_Xdot/Xdotc replaces blas::hip::Xdot(c)     HBV/src/dot.hip:24-118
+ * eb200_Xger/Xgerc replaces blas::hip::Xger(c)     HBV/src/ger.hip:46-122
+ * eb200_Xaxpy/axpby/scal/copy/lacgv                HBV/src/axpy.hip:22-100, scal.hip:25-70,
+ *                                                  copy.hip:24-49, lacgv.hip
+ * eb200_Xdirprod replaces blas::hip::Xdirprod      HBV/src/direct_prod.hip:202-270
+ * Early-return rules are the reference's: gemm returns at once if m, n or k is 0
+ * (gemm.hip:101-102), gemv if m or n is 0.
+ * ---------------------------------------------------------------------------------------- */
+#define EB200_DECL_BLAS(P, T)                                                                                   \
+    int eb200_##P##gemm(void *stream, char transa, char transb, int64_t m, int64_t n, int64_t k,              \
+                        const T *alpha, const T *A, int64_t lda, const T *B, int64_t ldb, const T *beta, T *C, \
+                        int64_t ldc);                                                                           \
+    int eb200_##P##gemm_strided_batched(void *stream, char transa, char transb, int64_t m, int64_t n,         \
+                                        int64_t k, const T *alpha, const T *A, int64_t lda, int64_t strideA,   \
+                                        const T *B, int64_t ldb, int64_t strideB, const T *beta, T *C,         \
+                                        int64_t ldc, int64_t strideC, int64_t batch);                          \
+    int eb200_##P##gemv(void *stream, char trans, int64_t m, int64_t n, const T *alpha, const T *A,           \
+                        int64_t lda, const T *x, int64_t incx, const T *beta, T *y, int64_t incy);             \
+    /* result written to HOST memory; synchronises the stream (reference: hipblasXdot + return) */             \
+    int eb200_##P##dot(void *stream, int64_t n, const T *x, int64_t incx, const T *y, int64_t incy,           \
+                       T *result_host);                                                                         \
+    /* result written to DEVICE memory; no synchronisation */                                                  \
+    int eb200_##P##dot_dev(void *stream, int64_t n, const T *x, int64_t incx, const T *y, int64_t incy,       \
+                           T *result_dev);                                                                      \
+    int eb200_##P##ger(void *stream, int64_t m, int64_t n, const T *alpha, const T *x, int64_t incx,          \
+                       const T *y, int64_t incy, T *A, int64_t lda);                                            \
+    int eb200_##P##axpy(void *stream, int64_t n, const T *alpha, const T *x, int64_t incx, T *y,              \
+                        int64_t incy);                                                                          \
+    int eb200_##P##axpby(void *stream, int64_t n, const T *alpha, const T *x, int64_t incx, const T *beta,    \
+                         T *y, int64_t incy);                                                                   \
+    int eb200_##P##scal(void *stream, int64_t n, const T *alpha, T *x, int64_t incx);                         \
+    int eb200_##P##copy(void *stream, int64_t n, const T *x, int64_t incx, T *y, int64_t incy);               \
+    int eb200_##P##fill(void *stream, int64_t n, const T *value, T *x, int64_t incx);                         \
+    /* z += alpha * x * y elementwise */                                                                       \
+    int eb200_##P##dirprod(void *stream, int64_t n, const T *alpha, const T *x, int64_t incx, const T *y,     \
+                           int64_t incy, T *z, int64_t incz);
+
+EB200_DECL_BLAS(s, float)
+EB200_DECL_BLAS(d, double)
+/* complex: T is the scalar component type; all counts are in complex elements */
+EB200_DECL_BLAS(c, float)
+EB200_DECL_BLAS(z, double)
+#undef EB200_DECL_BLAS
+
+/* conjugated variants (complex only): x^H y, A += alpha x y^H, x = conj(x) */
+int eb200_cdotc(void *stream, int64_t n, const float *x, int64_t incx, const float *y, int64_t incy, float *result_host);
+int eb200_zdotc(void *stream, int64_t n, const double *x, int64_t incx, const double *y, int64_t incy, double *result_host);
+int eb200_cgerc(void *stream, int64_t m, int64_t n, const float *alpha, const float *x, int64_t incx, const float *y,
+                int64_t incy, float *A, int64_t lda);
+int eb200_zgerc(void *stream, int64_t m, int64_t n, const double *alpha, const double *x, int64_t incx,
+                const double *y, int64_t incy, double *A, int64_t lda);
+int eb200_clacgv(void *stream, int64_t n, float *x, int64_t incx);
+int eb200_zlacgv(void *stream, int64_t n, double *x, int64_t incx);
+
+/* ------------------------------------------------------------------------------------------
+ * permute: C[perm] = beta*C + alpha*A.  Replaces tensor_algebra::detail::gpu_permute
+ * (TA/Backends/DevicePermute.hpp:25-32 -> LibreTT) and permute_kernel (:34-73).
+ *   rank        number of axes (<= EB200_MAX_RANK)
+ *   dimsA[i]    extent of axis i of A
+ *   stridesA[i] element stride of axis i of A
+ *   perm[i]     axis of A that axis i of C enumerates   (C.dim(i) >= A.dim(perm[i]))
+ *   stridesC[i] element stride of axis i of C
+ *   conj        non-zero: conjugate A (complex types)
+ * beta == 0 overwrites C without reading it (TA/Permute.hpp:377-385).
+ * ---------------------------------------------------------------------------------------- */
+int eb200_spermute(void *stream, int rank, const int64_t *dimsA, const int64_t *stridesA, const int *perm,
+                   const int64_t *stridesC, const float *alpha, const float *A, const float *beta, float *C, int conj);
+int eb200_dpermute(void *stream, int rank, const int64_t *dimsA, const int64_t *stridesA, const int *perm,
+                   const int64_t *stridesC, const double *alpha, const double *A, const double *beta, double *C,
+                   int conj);
+int eb200_cpermute(void *stream, int rank, const int64_t *dimsA, const int64_t *stridesA, const int *perm,
+                   const int64_t *stridesC, const float *alpha, const float *A, const float *beta, float *C, int conj);
+int eb200_zpermute(void *stream, int rank, const int64_t *dimsA, const int64_t *stridesA, const int *perm,
+                   const int64_t *stridesC, const double *alpha, const double *A, const double *beta, double *C,
+                   int conj);
+
+/* ------------------------------------------------------------------------------------------
+ * Generic contraction  C[c...] = beta*C[c...] + alpha * sum_{links} op(A[a...]) * op(B[b...])
+ * Replaces the device einsum_generic_algorithm + its three kernels
+ * (TA/Backends/GPUTensorAlgebra.hpp:28-342). The descriptor is exactly what that launcher
+ * builds on the host: the list of unique indices (order: C's, then A's, then B's first
+ * occurrences — UniqueT<C...,A...,B...>, :225), one extent per unique index resolved
+ * C -> A -> B (get_dim_ranges_for_many, TensorBase/IndexUtilities.hpp:24-120), and per tensor
+ * the compile_index_table output (position in the unique list of each axis) plus strides.
+ * Semantics = the reference device kernel: sum over the FULL unique-index space; an index
+ * repeated inside one tensor (Hadamard) walks the diagonal; an index that appears only in C
+ * broadcasts; beta == 0 zero-fills first (never reads C).
+ * The index permutation is fused into the operand loads: no transposed copy is ever made.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct eb200_tensor_desc {
+    void *data;                            /* device pointer (element 0)                        */
+    int32_t dtype;                         /* eb200_dtype                                       */
+    int32_t rank;                          /* 0 for a scalar                                    */
+    int32_t index[EB200_MAX_RANK];         /* position of axis i in the unique-index list       */
+    int64_t stride[EB200_MAX_RANK];        /* element stride of axis i                          */
+} eb200_tensor_desc;
+
+typedef struct eb200_contract_desc {
+    int32_t n_unique;
+    int32_t conj_a, conj_b;
+    int64_t extent[EB200_MAX_UNIQUE];      /* extent of each unique index                       */
+    eb200_tensor_desc C, A, B;
+    /* prefactors, as (re, im); im ignored for real C. Interpreted in C's type.                */
+    double alpha[2];
+    double beta[2];
+    /* tuning / testing knobs: 0 = automatic */
+    int32_t force_kernel;                  /* eb200_kernel_family to force (testing), 0 = auto  */
+    int32_t split_k;                       /* 0 = auto                                          */
+    /* outputs */
+    int32_t kernel_used;                   /* eb200_kernel_family that ran                      */
+    int32_t launches;                      /* number of kernels enqueued                        */
+} eb200_contract_desc;
+
+int eb200_contract(void *stream, eb200_contract_desc *desc);
+
+/* Host-side only (no device needed): classification the engine would pick for this
+ * descriptor, written to desc->kernel_used. Lets CPU tests pin the planner. */
+int eb200_contract_plan(eb200_contract_desc *desc);
+
+/* Number of kernel launches enqueued by this thread through this library since the last
+ * eb200_launch_count_reset(); bench.py reports it as "gpu_launches". */
+int64_t eb200_launch_count(void);
+void eb200_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EINSUMS_B200_H */
