@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the contraction hot path (contract: see the task brief §④).
+
+Workload (BASELINE.json configs[1]): CCD W intermediates, o=20, v=200, FP64, one step =
+    Wmnij[m,n,i,j] = 1.0*Wmnij + 0.25 * sum_ef g[m,n,e,f] t[i,j,e,f]      (M=N=400,   K=40000, split-K)
+    Wabef[a,b,e,f] = 1.0*Wabef + 0.25 * sum_mn g[m,n,e,f] t[m,n,a,b]      (M=N=40000, K=400, C = 12.8 GB)
+both through the C ABI (eb200_contract -> tile_mma_f64). flops/step = 2*o^4*v^2 + 2*v^4*o^2 = 1.2928e12.
+
+N > 1 (torchrun, one rank per GPU): the `a` index of Wabef is sharded — rank r owns the slab a in [r*v,(r+1)*v) of a
+W with N*v values of `a` (per-GPU work fixed => weak scaling); no collective on the data path.
+
+--impl reference : the reference's CPU path (oracle port: analyser + OpenBLAS dgemm, all host threads) on the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+O, V = 20, 200
+FLOPS_WMNIJ = 2.0 * O**4 * V**2
+FLOPS_WABEF = 2.0 * V**4 * O**2
+FLOPS_STEP = FLOPS_WMNIJ + FLOPS_WABEF
+NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 37.2: 64 FP64 FMA/clk/SM at clocks.max.sm
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-v", type=int, default=0, help="v for the CPU sample (0 = full config)")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+def fp64_peak():
+    """FP64 tensor-pipe (DMMA) peak measured on this GPU by tools/fp64_peaks; MEASURED_PEAKS.json holds no FP64 figure."""
+    exe = os.path.join(ROOT, "tools", "fp64_peaks")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("LOCAL_RANK", "0")
+                                                                                       if "CUDA_VISIBLE_DEVICES" not in os.environ else os.environ["CUDA_VISIBLE_DEVICES"]))
+        j = json.loads(out.stdout.strip().splitlines()[-1])
+        return float(j["dmma_tflops"]), "measured in this run by tools/fp64_peaks (DMMA.8x8x4 issue-bound loop)", j
+    except Exception as e:  # noqa: BLE001
+        return NOMINAL_FP64_TFLOPS, f"fallback: nominal 148 SM x 64 FMA/clk x 1.965 GHz ({type(e).__name__})", None
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference(steps, warmup, v_sample=0, threads=None):
+    import numpy as np
+    from oracle import binding as orc
+    info = orc.load_openblas()
+    ncores = os.cpu_count() or 1
+    threads = threads or ncores
+    orc.lib().orc_blas_set_threads(threads)
+    o, v = O, (v_sample or V)
+    rng = np.random.default_rng(20251017 + 2)
+    g = rng.uniform(-1, 1, (o, o, v, v))
+    t = rng.uniform(-1, 1, (o, o, v, v))
+    Wm = rng.uniform(-1, 1, (o, o, o, o))
+    Wa = rng.uniform(-1, 1, (v, v, v, v))
+    flops = 2.0 * o**4 * v**2 + 2.0 * v**4 * o**2
+
+    def step():
+        a1 = orc.einsum_f64("mnij", Wm, "mnef", g, "ijef", t, 0.25, 1.0)
+        a2 = orc.einsum_f64("abef", Wa, "mnef", g, "mnab", t, 0.25, 1.0)
+        assert a1 == "GEMM" and a2 == "GEMM", (a1, a2)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": flops / dt / 1e12, "unit": "TFLOP/s", "cores": threads, "kind": "port",
+            "sample": (f"full config o={o} v={v}" if v == V else f"reduced sample o={o} v={v} (same two einsums)") +
+                      f", {steps} steps after {warmup} warm-up; oracle analyser -> {info}", "ms_per_step": dt * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    cb = cpu_reference(steps, warm, args.cpu_sample_v)
+    line = {
+        "impl": "reference", "metric": "FP64 einsum TFLOP/s", "value": cb["value"], "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic uniform[-1,1), seeded", "config": {"workload": f"CCD Wmnij+Wabef o={O} v={V} FP64 (BASELINE configs[1])", "o": O, "v": V},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from einsums_b200 import KF, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the backend has no CPU fallback"
+    torch.cuda.set_device(local)
+    ops.init(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    o, v = O, V
+    gen = torch.Generator(device="cuda").manual_seed(20251017 + 2 + rank)
+    rnd = lambda *s: torch.rand(*s, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+    g, t = rnd(o, o, v, v), rnd(o, o, v, v)        # g_oovv replicated; t = this rank's a-slab t[m,n,a_r,b]
+    Wm, Wa = rnd(o, o, o, o), rnd(v, v, v, v)      # Wabef slab of this rank: a in [rank*v, (rank+1)*v)
+    stream = torch.cuda.current_stream()
+
+    kinds = {}
+
+    def step(ev=None):
+        d1 = ops.contract("mnij", Wm, "mnef", g, "ijef", t, 0.25, 1.0)
+        if ev is not None:
+            ev[0].record(stream)
+        d2 = ops.contract("abef", Wa, "mnef", g, "mnab", t, 0.25, 1.0)
+        if ev is not None:
+            ev[1].record(stream)
+        kinds["wmnij"], kinds["wabef"] = d1, d2
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    K = args.steps
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mids = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    ops.launch_count_reset()
+    barrier()
+    e0.record(stream)
+    for i in range(K):
+        step(mids[i])
+    e1.record(stream)
+    barrier()
+    launches = ops.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    ms_wabef = sum(m[0].elapsed_time(m[1]) for m in mids) / K
+    tms = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_step = tms.item() / K
+    value = world * FLOPS_STEP / (ms_step * 1e-3) / 1e12
+
+    # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        hg, ht = g.cpu().pin_memory(), t.cpu().pin_memory()
+        hWm, hWa = Wm.cpu().pin_memory(), Wa.cpu().pin_memory()
+        oWm, oWa = torch.empty_like(hWm).pin_memory(), torch.empty_like(hWa).pin_memory()
+        h2d = sum(x.numel() * 8 for x in (hg, ht, hWm, hWa))
+        d2h = sum(x.numel() * 8 for x in (oWm, oWa))
+
+        def e2e_step():
+            g.copy_(hg, non_blocking=True); t.copy_(ht, non_blocking=True)
+            Wm.copy_(hWm, non_blocking=True); Wa.copy_(hWa, non_blocking=True)
+            step()
+            oWm.copy_(Wm, non_blocking=True); oWa.copy_(Wa, non_blocking=True)
+
+        e2e_step(); barrier()
+        ke = max(1, min(K, 3))
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(ke):
+            e2e_step()
+        a1.record(stream)
+        barrier()
+        te = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * FLOPS_STEP / (te.item() / ke * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": te.item() / ke, "steps": ke,
+               "note": "host (pinned) -> device copies of g,t,Wmnij,Wabef, both einsums, device -> host copy of both results, per step"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src, peak_json = fp64_peak()
+    achieved = FLOPS_WABEF / (ms_wabef * 1e-3) / 1e12
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("tile_mma_f64_wabef_dram_bytes")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": "FP64 einsum TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic uniform[-1,1), seeded on device",
+        "config": {"workload": f"CCD Wmnij+Wabef o={O} v={V} FP64 (BASELINE configs[1])", "o": O, "v": V,
+                   "flops_per_step_per_gpu": FLOPS_STEP, "l2": "per-step traffic (25.9 GB) exceeds the 126 MB L2; no flush needed",
+                   "sharding": "none" if world == 1 else f"a-index of Wabef sharded over {world} ranks, no collective"},
+        "roofline": {"bound": "tensor", "kernel": "tile_mma_f64 (Wabef, M=N=40000 K=400)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "ms_per_launch": ms_wabef,
+                     "algorithmic_flops_per_launch": FLOPS_WABEF},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "kernels": {k: {"family": int(d.kernel_used), "split_k": int(d.split_k), "launches": int(d.launches)} for k, d in kinds.items()},
+    }
+    if peak_json:
+        line["fp64_peaks"] = peak_json
+    if not args.no_cpu_baseline and world == 1:
+        del Wa
+        torch.cuda.empty_cache()
+        cb = cpu_reference(2, 1, args.cpu_sample_v)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -25,6 +25,18 @@ template <typename K> int set_smem(K kernel, size_t bytes) {
 
 // stream-ordered scratch for split partials: no synchronisation, freed after the finalize kernel
 int ws_alloc(void **p, size_t bytes, cudaStream_t s) {
+    // keep freed scratch in the pool across synchronisations (the default threshold of 0 hands it back to the
+    // driver at every sync, which costs ~1 ms per split-K call)
+    static thread_local int pool_dev = -1;
+    int                     dev = 0;
+    EB_CUDA(cudaGetDevice(&dev));
+    if (pool_dev != dev) {
+        cudaMemPool_t pool;
+        EB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = UINT64_MAX;
+        EB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        pool_dev = dev;
+    }
     EB_CUDA(cudaMallocAsync(p, bytes, s));
     return EB200_OK;
 }
@@ -61,13 +73,13 @@ int launch_finalize(cudaStream_t s, const Grp &gb, const Grp &gm, const Grp &gn,
 // ---------------------------------------------------------------- tile kernels
 struct TileChoice { int bm, bn, bk, per_sm; };
 
-template <int BM, int BN, int BK, int WM, int WN, int STAGES, int MINB>
-int launch_mma_cfg(cudaStream_t s, TileArgs &args, dim3 grid) {
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, int MINB, bool VEC>
+int launch_mma_vec(cudaStream_t s, TileArgs &args, dim3 grid) {
     const bool ak = args.p.a_kmajor, bk = args.p.b_kmajor;
 #define EB_MMA_CASE(AK, BKM)                                                                          \
     {                                                                                                 \
         using Cfg = TileCfg<BM, BN, BK, WM, WN, STAGES, AK, BKM>;                                     \
-        auto kern = tile_mma_f64<BM, BN, BK, WM, WN, STAGES, AK, BKM, MINB>;                          \
+        auto kern = tile_mma_f64<BM, BN, BK, WM, WN, STAGES, AK, BKM, MINB, VEC>;                     \
         int  rc = set_smem(kern, Cfg::SMEM);                                                          \
         if (rc) return rc;                                                                            \
         kern<<<grid, Cfg::NT, Cfg::SMEM, s>>>(args);                                                  \
@@ -79,6 +91,25 @@ int launch_mma_cfg(cudaStream_t s, TileArgs &args, dim3 grid) {
 #undef EB_MMA_CASE
     EB_POST_LAUNCH("tile_mma_f64");
     return EB200_OK;
+}
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, int MINB>
+int launch_mma_cfg(cudaStream_t s, TileArgs &args, dim3 grid) {
+    if (args.vec_ab) return launch_mma_vec<BM, BN, BK, WM, WN, STAGES, MINB, true>(s, args, grid);
+    return launch_mma_vec<BM, BN, BK, WM, WN, STAGES, MINB, false>(s, args, grid);
+}
+
+inline bool even(int64_t x) { return (x & 1) == 0; }
+// every stride of `role` in group g is even, except index `skip` (-1: none)
+bool strides_even(const Grp &g, int role, int skip) {
+    for (int i = 0; i < g.n; i++)
+        if (i != skip && !even(g.s[role][i])) return false;
+    return true;
+}
+// operand `role` can be fetched as aligned pairs along the inner index of `fast`
+bool operand_pairs_ok(const Plan &p, int role, const Grp &fast, const Grp &other, const void *base) {
+    if (fast.n == 0 || fast.s[role][0] != 1 || !even(fast.ext[0])) return false;
+    if (!strides_even(fast, role, 0) || !strides_even(other, role, -1) || !strides_even(p.b, role, -1)) return false;
+    return ((uintptr_t)base % 16) == 0;
 }
 
 int g_mma_config = 0; // 0 = auto; 1 = 128x128 (1 CTA/SM); 2 = 128x64 (2 CTA/SM). Tuning hook (EB200_MMA_CONFIG).
@@ -108,6 +139,7 @@ template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract
     args.alpha[0] = d.alpha[0]; args.alpha[1] = d.alpha[1];
     args.beta[0] = beta_eff[0]; args.beta[1] = beta_eff[1];
     args.conj_a = d.conj_a; args.conj_b = d.conj_b;
+    args.vec_ab = 0; args.vec_c = 0;
 
     const bool mma = (p.family == EB200_KF_TILE_MMA);
     int bm, bn, bk, ctas_per_sm;
@@ -117,9 +149,12 @@ template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract
     });
     int cfg = 0;
     if (mma) {
-        cfg = g_mma_config ? g_mma_config : 1;
-        if (cfg == 2) { bm = 128; bn = 64; bk = 16; ctas_per_sm = 2; }
-        else { cfg = 1; bm = 128; bn = 128; bk = 16; ctas_per_sm = 1; }
+        cfg = g_mma_config ? g_mma_config : 2;
+        if (cfg == 1) { bm = 128; bn = 128; bk = 16; ctas_per_sm = 1; }
+        else { cfg = 2; bm = 128; bn = 64; bk = 16; ctas_per_sm = 2; }
+        args.vec_ab = operand_pairs_ok(p, ROLE_A, p.a_kmajor ? p.k : p.m, p.a_kmajor ? p.m : p.k, args.A) &&
+                      operand_pairs_ok(p, ROLE_B, p.b_kmajor ? p.k : p.n, p.b_kmajor ? p.n : p.k, args.B);
+        args.vec_c = operand_pairs_ok(p, ROLE_C, p.n, p.m, args.C);
     } else { bm = 64; bn = 64; bk = 8; ctas_per_sm = 4; }
 
     const int64_t tm = (p.m.tot + bm - 1) / bm, tn = (p.n.tot + bn - 1) / bn;
@@ -154,8 +189,8 @@ template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract
     int  rc;
     if (mma) {
         if constexpr (std::is_same_v<T, double>) {
-            if (cfg == 2) rc = launch_mma_cfg<128, 64, 16, 32, 32, 3, 2>(s, args, grid);
-            else rc = launch_mma_cfg<128, 128, 16, 64, 32, 4, 1>(s, args, grid);
+            if (cfg == 1) rc = launch_mma_cfg<128, 128, 16, 64, 32, 4, 1>(s, args, grid);
+            else rc = launch_mma_cfg<128, 64, 16, 32, 32, 3, 2>(s, args, grid);
         } else {
             rc = fail(EB200_ERR_UNSUPPORTED, "tile_mma is FP64 only");
         }
@@ -173,9 +208,33 @@ template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract
 }
 
 // ---------------------------------------------------------------- streaming reductions
+// 0: flat kernel; 1: segmented, scalar loads; 2: segmented, 16-byte pairs
+template <typename T> int reduce_seg_mode(const ReduceArgs &a) {
+    if (a.k.n == 0 || a.k.ext[0] < 32) return 0;
+    if (sizeof(T) > 8 || a.k.s[ROLE_A][0] != 1 || a.k.s[ROLE_B][0] != 1 || (a.k.ext[0] & 1)) return 1;
+    auto all_even = [](const Grp &g, int role, int skip) {
+        for (int i = 0; i < g.n; i++)
+            if (i != skip && (g.s[role][i] & 1)) return false;
+        return true;
+    };
+    if (!all_even(a.k, ROLE_A, 0) || !all_even(a.k, ROLE_B, 0) || !all_even(a.rows, ROLE_A, -1) || !all_even(a.rows, ROLE_B, -1) ||
+        !all_even(a.n, ROLE_B, -1))
+        return 1;
+    constexpr uintptr_t AL = 2 * sizeof(T);
+    if ((uintptr_t)a.A % AL || (uintptr_t)a.B % AL) return 1;
+    return 2;
+}
+
 template <typename T, int NN, bool CA, bool CB> int launch_reduce_nn(cudaStream_t s, bool row, ReduceArgs &a, dim3 grid) {
     if (row) {
-        row_reduce<T, NN, 4, CA, CB><<<grid, 256, 0, s>>>(a);
+        int mode = reduce_seg_mode<T>(a);
+        if (mode == 2) {
+            if constexpr (sizeof(T) <= 8) row_reduce_seg<T, NN, 4, 2, CA, CB><<<grid, 256, 0, s>>>(a);
+        } else if (mode == 1) {
+            row_reduce_seg<T, NN, 4, 1, CA, CB><<<grid, 256, 0, s>>>(a);
+        } else {
+            row_reduce<T, NN, 4, CA, CB><<<grid, 256, 0, s>>>(a);
+        }
         EB_POST_LAUNCH("row_reduce");
     } else {
         col_reduce<T, NN, 2, CA, CB><<<grid, 256, 0, s>>>(a);
@@ -220,7 +279,7 @@ template <typename T> int run_reduce(cudaStream_t s, const Plan &p, eb200_contra
     if (d.split_k > 0) splits = d.split_k;
     else {
         const int64_t target = (int64_t)sm_count() * 8;
-        const int64_t min_k_per_split = row ? 4096 : 64;
+        const int64_t min_k_per_split = row ? 8192 : 64;
         if (row_blocks < target) splits = (int)std::min<int64_t>((target + row_blocks - 1) / row_blocks, std::max<int64_t>(1, K / min_k_per_split));
     }
     splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(splits, K), 65535));

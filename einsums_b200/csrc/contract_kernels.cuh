@@ -43,7 +43,14 @@ struct TileArgs {
     int32_t       splits;    // >= 1
     int32_t       tiles_m, tiles_n;
     int32_t       conj_a, conj_b;
+    int32_t       vec_ab;    // A and B tiles can be fetched as aligned 16-byte pairs along their fast direction
+    int32_t       vec_c;     // C pairs (n, n+1) are adjacent and 16-byte aligned
 };
+
+// 16-byte async copy global->shared (L2 only); src_bytes == 0 zero-fills
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes));
+}
 
 // ------------------------------------------------------------------------------------------
 // FP64 tensor-pipe tile kernel
@@ -60,7 +67,7 @@ template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool A_KMAJOR, boo
     static constexpr size_t SMEM = (size_t)STAGES * (A_ELEMS + B_ELEMS) * 8 + (size_t)(2 * BM + 2 * BN) * 8 + (size_t)RING * BK * 2 * 8;
 };
 
-template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool A_KMAJOR, bool B_KMAJOR, int MINB>
+template <int BM, int BN, int BK, int WM, int WN, int STAGES, bool A_KMAJOR, bool B_KMAJOR, int MINB, bool VEC>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) tile_mma_f64(const __grid_constant__ TileArgs args) {
     using Cfg = TileCfg<BM, BN, BK, WM, WN, STAGES, A_KMAJOR, B_KMAJOR>;
     constexpr int NT = Cfg::NT;
@@ -129,31 +136,52 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) tile_mma_f64
         for (int s = 0; s < STAGES && s < nsteps; s++) compute_koff(s);
     __syncthreads();
 
-    auto load_stage = [&](int step /*local*/) {
+    // The stage loader is cut into BK/4 parts so that it can be interleaved with the k4 sub-steps of the
+    // MMA loop (keeps the tensor pipe fed while addresses are generated). part < 0 issues everything.
+    constexpr int NPART = BK / 4;
+    constexpr int A_OPS = VEC ? BM * BK / 2 / NT : BM * BK / NT;
+    constexpr int B_OPS = VEC ? BN * BK / 2 / NT : BN * BK / NT;
+    static_assert(A_OPS >= 1 && B_OPS >= 1, "tile too small for the thread count");
+    auto load_part = [&](int step /*local*/, int part) {
         const int      buf  = step % STAGES;
         const int      slot = step % Cfg::RING;
         const uint32_t as = smem_u32(As + buf * Cfg::A_ELEMS), bs = smem_u32(Bs + buf * Cfg::B_ELEMS);
 #pragma unroll
-        for (int j = 0; j < BM * BK / NT; j++) {
+        for (int j = 0; j < A_OPS; j++) {
+            if (part >= 0 && (j % NPART) != part) continue;
             int e = tid + j * NT, ml, kl;
-            if constexpr (A_KMAJOR) { kl = e % BK; ml = e / BK; }
-            else { ml = e % BM; kl = e / BM; }
+            if constexpr (VEC) {
+                if constexpr (A_KMAJOR) { kl = 2 * (e % (BK / 2)); ml = e / (BK / 2); }
+                else { ml = 2 * (e % (BM / 2)); kl = e / (BM / 2); }
+            } else {
+                if constexpr (A_KMAJOR) { kl = e % BK; ml = e / BK; }
+                else { ml = e % BM; kl = e / BM; }
+            }
             int64_t  om = moffA[ml], ok = koffA[slot * BK + kl];
             bool     v = (om != OFF_INVALID) && (ok != OFF_INVALID);
             uint32_t dst = as + 8u * (A_KMAJOR ? ml * Cfg::A_PITCH + kl : kl * Cfg::A_PITCH + ml);
-            cp_async8(dst, v ? (const void *)(A + om + ok) : (const void *)A, v ? 8 : 0);
+            if constexpr (VEC) cp_async16(dst, v ? (const void *)(A + om + ok) : (const void *)A, v ? 16 : 0);
+            else cp_async8(dst, v ? (const void *)(A + om + ok) : (const void *)A, v ? 8 : 0);
         }
 #pragma unroll
-        for (int j = 0; j < BN * BK / NT; j++) {
+        for (int j = 0; j < B_OPS; j++) {
+            if (part >= 0 && (j % NPART) != part) continue;
             int e = tid + j * NT, nl, kl;
-            if constexpr (B_KMAJOR) { kl = e % BK; nl = e / BK; }
-            else { nl = e % BN; kl = e / BN; }
+            if constexpr (VEC) {
+                if constexpr (B_KMAJOR) { kl = 2 * (e % (BK / 2)); nl = e / (BK / 2); }
+                else { nl = 2 * (e % (BN / 2)); kl = e / (BN / 2); }
+            } else {
+                if constexpr (B_KMAJOR) { kl = e % BK; nl = e / BK; }
+                else { nl = e % BN; kl = e / BN; }
+            }
             int64_t  on = noffB[nl], ok = koffB[slot * BK + kl];
             bool     v = (on != OFF_INVALID) && (ok != OFF_INVALID);
             uint32_t dst = bs + 8u * (B_KMAJOR ? nl * Cfg::B_PITCH + kl : kl * Cfg::B_PITCH + nl);
-            cp_async8(dst, v ? (const void *)(B + on + ok) : (const void *)B, v ? 8 : 0);
+            if constexpr (VEC) cp_async16(dst, v ? (const void *)(B + on + ok) : (const void *)B, v ? 16 : 0);
+            else cp_async8(dst, v ? (const void *)(B + on + ok) : (const void *)B, v ? 8 : 0);
         }
     };
+    auto load_stage = [&](int step) { load_part(step, -1); };
 
     double acc[FM][FN][2];
 #pragma unroll
@@ -171,8 +199,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) tile_mma_f64
     for (int it = 0; it < nsteps; it++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        if (it + STAGES - 1 < nsteps) load_stage(it + STAGES - 1);
-        cp_async_commit();
+        const bool prefetch = it + STAGES - 1 < nsteps;
         if (tid < BK && it + STAGES < nsteps) compute_koff(it + STAGES);
 
         const double *a_s = As + (it % STAGES) * Cfg::A_ELEMS;
@@ -190,11 +217,14 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) tile_mma_f64
                 int n = wn0 + 8 * j + fr, k = kk + fk;
                 b[j] = b_s[B_KMAJOR ? n * Cfg::B_PITCH + k : k * Cfg::B_PITCH + n];
             }
+            // one slice of next stage's copies is issued while the fragment loads are in flight
+            if (prefetch) load_part(it + STAGES - 1, kk / 4);
 #pragma unroll
             for (int i = 0; i < FM; i++)
 #pragma unroll
                 for (int j = 0; j < FN; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
+        cp_async_commit();
     }
     cp_async_wait<0>();
 
@@ -203,20 +233,51 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) tile_mma_f64
         double      *C = reinterpret_cast<double *>(args.C) + baseC;
         const double alpha = args.alpha[0], beta = args.beta[0];
         const bool   has_beta = beta != 0.0;
+        // two passes over the fragment rows; inside a pass every C load is issued before the first use
+        constexpr int HM = (FM + 1) / 2;
 #pragma unroll
-        for (int i = 0; i < FM; i++) {
-            int64_t om = moffC[wm0 + 8 * i + fr];
-            if (om == OFF_INVALID) continue;
+        for (int h = 0; h < FM; h += HM) {
+            double  cold[HM][FN][2];
+            int64_t offs[HM][FN];
 #pragma unroll
-            for (int j = 0; j < FN; j++) {
+            for (int ii = 0; ii < HM; ii++) {
+                const int     i = h + ii;
+                const int64_t om = (i < FM) ? moffC[wm0 + 8 * i + fr] : OFF_INVALID;
 #pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    int64_t on = noffC[wn0 + 8 * j + 2 * fk + c];
-                    if (on == OFF_INVALID) continue;
-                    double *dst = C + om + on;
-                    double  v = alpha * acc[i][j][c];
-                    if (has_beta) v = fma(beta, *dst, v);
-                    *dst = v;
+                for (int j = 0; j < FN; j++) {
+                    const int64_t on0 = noffC[wn0 + 8 * j + 2 * fk], on1 = noffC[wn0 + 8 * j + 2 * fk + 1];
+                    cold[ii][j][0] = cold[ii][j][1] = 0.0;
+                    if (args.vec_c) {
+                        offs[ii][j] = (om != OFF_INVALID && on0 != OFF_INVALID) ? om + on0 : OFF_INVALID;
+                        if (has_beta && offs[ii][j] != OFF_INVALID) {
+                            double2 v = *reinterpret_cast<const double2 *>(C + offs[ii][j]);
+                            cold[ii][j][0] = v.x; cold[ii][j][1] = v.y;
+                        }
+                    } else {
+                        offs[ii][j] = om; // row offset; columns looked up again below
+                        if (has_beta && om != OFF_INVALID) {
+                            if (on0 != OFF_INVALID) cold[ii][j][0] = C[om + on0];
+                            if (on1 != OFF_INVALID) cold[ii][j][1] = C[om + on1];
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int ii = 0; ii < HM; ii++) {
+                const int i = h + ii;
+                if (i >= FM) continue;
+#pragma unroll
+                for (int j = 0; j < FN; j++) {
+                    if (offs[ii][j] == OFF_INVALID) continue;
+                    double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
+                    if (has_beta) { v0 = fma(beta, cold[ii][j][0], v0); v1 = fma(beta, cold[ii][j][1], v1); }
+                    if (args.vec_c) {
+                        *reinterpret_cast<double2 *>(C + offs[ii][j]) = make_double2(v0, v1);
+                    } else {
+                        const int64_t on0 = noffC[wn0 + 8 * j + 2 * fk], on1 = noffC[wn0 + 8 * j + 2 * fk + 1];
+                        if (on0 != OFF_INVALID) C[offs[ii][j] + on0] = v0;
+                        if (on1 != OFF_INVALID) C[offs[ii][j] + on1] = v1;
+                    }
                 }
             }
         }
@@ -475,6 +536,133 @@ __global__ void __launch_bounds__(256) row_reduce(const __grid_constant__ Reduce
     }
     (void)lane;
     // block reduction, fixed order
+#pragma unroll
+    for (int j = 0; j < RB; j++)
+#pragma unroll
+        for (int c = 0; c < NN; c++) {
+            T v = warp_sum(acc[j][c]);
+            if (lane == 0) red[warp][j * NN + c] = v;
+        }
+    __syncthreads();
+    if (tid < RB * NN) {
+        int     j = tid / NN, c = tid % NN;
+        int64_t r = r0 + j;
+        if (r < R && c < ncols) {
+            T s = zero_of<T>();
+#pragma unroll
+            for (int w = 0; w < NW; w++) s = add_(s, red[w][tid]);
+            if (a.splits == 1) {
+                const T    alpha = make_scalar<T>(a.alpha[0], a.alpha[1]), beta = make_scalar<T>(a.beta[0], a.beta[1]);
+                const bool has_beta = !is_zero(beta);
+                T         *dst = reinterpret_cast<T *>(a.C) + grp_offset(a.rows, r, ROLE_C) + grp_offset(a.n, c, ROLE_C);
+                *dst = axpby_(alpha, s, beta, has_beta ? *dst : zero_of<T>(), has_beta);
+            } else {
+                reinterpret_cast<T *>(a.ws)[((int64_t)split * R + r) * ncols + c] = s;
+            }
+        }
+    }
+}
+
+// row_reduce_seg: the bandwidth path for contractions whose contracted direction is contiguous in A
+// (gemv, Fock J/K, dot). The K space is seen as (outer composite ko) x (inner index ki of extent E0,
+// unit stride in A). A work unit = one run of 32*VEC consecutive ki for one ko; a warp decodes ko once
+// per unit (no per-element division), lanes stream A with VEC*sizeof(T)-byte loads for RB rows at a
+// time and reuse each B value RB times. Units are split over blockIdx.y; partial sums are combined
+// in a fixed order (deterministic).
+template <typename T, int NN, int RB, int VEC, bool CONJ_A, bool CONJ_B>
+__global__ void __launch_bounds__(256, (NN * RB * sizeof(T) <= 64 ? 3 : 1)) row_reduce_seg(const __grid_constant__ ReduceArgs a) {
+    constexpr int NT = 256, NW = NT / 32;
+    __shared__ T  red[NW][RB * NN];
+    const int     tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t R = a.rows.tot;
+    const int     ncols = (int)a.n.tot;
+    const int64_t r0 = (int64_t)blockIdx.x * RB;
+    const int     split = blockIdx.y;
+    const T      *A = reinterpret_cast<const T *>(a.A);
+    const T      *B = reinterpret_cast<const T *>(a.B);
+
+    const int64_t E0 = a.k.ext[0], sA0 = a.k.s[ROLE_A][0], sB0 = a.k.s[ROLE_B][0];
+    const int64_t KO = a.k.tot / E0;
+    constexpr int CH = 32 * VEC;
+    const int64_t chunks = (E0 + CH - 1) / CH;
+    const int64_t units = KO * chunks;
+    const int64_t u_begin = units * split / a.splits, u_end = units * (split + 1) / a.splits;
+
+    int64_t rowA[RB], rowB[RB];
+    bool    same_b = true;
+#pragma unroll
+    for (int j = 0; j < RB; j++) {
+        int64_t r = r0 + j, oa = 0, ob = 0, oc = 0;
+        if (r < R) grp_offset3(a.rows, r, oa, ob, oc);
+        rowA[j] = (r < R) ? oa : rowA[0]; // out-of-range rows re-read row 0 (results discarded)
+        rowB[j] = (r < R) ? ob : 0;
+        if (rowB[j] != 0) same_b = false;
+    }
+    int64_t colB[NN];
+#pragma unroll
+    for (int c = 0; c < NN; c++) colB[c] = (c < ncols) ? grp_offset(a.n, c, ROLE_B) : 0;
+
+    T acc[RB][NN];
+#pragma unroll
+    for (int j = 0; j < RB; j++)
+#pragma unroll
+        for (int c = 0; c < NN; c++) acc[j][c] = zero_of<T>();
+
+    struct alignas(sizeof(T) * VEC) Pack { T v[VEC]; };
+
+    for (int64_t u = u_begin + warp; u < u_end; u += NW) {
+        int64_t ko, ch;
+        if (chunks == 1) { ko = u; ch = 0; }
+        else if (units <= 0x7fffffffLL) { uint32_t q = (uint32_t)u / (uint32_t)chunks; ko = q; ch = (uint32_t)u - q * (uint32_t)chunks; }
+        else { ko = u / chunks; ch = u - ko * chunks; }
+        int64_t offA = 0, offB = 0;
+        if (a.k.n > 1) { // decode the outer K indices (index 0 is the inner run)
+            int64_t x = ko;
+            for (int i = 1; i < a.k.n; i++) {
+                int64_t q = x / a.k.ext[i], r = x - q * a.k.ext[i];
+                offA += r * a.k.s[ROLE_A][i];
+                offB += r * a.k.s[ROLE_B][i];
+                x = q;
+            }
+        }
+        const int64_t ki = ch * CH + (int64_t)lane * VEC;
+        if (ki >= E0) continue;
+        Pack av[RB];
+        if constexpr (VEC > 1) {
+#pragma unroll
+            for (int j = 0; j < RB; j++) av[j] = *reinterpret_cast<const Pack *>(A + rowA[j] + offA + ki);
+        } else {
+#pragma unroll
+            for (int j = 0; j < RB; j++) av[j].v[0] = A[rowA[j] + offA + ki * sA0];
+        }
+        if (same_b) {
+#pragma unroll
+            for (int c = 0; c < NN; c++) {
+                if (c >= ncols) break;
+                Pack bv;
+                if constexpr (VEC > 1) bv = *reinterpret_cast<const Pack *>(B + offB + ki + colB[c]);
+                else bv.v[0] = B[offB + ki * sB0 + colB[c]];
+#pragma unroll
+                for (int e = 0; e < VEC; e++) {
+                    T b = maybe_conj<CONJ_B>(bv.v[e]);
+#pragma unroll
+                    for (int j = 0; j < RB; j++) acc[j][c] = fma_(maybe_conj<CONJ_A>(av[j].v[e]), b, acc[j][c]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < RB; j++)
+#pragma unroll
+                for (int c = 0; c < NN; c++) {
+                    if (c >= ncols) break;
+#pragma unroll
+                    for (int e = 0; e < VEC; e++) {
+                        T b = maybe_conj<CONJ_B>(B[rowB[j] + offB + (ki + e) * sB0 + colB[c]]);
+                        acc[j][c] = fma_(maybe_conj<CONJ_A>(av[j].v[e]), b, acc[j][c]);
+                    }
+                }
+        }
+    }
 #pragma unroll
     for (int j = 0; j < RB; j++)
 #pragma unroll

@@ -77,6 +77,76 @@ template <typename T, bool CONJ, int TILE, int ROWS> __global__ void __launch_bo
     }
 }
 
+// 16-byte plane transpose for 4/8-byte real types: 64 x 64 elements per tile, 256 threads.
+// Phase 1: every thread issues 8 independent 2-element loads along axis a (all in flight before the
+// first use); the pairs are scattered into an XOR-swizzled tile[a][c]. Phase 2: 2-element reads along
+// axis c, 8 independent stores. Needs even extents/strides and 2-element-aligned bases (checked on the host).
+template <typename T> struct alignas(2 * sizeof(T)) Pair { T x, y; };
+
+template <typename T> __global__ void __launch_bounds__(256) permute_tile_vec(const __grid_constant__ PermArgs a) {
+    constexpr int TILE = 64;
+    __shared__ __align__(16) T tile[TILE * TILE];
+    const T      *A = reinterpret_cast<const T *>(a.A);
+    T            *C = reinterpret_cast<T *>(a.C);
+    const T       alpha = make_scalar<T>(a.alpha[0], a.alpha[1]), beta = make_scalar<T>(a.beta[0], a.beta[1]);
+    const bool    has_beta = !is_zero(beta), plain = is_one(alpha) && !has_beta;
+    const int     tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
+    const int64_t per_rest = a.tiles_a * a.tiles_c;
+    const int64_t ntiles = per_rest * a.rest.tot;
+    // swizzle: element (ia, ic) lives at tile[ia*64 + (ic ^ sw(ia))], sw(ia) = 2*((ia>>1)&7) keeps (even,odd) pairs together
+    auto sw = [](int ia) { return ((ia >> 1) & 7) << 1; };
+
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int64_t rest, ta, tc;
+        if (ntiles <= 0x7fffffffLL) {
+            uint32_t tt = (uint32_t)t, pr = (uint32_t)per_rest, r_ = tt / pr, in = tt - r_ * pr;
+            uint32_t c_ = in / (uint32_t)a.tiles_a;
+            rest = r_; tc = c_; ta = in - c_ * (uint32_t)a.tiles_a;
+        } else {
+            rest = t / per_rest;
+            int64_t in = t - rest * per_rest;
+            tc = in / a.tiles_a; ta = in - tc * a.tiles_a;
+        }
+        int64_t offA, offC;
+        grp_offset2(a.rest, rest, ROLE_A, ROLE_C, offA, offC);
+        const int64_t a0 = ta * TILE, c0 = tc * TILE;
+        Pair<T> v[8];
+        {
+            const int64_t ia = a0 + 2 * lx;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int64_t ic = c0 + ly + 8 * i;
+                if (ia < a.ea && ic < a.ec) v[i] = *reinterpret_cast<const Pair<T> *>(A + offA + ia + ic * a.sa_c);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int icl = ly + 8 * i, ial = 2 * lx;
+                tile[ial * TILE + (icl ^ sw(ial))] = v[i].x;
+                tile[(ial + 1) * TILE + (icl ^ sw(ial + 1))] = v[i].y;
+            }
+        }
+        __syncthreads();
+        {
+            const int64_t ic = c0 + 2 * lx;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int     ial = ly + 8 * i;
+                const int64_t ia = a0 + ial;
+                if (ia < a.ea && ic < a.ec) {
+                    Pair<T>  w = *reinterpret_cast<const Pair<T> *>(&tile[ial * TILE + ((2 * lx) ^ sw(ial))]);
+                    Pair<T> *dst = reinterpret_cast<Pair<T> *>(C + offC + ia * a.sc_a + ic);
+                    if (!plain) {
+                        w.x = mul_(alpha, w.x); w.y = mul_(alpha, w.y);
+                        if (has_beta) { Pair<T> o = *dst; w.x = fma_(beta, o.x, w.x); w.y = fma_(beta, o.y, w.y); }
+                    }
+                    *dst = w;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // row kernel: the same axis is fastest on both sides. VEC elements per thread per step.
 template <typename T, bool CONJ, int VEC> __global__ void __launch_bounds__(256) permute_rows(const __grid_constant__ PermArgs a) {
     const T      *A = reinterpret_cast<const T *>(a.A);
@@ -85,29 +155,42 @@ template <typename T, bool CONJ, int VEC> __global__ void __launch_bounds__(256)
     const bool    has_beta = !is_zero(beta);
     const int64_t chunks_per_row = (a.ea + VEC - 1) / VEC;
     const int64_t total = chunks_per_row * a.rest.tot;
-    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (int64_t)gridDim.x * blockDim.x) {
-        int64_t row = x / chunks_per_row, ch = x - row * chunks_per_row;
-        int64_t offA, offC;
-        grp_offset2(a.rest, row, ROLE_A, ROLE_C, offA, offC);
-        int64_t i0 = ch * VEC;
-        if constexpr (VEC > 1) {
-            // only launched when sa_a == sc_a == 1, ea % VEC == 0 and everything is VEC-aligned
-            struct alignas(sizeof(T) * VEC) Pack { T v[VEC]; };
-            Pack in = *reinterpret_cast<const Pack *>(A + offA + i0);
-            Pack out;
-            T   *dst = C + offC + i0;
-            if (has_beta) out = *reinterpret_cast<const Pack *>(dst);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    constexpr int UNR = 4;
+    struct alignas(sizeof(T) * VEC) Pack { T v[VEC]; };
+    auto locate = [&](int64_t x, int64_t &oa, int64_t &oc) {
+        int64_t row, ch;
+        if (a.rest.tot == 1) { row = 0; ch = x; }
+        else if (total <= 0x7fffffffLL) { uint32_t q = (uint32_t)x / (uint32_t)chunks_per_row; row = q; ch = (uint32_t)x - q * (uint32_t)chunks_per_row; }
+        else { row = x / chunks_per_row; ch = x - row * chunks_per_row; }
+        grp_offset2(a.rest, row, ROLE_A, ROLE_C, oa, oc);
+        oa += ch * VEC * (VEC > 1 ? 1 : a.sa_a);
+        oc += ch * VEC * (VEC > 1 ? 1 : a.sc_a);
+    };
+    for (int64_t x0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x0 < total; x0 += stride * UNR) {
+        int64_t oa[UNR], oc[UNR];
+        Pack    in[UNR], old[UNR];
 #pragma unroll
-            for (int u = 0; u < VEC; u++) {
-                T v = mul_(alpha, maybe_conj<CONJ>(in.v[u]));
-                if (has_beta) v = fma_(beta, out.v[u], v);
-                out.v[u] = v;
+        for (int u = 0; u < UNR; u++) {
+            int64_t x = x0 + u * stride;
+            if (x < total) {
+                locate(x, oa[u], oc[u]);
+                in[u] = *reinterpret_cast<const Pack *>(A + oa[u]);
+                if (has_beta) old[u] = *reinterpret_cast<const Pack *>(C + oc[u]);
             }
-            *reinterpret_cast<Pack *>(dst) = out;
-        } else {
-            if (i0 < a.ea) {
-                T *dst = C + offC + i0 * a.sc_a;
-                *dst = perm_out<T, CONJ>(alpha, A[offA + i0 * a.sa_a], beta, dst, has_beta);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            int64_t x = x0 + u * stride;
+            if (x < total) {
+                Pack out;
+#pragma unroll
+                for (int e = 0; e < VEC; e++) {
+                    T v = mul_(alpha, maybe_conj<CONJ>(in[u].v[e]));
+                    if (has_beta) v = fma_(beta, old[u].v[e], v);
+                    out.v[e] = v;
+                }
+                *reinterpret_cast<Pack *>(C + oc[u]) = out;
             }
         }
     }
@@ -189,6 +272,21 @@ int permute_impl(void *stream, int rank, const int64_t *dimsA, const int64_t *st
         pa.ec = ax[ic].ext; pa.sa_c = ax[ic].sa; pa.sc_c = ax[ic].sc;
         for (size_t i = 0; i < ax.size(); i++)
             if (i != ia && i != ic && !push_rest(ax[i])) return fail(EB200_ERR_UNSUPPORTED, "permute: more than %d non-mergeable axes", MAXG + 2);
+        if constexpr (!Scalar<T>::is_complex) {
+            bool vec_ok = !cj && pa.sa_a == 1 && pa.sc_c == 1 && pa.ea % 2 == 0 && pa.ec % 2 == 0 && pa.sa_c % 2 == 0 && pa.sc_a % 2 == 0 &&
+                          ((uintptr_t)A % (2 * sizeof(T)) == 0) && ((uintptr_t)C % (2 * sizeof(T)) == 0);
+            for (int i = 0; i < pa.rest.n && vec_ok; i++)
+                if (pa.rest.s[ROLE_A][i] % 2 || pa.rest.s[ROLE_C][i] % 2) vec_ok = false;
+            if (vec_ok) {
+                pa.tiles_a = (pa.ea + 63) / 64;
+                pa.tiles_c = (pa.ec + 63) / 64;
+                int64_t ntiles = pa.tiles_a * pa.tiles_c * pa.rest.tot;
+                int     grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)sm_count() * 24));
+                permute_tile_vec<T><<<grid, 256, 0, s>>>(pa);
+                EB_POST_LAUNCH("permute_tile_vec");
+                return EB200_OK;
+            }
+        }
         constexpr int TILE = 32, ROWS = 8;
         pa.tiles_a = (pa.ea + TILE - 1) / TILE;
         pa.tiles_c = (pa.ec + TILE - 1) / TILE;

@@ -1,0 +1,347 @@
+"""GPU parity tests (pytest -m gpu, on the B200): every kernel family of libeinsums_b200.so against the CPU
+oracle on the same seeded inputs, through the C ABI. FP64 tolerance 1e-12 relative, FP32 1e-5 (helpers.TOL);
+copies/permutes with alpha=1,beta=0 bit-exact."""
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import TOL, assert_close, golden, load_water, rand, rel_err, rhf_mp2_water
+from test_oracle_golden import CASES
+
+pytestmark = pytest.mark.gpu
+
+NP2T = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32, np.dtype(np.complex128): torch.complex128,
+        np.dtype(np.complex64): torch.complex64}
+
+
+def dev(x):
+    x = np.asarray(x)
+    return torch.from_numpy(np.array(x, order="C", copy=True)).cuda()
+
+
+def dev_like(x: np.ndarray):
+    """Upload preserving the numpy strides (views with padding stay views)."""
+    if x.ndim == 0 or x.flags.c_contiguous:
+        return dev(x)
+    base = x.base if x.base is not None else x
+    while base.base is not None:
+        base = base.base
+    tb = torch.from_numpy(np.ascontiguousarray(base)).cuda() if base.flags.c_contiguous else None
+    if tb is None:
+        return dev(x)
+    off = (x.__array_interface__["data"][0] - base.__array_interface__["data"][0]) // x.itemsize
+    return torch.as_strided(tb.view(-1), x.shape, [s // x.itemsize for s in x.strides], off)
+
+
+def run_case(gpu, oracle, c_idx, a_idx, b_idx, ext, dtype, alpha, beta, conj_a=False, conj_b=False, force=0, seed=0, split_k=0):
+    rng = np.random.default_rng(seed)
+    A = rand(rng, tuple(ext[x] for x in a_idx), dtype)
+    B = rand(rng, tuple(ext[x] for x in b_idx), dtype)
+    C0 = rand(rng, tuple(ext[x] for x in c_idx), dtype)
+    ref = C0.copy()
+    oracle.einsum_generic(c_idx, ref, a_idx, A, b_idx, B, alpha, beta, conj_a, conj_b)
+    Cd = dev(C0)
+    d = gpu.contract(c_idx, Cd, a_idx, dev(A), b_idx, dev(B), alpha, beta, conj_a, conj_b, force_kernel=force, split_k=split_k)
+    torch.cuda.synchronize()
+    assert_close(Cd.cpu().numpy(), ref, dtype, f"{c_idx}<-{a_idx},{b_idx} {np.dtype(dtype)} alpha={alpha} beta={beta} kernel={d.kernel_used}")
+    return d
+
+
+# ---------------------------------------------------------------------------------------------
+def test_known_answers_einsum1_device(gpu):
+    """GPUTensorAlgebra.hip:449-517: exact integers."""
+    A = dev(np.arange(1, 10, dtype=np.float64).reshape(3, 3))
+    C = torch.zeros(3, 3, dtype=torch.float64, device="cuda")
+    gpu.contract("ij", C, "ik", A, "kj", A.clone())
+    assert C.cpu().numpy().ravel().tolist() == [30, 36, 42, 66, 81, 96, 102, 126, 150]
+    A3 = dev(np.arange(1, 28, dtype=np.float64).reshape(3, 3, 3))
+    C = torch.zeros(3, 3, dtype=torch.float64, device="cuda")
+    gpu.contract("il", C, "ijk", A3, "jkl", A3.clone())
+    assert C.cpu().numpy().ravel().tolist() == [765, 810, 855, 1818, 1944, 2070, 2871, 3078, 3285]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}<-{c[1]},{c[2]}" for c in CASES])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.complex128, np.complex64])
+def test_contract_small_all_patterns(gpu, oracle, case, dtype):
+    c_idx, a_idx, b_idx, ext = case
+    for alpha, beta in ((1.0, 0.0), (0.5, 2.0), (-1.0, 1.0)):
+        run_case(gpu, oracle, c_idx, a_idx, b_idx, ext, dtype, alpha, beta)
+
+
+@pytest.mark.parametrize("conj", [(True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("case", [CASES[0], CASES[1], CASES[4], CASES[6], CASES[7], CASES[8], CASES[10]], ids=lambda c: f"{c[0]}<-{c[1]},{c[2]}")
+def test_contract_conj(gpu, oracle, case, conj):
+    c_idx, a_idx, b_idx, ext = case
+    run_case(gpu, oracle, c_idx, a_idx, b_idx, ext, np.complex128, 0.5 + 0.25j, 2.0 - 1.0j, conj[0], conj[1])
+
+
+MID = [
+    # benchmark-config patterns at sizes that cross tile boundaries (ragged edges) and exercise split-K
+    ("abef", "mnef", "mnab", dict(a=13, b=11, e=12, f=14, m=5, n=6)),            # Wabef: M,N contiguous operands
+    ("mnij", "mnef", "ijef", dict(m=7, n=6, i=5, j=9, e=31, f=29)),              # Wmnij: K contiguous, split-K
+    ("mbej", "jnfb", "mnef", dict(m=6, b=21, e=19, j=7, n=5, f=23)),             # Wmbej: fused permutation
+    ("pq", "prqs", "rs", dict(p=37, q=41, r=33, s=35)),                          # Fock K
+    ("pq", "pqrs", "rs", dict(p=37, q=41, r=33, s=35)),                          # Fock J
+    ("ij", "ik", "kj", dict(i=257, j=131, k=193)),
+    ("ij", "ki", "jk", dict(i=130, j=258, k=77)),
+    ("ji", "ik", "kj", dict(i=129, j=70, k=300)),
+    ("ijb", "ikb", "kjb", dict(i=65, j=33, k=40, b=3)),                          # batch index innermost
+    ("bij", "bik", "bkj", dict(i=65, j=33, k=40, b=5)),                          # batch index outermost
+    ("q", "pq", "p", dict(p=1000, q=777)),                                       # col reduce
+    ("p", "pq", "q", dict(p=777, q=1000)),                                       # row reduce
+    ("", "ijab", "ijab", dict(i=17, j=19, a=23, b=29)),                          # dot
+    ("pn", "pqrs", "qrsn", dict(p=200, q=11, r=12, s=13, n=3)),                  # few columns (NN=4)
+    ("np", "qrsn", "pqrs", dict(p=200, q=11, r=12, s=13, n=7)),                  # few rows on the A side -> swap
+]
+
+
+@pytest.mark.parametrize("case", MID, ids=lambda c: f"{c[0]}<-{c[1]},{c[2]}")
+def test_contract_mid_f64(gpu, oracle, case):
+    c_idx, a_idx, b_idx, ext = case
+    run_case(gpu, oracle, c_idx, a_idx, b_idx, ext, np.float64, 0.25, 1.0, seed=11)
+    run_case(gpu, oracle, c_idx, a_idx, b_idx, ext, np.float64, 1.0, 0.0, seed=12)
+
+
+@pytest.mark.parametrize("case", MID[:8], ids=lambda c: f"{c[0]}<-{c[1]},{c[2]}")
+def test_kernel_families_agree(gpu, oracle, case):
+    """The same contraction forced through the tensor-pipe tile kernel, the FMA tile kernel and (when the shape
+    allows) the streaming reductions must all match the oracle."""
+    from einsums_b200 import KF
+    c_idx, a_idx, b_idx, ext = case
+    used = set()
+    for fam in ("TILE_MMA", "TILE_SIMT", "ROWREDUCE", "COLREDUCE"):
+        d = run_case(gpu, oracle, c_idx, a_idx, b_idx, ext, np.float64, 0.5, 2.0, force=KF[fam], seed=5)
+        used.add(d.kernel_used)
+    assert KF["TILE_MMA"] in used and KF["TILE_SIMT"] in used
+    for sk in (1, 2, 5):
+        run_case(gpu, oracle, c_idx, a_idx, b_idx, ext, np.float64, 0.5, 2.0, force=KF["TILE_MMA"], seed=6, split_k=sk)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.complex128])
+def test_contract_mid_other_types(gpu, oracle, dtype):
+    for case in (MID[0], MID[2], MID[3], MID[5], MID[10], MID[12]):
+        c_idx, a_idx, b_idx, ext = case
+        run_case(gpu, oracle, c_idx, a_idx, b_idx, ext, dtype, 0.25, 1.0, seed=21)
+
+
+def test_contract_strided_views(gpu, oracle):
+    """Views with padding (Einsum1.cpp:96-140, Einsum7.cpp:195-210): strides are honoured, bytes outside the view untouched."""
+    rng = np.random.default_rng(4)
+    big = rand(rng, (9, 7, 7))
+    qov = big[:, :3, 3:]
+    iax = rand(rng, (3, 4, 5))
+    Cfull = rand(rng, (12, 8))
+    Cview = Cfull[2:11, 1:6]
+    ref_full = Cfull.copy()
+    oracle.einsum_generic("QX", ref_full[2:11, 1:6], "Qia", qov, "iaX", iax, 0.5, 2.0)
+    bd, cd = dev(big), dev(Cfull)
+    gpu.contract("QX", cd[2:11, 1:6], "Qia", bd[:, :3, 3:], "iaX", dev(iax), 0.5, 2.0)
+    assert_close(cd.cpu().numpy(), ref_full)
+    mask = np.ones_like(Cfull, bool)
+    mask[2:11, 1:6] = False
+    assert np.array_equal(cd.cpu().numpy()[mask], Cfull[mask])
+
+
+def test_beta_zero_never_reads_c(gpu):
+    A = torch.rand(70, 50, dtype=torch.float64, device="cuda")
+    B = torch.rand(50, 90, dtype=torch.float64, device="cuda")
+    for fam_shape in (("ij", "ik", "kj", A, B, (70, 90)), ("i", "ik", "k", A, B[:, 0].contiguous(), (70,)), ("", "ik", "ik", A, A.clone(), ())):
+        c, a, b, At, Bt, shp = fam_shape
+        Ct = torch.full(shp, float("nan"), dtype=torch.float64, device="cuda")
+        gpu.contract(c, Ct, a, At, b, Bt, 1.0, 0.0)
+        assert not torch.isnan(Ct).any()
+
+
+# ---------------------------------------------------------------------------------------------
+# BLAS-like flat seam (column-major)
+@pytest.mark.parametrize("ta,tb", list(itertools.product("ntc", "ntc")))
+def test_dgemm_all_trans_with_padding(gpu, oracle, ta, tb):
+    import ctypes as C
+    rng = np.random.default_rng(8)
+    m, n, k = 70, 45, 133
+    lda = (m if ta == "n" else k) + 3
+    ldb = (k if tb == "n" else n) + 2
+    ldc = m + 5
+    A = rand(rng, ((k if ta == "n" else m), lda))  # column-major: numpy row = BLAS column
+    B = rand(rng, ((n if tb == "n" else k), ldb))
+    Cm = rand(rng, (n, ldc))
+    ref = Cm.copy()
+    oracle.lib().orc_dgemm(ta.encode(), tb.encode(), m, n, k, 0.75, A.ctypes.data, lda, B.ctypes.data, ldb, -0.5, ref.ctypes.data, ldc)
+    Cd = dev(Cm)
+    gpu.gemm(ta, tb, m, n, k, 0.75, dev(A), lda, dev(B), ldb, -0.5, Cd, ldc)
+    assert_close(Cd.cpu().numpy(), ref)
+    assert np.array_equal(Cd.cpu().numpy()[:, m:], Cm[:, m:]), "padding rows of C were touched"
+
+
+def test_sgemm_zgemm(gpu, oracle):
+    import ctypes as C
+    rng = np.random.default_rng(9)
+    m, n, k = 100, 64, 50
+    A, B, Cm = rand(rng, (k, m), np.float32), rand(rng, (n, k), np.float32), rand(rng, (n, m), np.float32)
+    ref = Cm.copy()
+    oracle.lib().orc_sgemm(b"n", b"n", m, n, k, 0.5, A.ctypes.data, m, B.ctypes.data, k, 1.5, ref.ctypes.data, m)
+    Cd = dev(Cm)
+    gpu.gemm("n", "n", m, n, k, 0.5, dev(A), m, dev(B), k, 1.5, Cd, m)
+    assert_close(Cd.cpu().numpy(), ref, np.float32)
+    A, B, Cm = rand(rng, (m, k), np.complex128), rand(rng, (n, k), np.complex128), rand(rng, (n, m), np.complex128)
+    ref = Cm.copy()
+    d2 = C.c_double * 2
+    oracle.lib().orc_zgemm(b"c", b"n", m, n, k, d2(0.5, 0.25), A.ctypes.data, k, B.ctypes.data, k, d2(1.0, -1.0), ref.ctypes.data, m)
+    Cd = dev(Cm)
+    gpu.gemm("c", "n", m, n, k, 0.5 + 0.25j, dev(A), k, dev(B), k, 1.0 - 1.0j, Cd, m)
+    assert_close(Cd.cpu().numpy(), ref, np.complex128)
+
+
+@pytest.mark.parametrize("t", "nt")
+@pytest.mark.parametrize("incx,incy", [(1, 1), (2, 3), (-1, 2)])
+def test_dgemv(gpu, oracle, t, incx, incy):
+    rng = np.random.default_rng(10)
+    m, n, lda = 300, 170, 307
+    A = rand(rng, (n, lda))
+    lenx, leny = (n, m) if t == "n" else (m, n)
+    x, y = rand(rng, (1 + (lenx - 1) * abs(incx),)), rand(rng, (1 + (leny - 1) * abs(incy),))
+    ref = y.copy()
+    oracle.lib().orc_dgemv(t.encode(), m, n, 1.5, A.ctypes.data, lda, x.ctypes.data, incx, 0.5, ref.ctypes.data, incy)
+    yd = dev(y)
+    gpu.gemv(t, m, n, 1.5, dev(A), lda, dev(x), incx, 0.5, yd, incy)
+    assert_close(yd.cpu().numpy(), ref)
+
+
+def test_level1_and_ger(gpu, oracle):
+    rng = np.random.default_rng(12)
+    n = 100003
+    x, y, z = rand(rng, (n,)), rand(rng, (n,)), rand(rng, (n,))
+    assert abs(gpu.dot(n, dev(x), 1, dev(y), 1) - oracle.lib().orc_ddot(n, x.ctypes.data, 1, y.ctypes.data, 1)) <= 1e-12 * n ** 0.5
+    assert abs(gpu.dot(n // 3, dev(x), 3, dev(y), 2) - float(np.dot(x[: 3 * (n // 3) : 3], y[: 2 * (n // 3) : 2]))) <= 1e-11
+    yd = dev(y); gpu.axpy(n, 0.5, dev(x), 1, yd, 1); assert_close(yd.cpu().numpy(), y + 0.5 * x)
+    yd = dev(y); gpu.axpby(n, 0.5, dev(x), 1, -2.0, yd, 1); assert_close(yd.cpu().numpy(), 0.5 * x - 2.0 * y)
+    yd = dev(np.full(n, np.nan)); gpu.axpby(n, 0.5, dev(x), 1, 0.0, yd, 1); assert_close(yd.cpu().numpy(), 0.5 * x)
+    yd = dev(y); gpu.scal(n, -3.0, yd, 1); assert np.array_equal(yd.cpu().numpy(), -3.0 * y)
+    yd = dev(y); gpu.copy(n // 2, dev(x), 2, yd, 1); assert np.array_equal(yd.cpu().numpy()[: n // 2], x[: 2 * (n // 2) : 2])
+    yd = dev(y); gpu.fill(n // 2, 7.0, yd, 2); assert np.array_equal(yd.cpu().numpy()[: 2 * (n // 2) : 2], np.full(n // 2, 7.0))
+    zd = dev(z); gpu.dirprod(n, 0.5, dev(x), 1, dev(y), 1, zd, 1); assert_close(zd.cpu().numpy(), z + 0.5 * x * y)
+    m, k, lda = 211, 97, 215
+    A = rand(rng, (k, lda)); u, w = rand(rng, (m,)), rand(rng, (k,))
+    ref = A.copy(); oracle.lib().orc_dger(m, k, 0.5, u.ctypes.data, 1, w.ctypes.data, 1, ref.ctypes.data, lda)
+    Ad = dev(A); gpu.ger(m, k, 0.5, dev(u), 1, dev(w), 1, Ad, lda); assert_close(Ad.cpu().numpy(), ref)
+    # complex: dotc and gerc
+    xc, yc = rand(rng, (1000,), np.complex128), rand(rng, (1000,), np.complex128)
+    assert abs(gpu.dot(1000, dev(xc), 1, dev(yc), 1, conj=True) - np.vdot(xc, yc)) < 1e-11
+    assert abs(gpu.dot(1000, dev(xc), 1, dev(yc), 1) - np.dot(xc, yc)) < 1e-11
+
+
+# ---------------------------------------------------------------------------------------------
+# permute
+@pytest.mark.parametrize("order", list(itertools.permutations(range(4))), ids=lambda o: "".join("ijkl"[x] for x in o))
+def test_permute_rank4_all_orders(gpu, oracle, order):
+    """Config 4 at a size the oracle handles in seconds; unequal, non-tile-multiple extents; bit-exact for alpha=1,beta=0."""
+    rng = np.random.default_rng(13)
+    shape = (19, 33, 10, 45)
+    A = rand(rng, shape)
+    c_idx = "".join("ijkl"[o] for o in order)
+    C0 = rand(rng, tuple(shape[o] for o in order))
+    ref = C0.copy(); oracle.permute(c_idx, ref, "ijkl", A, 1.0, 0.0)
+    Cd = dev(C0); gpu.permute(c_idx, Cd, "ijkl", dev(A), 1.0, 0.0)
+    assert np.array_equal(Cd.cpu().numpy(), ref)
+    ref = C0.copy(); oracle.permute(c_idx, ref, "ijkl", A, 0.5, 2.0)
+    Cd = dev(C0); gpu.permute(c_idx, Cd, "ijkl", dev(A), 0.5, 2.0)
+    assert_close(Cd.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.complex128])
+def test_permute_ranks_types_conj(gpu, oracle, dtype):
+    rng = np.random.default_rng(14)
+    for rank, shape in ((0, ()), (1, (37,)), (2, (65, 130)), (3, (33, 7, 64)), (5, (6, 5, 9, 4, 8))):
+        letters = "ijklm"[:rank]
+        A = rand(rng, shape, dtype)
+        for order in list(itertools.permutations(range(rank)))[:: max(1, rank)]:
+            c_idx = "".join(letters[o] for o in order)
+            for conj in ((False, True) if np.dtype(dtype).kind == "c" else (False,)):
+                ref = np.zeros(tuple(shape[o] for o in order), dtype); oracle.permute(c_idx, ref, letters, A, 1.0, 0.0, conj)
+                Cd = dev(np.zeros_like(ref)); gpu.permute(c_idx, Cd, letters, dev(A), 1.0, 0.0, conj)
+                assert np.array_equal(Cd.cpu().numpy(), ref), f"rank {rank} order {c_idx} conj {conj}"
+
+
+def test_permute_into_larger_output_and_errors(gpu, oracle):
+    """DevicePermute.hpp:121-131: C may be larger than A along an axis; smaller is a dimension_error."""
+    rng = np.random.default_rng(15)
+    A = rand(rng, (5, 6))
+    C0 = rand(rng, (8, 7))
+    Cd = dev(C0)
+    gpu.permute("ji", Cd[:6, :5], "ij", dev(A))
+    out = Cd.cpu().numpy()
+    assert np.array_equal(out[:6, :5], A.T) and np.array_equal(out[6:], C0[6:]) and np.array_equal(out[:, 5:], C0[:, 5:])
+    with pytest.raises(ValueError):
+        gpu.permute("ji", dev(np.zeros((5, 5))), "ij", dev(A))
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at (near) benchmark sizes, where the oracle would take too long
+def test_permute_round_trip_large(gpu):
+    n = 96
+    A = torch.rand(n, n, n, n, dtype=torch.float64, device="cuda")
+    for order in ((3, 2, 1, 0), (1, 0, 3, 2), (2, 3, 0, 1), (0, 2, 1, 3), (3, 0, 1, 2)):
+        c_idx = "".join("ijkl"[o] for o in order)
+        B = torch.empty([n] * 4, dtype=torch.float64, device="cuda")
+        gpu.permute(c_idx, B, "ijkl", A)
+        assert torch.equal(B, A.permute(*order))           # bit-exact against torch's view
+        back = torch.empty_like(A)
+        gpu.permute("ijkl", back, c_idx, B)
+        assert torch.equal(back, A)                         # round trip is the identity
+
+
+def test_gemm_checksum_large(gpu):
+    """Checksum of checksums: 1^T C 1 = (1^T A)(B 1) for C = A B, at a Wabef-like shape (M=N=6400, K=400)."""
+    o, v = 20, 80
+    g = torch.rand(o, o, v, v, dtype=torch.float64, device="cuda") * 2 - 1
+    t = torch.rand(o, o, v, v, dtype=torch.float64, device="cuda") * 2 - 1
+    W = torch.rand(v, v, v, v, dtype=torch.float64, device="cuda") * 2 - 1
+    W0 = W.clone()
+    d = gpu.contract("abef", W, "mnef", g, "mnab", t, 0.25, 1.0)
+    assert d.kernel_used == 1
+    lhs = (W - W0).sum(dtype=torch.float64).item()
+    rhs = 0.25 * torch.dot(t.reshape(o * o, -1).sum(1), g.reshape(o * o, -1).sum(1)).item()
+    assert abs(lhs - rhs) <= 1e-12 * max(1.0, (W - W0).abs().sum().item())
+    # spot rows against a float64 matmul on the same device (different summation order)
+    ref = W0 + 0.25 * (t.reshape(o * o, -1).T @ g.reshape(o * o, -1)).reshape(v, v, v, v)
+    assert rel_err(W.cpu().numpy(), ref.cpu().numpy()) <= TOL[np.dtype(np.float64)]
+
+
+def test_linearity_fock(gpu):
+    n = 48
+    g = torch.rand(n, n, n, n, dtype=torch.float64, device="cuda") - 0.5
+    D1 = torch.rand(n, n, dtype=torch.float64, device="cuda") - 0.5
+    D2 = torch.rand(n, n, dtype=torch.float64, device="cuda") - 0.5
+    outs = []
+    for D in (D1, D2, D1 + 2.0 * D2):
+        K = torch.empty(n, n, dtype=torch.float64, device="cuda")
+        gpu.contract("pq", K, "prqs", g, "rs", D, -1.0, 0.0)
+        outs.append(K)
+    assert rel_err((outs[0] + 2.0 * outs[1]).cpu().numpy(), outs[2].cpu().numpy()) <= 1e-12
+    ref = -torch.einsum("prqs,rs->pq", g, D1)
+    assert rel_err(outs[0].cpu().numpy(), ref.cpu().numpy()) <= 1e-12
+
+
+def test_water_sto3g_on_device(gpu):
+    """QChemTests.cpp:185-416 with every contraction on the GPU: RHF -74.942079928192, MP2 -0.049149636120."""
+    def es(c, C, a, A, b, B, alpha, beta):
+        Cd = dev_like(np.asarray(C))
+        gpu.contract(c, Cd, a, dev_like(np.asarray(A)), b, dev_like(np.asarray(B)), alpha, beta)
+        C[...] = Cd.cpu().numpy()
+    e_rhf, e_mp2 = rhf_mp2_water(es)
+    exp = load_water()[4]
+    assert abs(e_rhf - exp["rhf_total_energy"]) < 1e-6
+    assert abs(e_mp2 - exp["mp2_correlation_energy"]) < 1e-6
+
+
+def test_launch_counter_and_errors(gpu):
+    from einsums_b200 import Eb200Error
+    gpu.launch_count_reset()
+    A = torch.rand(64, 64, dtype=torch.float64, device="cuda")
+    C = torch.zeros(64, 64, dtype=torch.float64, device="cuda")
+    gpu.contract("ij", C, "ik", A, "kj", A)
+    assert gpu.launch_count() >= 1
+    with pytest.raises(Eb200Error):
+        gpu.gemm("x", "n", 2, 2, 2, 1.0, A, 2, A, 2, 0.0, C, 2)
