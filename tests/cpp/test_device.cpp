@@ -1,0 +1,424 @@
+// GPU tests of the C++20 host shim: the reference's own device test cases (GPUTensorAlgebra.hip, GPULinearAlgebra.hip,
+// Sort.cpp / Transpose.cpp / Hadamard.cpp / Dot.cpp twins) rewritten against DeviceTensor + einsum/permute/linear_algebra of
+// this backend. Expected values come from hand loops on host copies, as the reference tests do; tolerances: 1e-12
+// relative (FP64), exact where the reference asserts exact integers.
+#include <Einsums/LinearAlgebra.hpp>
+#include <Einsums/Tensor/DeviceTensor.hpp>
+#include <Einsums/TensorAlgebra.hpp>
+
+#include "mini_test.hpp"
+
+#include <complex>
+#include <thread>
+
+using namespace einsums;
+using namespace einsums::tensor_algebra;
+using einsums::tensor_algebra::detail::AlgorithmChoice;
+namespace ta = einsums::tensor_algebra::detail;
+
+// ---- small host mirror helpers ---------------------------------------------------------------------------------------
+template <typename T, size_t R> struct Host {
+    std::array<int64_t, R> d{};
+    std::vector<T>         v;
+    template <typename TensorT> explicit Host(TensorT const &t) : v(t.to_host()) {
+        for (size_t i = 0; i < R; i++) d[i] = t.dim(i);
+    }
+    template <typename... I> T &operator()(I... i) {
+        std::array<int64_t, R> ix{int64_t(i)...};
+        int64_t                off = 0;
+        for (size_t k = 0; k < R; k++) off = off * d[k] + ix[k];
+        return v[off];
+    }
+};
+template <typename TensorT> auto host(TensorT const &t) { return Host<typename TensorT::ValueType, TensorT::Rank>(t); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+TEST_CASE(gpu_einsum1_known_answers) { // GPUTensorAlgebra.hip:445-518
+    using namespace einsums::index;
+    DeviceTensor<double, 2> A{"A", einsums::detail::DEV_ONLY, 3, 3}, B{"B", einsums::detail::DEV_ONLY, 3, 3}, C{"C", einsums::detail::DEV_ONLY, 3, 3};
+    for (int i0 = 0, ij = 1; i0 < 3; i0++)
+        for (int j0 = 0; j0 < 3; j0++, ij++) {
+            A(i0, j0) = ij;
+            B(i0, j0) = ij;
+        }
+    AlgorithmChoice alg;
+    einsum(Indices{i, j}, &C, Indices{i, k}, A, Indices{k, j}, B, &alg);
+    CHECK(alg == ta::GEMM);
+    double want[9] = {30, 36, 42, 66, 81, 96, 102, 126, 150};
+    for (int x = 0; x < 9; x++) CHECK((double)C(x / 3, x % 3) == want[x]);
+
+    DeviceTensor<double, 3> A3{"A", 3, 3, 3}, B3{"B", 3, 3, 3};
+    std::vector<double>     inc(27);
+    for (int x = 0; x < 27; x++) inc[x] = x + 1;
+    A3 = inc;
+    B3 = inc;
+    einsum(Indices{i, l}, &C, Indices{i, j, k}, A3, Indices{j, k, l}, B3, &alg);
+    CHECK(alg == ta::GEMM);
+    double want2[9] = {765, 810, 855, 1818, 1944, 2070, 2871, 3078, 3285};
+    for (int x = 0; x < 9; x++) CHECK((double)C(x / 3, x % 3) == want2[x]);
+}
+
+TEST_CASE(gpu_wmnij_and_wabef) { // GPUTensorAlgebra.hip:1636-1672 (Wmnij) + the Wabef pattern of config 2
+    using namespace einsums::index;
+    size_t _m = 12, _n = 12, _i = 5, _j = 5, _e = 7, _f = 7;
+    auto   W = create_random_gpu_tensor("Wmnij", _m, _n, _i, _j);
+    auto   t_oovv = create_random_gpu_tensor("t_oovv", _i, _j, _e, _f), g_oovv = create_random_gpu_tensor("g_oovv", _m, _n, _e, _f);
+    auto   hW = host(W), ht = host(t_oovv), hg = host(g_oovv);
+    AlgorithmChoice alg;
+    einsum(1.0, Indices{m, n, i, j}, &W, 0.25, Indices{i, j, e, f}, t_oovv, Indices{m, n, e, f}, g_oovv, &alg);
+    CHECK(alg == ta::GEMM);
+    auto out = host(W);
+    for (size_t m0 = 0; m0 < _m; m0++)
+        for (size_t n0 = 0; n0 < _n; n0++)
+            for (size_t i0 = 0; i0 < _i; i0++)
+                for (size_t j0 = 0; j0 < _j; j0++) {
+                    double s = hW(m0, n0, i0, j0);
+                    for (size_t e0 = 0; e0 < _e; e0++)
+                        for (size_t f0 = 0; f0 < _f; f0++) s += 0.25 * ht(i0, j0, e0, f0) * hg(m0, n0, e0, f0);
+                    CHECK_CLOSE(out(m0, n0, i0, j0), s, 1e-12);
+                }
+    // Wabef[a,b,e,f] += 0.25 sum_mn g[m,n,e,f] t[m,n,a,b]
+    size_t o = 4, v = 9;
+    auto   Wv = create_random_gpu_tensor("Wabef", v, v, v, v), g2 = create_random_gpu_tensor("g", o, o, v, v), t2 = create_random_gpu_tensor("t", o, o, v, v);
+    auto   h0 = host(Wv), hg2 = host(g2), ht2 = host(t2);
+    einsum(1.0, Indices{a, b, e, f}, &Wv, 0.25, Indices{m, n, e, f}, g2, Indices{m, n, a, b}, t2, &alg);
+    CHECK(alg == ta::GEMM);
+    auto h1 = host(Wv);
+    for (size_t a0 = 0; a0 < v; a0++)
+        for (size_t b0 = 0; b0 < v; b0++)
+            for (size_t e0 = 0; e0 < v; e0++)
+                for (size_t f0 = 0; f0 < v; f0++) {
+                    double s = h0(a0, b0, e0, f0);
+                    for (size_t m0 = 0; m0 < o; m0++)
+                        for (size_t n0 = 0; n0 < o; n0++) s += 0.25 * hg2(m0, n0, e0, f0) * ht2(m0, n0, a0, b0);
+                    CHECK_CLOSE(h1(a0, b0, e0, f0), s, 1e-12);
+                }
+}
+
+TEST_CASE(gpu_fock_j_k_and_wmbej) { // config 1 (GEMV swapped / GENERIC) and config 3 (generic Wmbej)
+    using namespace einsums::index;
+    size_t nb = 9;
+    auto   g = create_random_gpu_tensor("g", nb, nb, nb, nb);
+    auto   D = create_random_gpu_tensor("D", nb, nb);
+    DeviceTensor<double, 2> J{"J", nb, nb}, K{"K", nb, nb};
+    AlgorithmChoice algJ, algK;
+    einsum(0.0, Indices{p, q}, &J, 2.0, Indices{p, q, r, s}, g, Indices{r, s}, D, &algJ);
+    einsum(0.0, Indices{p, q}, &K, -1.0, Indices{p, r, q, s}, g, Indices{r, s}, D, &algK);
+    CHECK(algJ == ta::GEMV);
+    CHECK(algK == ta::GENERIC);
+    auto hg = host(g);
+    auto hD = host(D), hJ = host(J), hK = host(K);
+    for (size_t p0 = 0; p0 < nb; p0++)
+        for (size_t q0 = 0; q0 < nb; q0++) {
+            double sj = 0, sk = 0;
+            for (size_t r0 = 0; r0 < nb; r0++)
+                for (size_t s0 = 0; s0 < nb; s0++) {
+                    sj += 2.0 * hg(p0, q0, r0, s0) * hD(r0, s0);
+                    sk -= hg(p0, r0, q0, s0) * hD(r0, s0);
+                }
+            CHECK_CLOSE(hJ(p0, q0), sj, 1e-12);
+            CHECK_CLOSE(hK(p0, q0), sk, 1e-12);
+        }
+    // swapped-operand form used by QChemTests.cpp:301-302
+    DeviceTensor<double, 2> F{"F", nb, nb};
+    F.zero();
+    einsum(1.0, Indices{i, j}, &F, 2.0, Indices{k, l}, D, Indices{i, j, k, l}, g, &algJ);
+    CHECK(algJ == ta::GEMV);
+    auto hF = host(F);
+    for (size_t p0 = 0; p0 < nb; p0++)
+        for (size_t q0 = 0; q0 < nb; q0++) CHECK_CLOSE(hF(p0, q0), hJ(p0, q0), 1e-12);
+
+    size_t o = 5, v = 8;
+    auto   t = create_random_gpu_tensor("t", o, o, v, v), gg = create_random_gpu_tensor("g", o, o, v, v), W = create_random_gpu_tensor("W", o, v, v, o);
+    auto   h0 = host(W), ht = host(t), hgg = host(gg);
+    AlgorithmChoice alg;
+    einsum(1.0, Indices{m, b, e, j}, &W, -0.5, Indices{j, n, f, b}, t, Indices{m, n, e, f}, gg, &alg);
+    CHECK(alg == ta::GENERIC);
+    auto h1 = host(W);
+    for (size_t m0 = 0; m0 < o; m0++)
+        for (size_t b0 = 0; b0 < v; b0++)
+            for (size_t e0 = 0; e0 < v; e0++)
+                for (size_t j0 = 0; j0 < o; j0++) {
+                    double s = h0(m0, b0, e0, j0);
+                    for (size_t n0 = 0; n0 < o; n0++)
+                        for (size_t f0 = 0; f0 < v; f0++) s -= 0.5 * ht(j0, n0, f0, b0) * hgg(m0, n0, e0, f0);
+                    CHECK_CLOSE(h1(m0, b0, e0, j0), s, 1e-12);
+                }
+}
+
+TEST_CASE(gpu_transposed_c_variants) { // Transpose.cpp:17-125, GPUTensorAlgebra.hip:1527-1634
+    using namespace einsums::index;
+    size_t ni = 6, nj = 7, nk = 5;
+    auto   A = create_random_gpu_tensor("A", ni, nk), At = create_random_gpu_tensor("At", nk, ni);
+    auto   B = create_random_gpu_tensor("B", nk, nj), Bt = create_random_gpu_tensor("Bt", nj, nk);
+    auto   hA = host(A), hAt = host(At), hB = host(B), hBt = host(Bt);
+    AlgorithmChoice alg;
+    auto check = [&](auto &C, bool transposed_c, auto &&aval, auto &&bval) {
+        auto hC = host(C);
+        for (size_t i0 = 0; i0 < ni; i0++)
+            for (size_t j0 = 0; j0 < nj; j0++) {
+                double s = 0;
+                for (size_t k0 = 0; k0 < nk; k0++) s += aval(i0, k0) * bval(k0, j0);
+                CHECK_CLOSE(transposed_c ? hC(j0, i0) : hC(i0, j0), s, 1e-12);
+            }
+    };
+    DeviceTensor<double, 2> C{"C", ni, nj}, Ct{"Ct", nj, ni};
+    einsum(Indices{i, j}, &C, Indices{i, k}, A, Indices{k, j}, B, &alg);   CHECK(alg == ta::GEMM);
+    check(C, false, [&](size_t x, size_t y) { return hA(x, y); }, [&](size_t x, size_t y) { return hB(x, y); });
+    einsum(Indices{i, j}, &C, Indices{k, i}, At, Indices{k, j}, B, &alg);  CHECK(alg == ta::GEMM);
+    check(C, false, [&](size_t x, size_t y) { return hAt(y, x); }, [&](size_t x, size_t y) { return hB(x, y); });
+    einsum(Indices{i, j}, &C, Indices{i, k}, A, Indices{j, k}, Bt, &alg);  CHECK(alg == ta::GEMM);
+    check(C, false, [&](size_t x, size_t y) { return hA(x, y); }, [&](size_t x, size_t y) { return hBt(y, x); });
+    einsum(Indices{i, j}, &C, Indices{k, i}, At, Indices{j, k}, Bt, &alg); CHECK(alg == ta::GEMM);
+    check(C, false, [&](size_t x, size_t y) { return hAt(y, x); }, [&](size_t x, size_t y) { return hBt(y, x); });
+    einsum(Indices{j, i}, &Ct, Indices{i, k}, A, Indices{k, j}, B, &alg);  CHECK(alg == ta::GEMM);
+    check(Ct, true, [&](size_t x, size_t y) { return hA(x, y); }, [&](size_t x, size_t y) { return hB(x, y); });
+    einsum(Indices{j, i}, &Ct, Indices{k, i}, At, Indices{j, k}, Bt, &alg); CHECK(alg == ta::GEMM);
+    check(Ct, true, [&](size_t x, size_t y) { return hAt(y, x); }, [&](size_t x, size_t y) { return hBt(y, x); });
+}
+
+TEST_CASE(gpu_views_runtime_decision) { // Einsum7.cpp:172-210 and Einsum1.cpp:96-140 on device tensors
+    using namespace einsums::index;
+    size_t naux = 9, nocc = 3, nvirt = 4, ur = 5, nmo = nocc + nvirt;
+    auto   Bq = create_random_gpu_tensor("Q", naux, nmo, nmo);
+    auto   iaX = create_random_gpu_tensor("ia_X", nocc, nvirt, ur);
+    DeviceTensor<double, 2> N1{"N", naux, ur}, N2{"N", naux, ur};
+    auto   Qov = Bq(All, Range{0, nocc}, Range{nocc, nmo});
+    AlgorithmChoice alg;
+    einsum(Indices{Q, X}, &N1, Indices{Q, i, a}, Qov, Indices{i, a, X}, iaX, &alg);
+    CHECK(alg == ta::GENERIC); // strided view: GEMM pattern falls back at run time
+    DeviceTensor<double, 3> dense(Qov);
+    einsum(Indices{Q, X}, &N2, Indices{Q, i, a}, dense, Indices{i, a, X}, iaX, &alg);
+    CHECK(alg == ta::GEMM);
+    auto h1 = host(N1), h2 = host(N2);
+    for (size_t x = 0; x < naux * ur; x++) CHECK_CLOSE(h1.v[x], h2.v[x], 1e-12);
+
+    auto A = create_random_gpu_tensor("A", 3, 5), B = create_random_gpu_tensor("B", 3, 5);
+    DeviceTensor<double, 2> C{"C", 10, 10};
+    C.zero();
+    DeviceTensorView Av{A, Dim<2>{3, 3}, Offset<2>{0, 0}}, Bv{B, Dim<2>{3, 3}, Offset<2>{0, 2}}, Cv{C, Dim<2>{3, 3}, Offset<2>{5, 5}};
+    einsum(Indices{i, j}, &Cv, Indices{i, k}, Av, Indices{j, k}, Bv, &alg);
+    CHECK(alg == ta::GEMM);
+    auto hA = host(A), hB = host(B), hC = host(C);
+    for (size_t x = 0; x < 10; x++)
+        for (size_t y = 0; y < 10; y++) {
+            double s = 0;
+            if (x >= 5 && x < 8 && y >= 5 && y < 8)
+                for (size_t k0 = 0; k0 < 3; k0++) s += hA(x - 5, k0) * hB(y - 5, k0 + 2);
+            CHECK_CLOSE(hC(x, y), s, 1e-12);
+        }
+}
+
+TEST_CASE(gpu_dot_direct_outer_hadamard) { // DotGPU.hip, Element.cpp, OuterProduct.cpp, Hadamard.cpp
+    using namespace einsums::index;
+    auto A = create_random_gpu_tensor("A", 4, 5, 6), B = create_random_gpu_tensor("B", 4, 5, 6);
+    auto hA = host(A), hB = host(B);
+    DeviceTensor<double, 0> d0;
+    AlgorithmChoice         alg;
+    einsum(Indices{}, &d0, Indices{i, j, a}, A, Indices{i, j, a}, B, &alg);
+    CHECK(alg == ta::DOT);
+    double want = 0;
+    for (size_t x = 0; x < hA.v.size(); x++) want += hA.v[x] * hB.v[x];
+    CHECK_CLOSE((double)d0, want, 1e-12);
+    double hs = 3.0; // host scalar C
+    einsum(2.0, Indices{}, &hs, 0.5, Indices{i, j, a}, A, Indices{i, j, a}, B, &alg);
+    CHECK(alg == ta::DOT);
+    CHECK_CLOSE(hs, 6.0 + 0.5 * want, 1e-12);
+    CHECK_CLOSE(linear_algebra::dot(A, B), want, 1e-12);
+
+    auto C = create_random_gpu_tensor("C", 4, 5, 6);
+    auto h0 = host(C);
+    einsum(2.0, Indices{i, j, a}, &C, -1.0, Indices{i, j, a}, A, Indices{i, j, a}, B, &alg);
+    CHECK(alg == ta::DIRECT);
+    auto h1 = host(C);
+    for (size_t x = 0; x < h1.v.size(); x++) CHECK_CLOSE(h1.v[x], 2.0 * h0.v[x] - hA.v[x] * hB.v[x], 1e-12);
+
+    auto u = create_random_gpu_tensor("u", 7), w = create_random_gpu_tensor("w", 9);
+    DeviceTensor<double, 2> O{"O", 7, 9}, Ot{"Ot", 9, 7};
+    einsum(Indices{a, b}, &O, Indices{a}, u, Indices{b}, w, &alg);  CHECK(alg == ta::GER);
+    einsum(Indices{b, a}, &Ot, Indices{a}, u, Indices{b}, w, &alg); CHECK(alg == ta::GER);
+    auto hu = host(u), hw = host(w);
+    auto hO = host(O), hOt = host(Ot);
+    for (size_t x = 0; x < 7; x++)
+        for (size_t y = 0; y < 9; y++) {
+            CHECK_CLOSE(hO(x, y), hu(x) * hw(y), 1e-14);
+            CHECK_CLOSE(hOt(y, x), hu(x) * hw(y), 1e-14);
+        }
+    // rank-2 x rank-2 outer product into rank 4 (OuterProduct.cpp)
+    auto P = create_random_gpu_tensor("P", 3, 4), Qm = create_random_gpu_tensor("Q", 5, 2);
+    DeviceTensor<double, 4> R4{"R", 3, 4, 5, 2};
+    einsum(Indices{i, j, k, l}, &R4, Indices{i, j}, P, Indices{k, l}, Qm, &alg);
+    CHECK(alg == ta::GER);
+    auto hP = host(P), hQ = host(Qm);
+    auto hR = host(R4);
+    for (size_t x = 0; x < 3; x++) for (size_t y = 0; y < 4; y++) for (size_t z = 0; z < 5; z++) for (size_t t = 0; t < 2; t++)
+        CHECK_CLOSE(hR(x, y, z, t), hP(x, y) * hQ(z, t), 1e-14);
+
+    // Hadamard: C[i] = sum_j A[i,i,j]... keep it simple: i <- ii, i  and  ij <- ij... with repeated index in A (Hadamard.cpp:17-60)
+    auto H = create_random_gpu_tensor("H", 6, 6);
+    auto hv = create_random_gpu_tensor("h", 6);
+    DeviceTensor<double, 1> Hd{"Hd", 6};
+    einsum(Indices{i}, &Hd, Indices{i, i}, H, Indices{i}, hv, &alg);
+    CHECK(alg == ta::GENERIC);
+    auto hH = host(H);
+    auto hhv = host(hv), hHd = host(Hd);
+    for (size_t x = 0; x < 6; x++) CHECK_CLOSE(hHd(x), hH(x, x) * hhv(x), 1e-14);
+    // index only in C: broadcast (GPUTensorAlgebra.hip:962-995)
+    auto A3 = create_random_gpu_tensor("A3", 3, 3, 4), B3 = create_random_gpu_tensor("B3", 3, 3, 4);
+    DeviceTensor<double, 2> Cb{"Cb", 3, 2};
+    einsum(Indices{i, l}, &Cb, Indices{i, j, k}, A3, Indices{j, i, k}, B3, &alg);
+    CHECK(alg == ta::GENERIC);
+    auto hA3 = host(A3), hB3 = host(B3);
+    auto hCb = host(Cb);
+    for (size_t x = 0; x < 3; x++) {
+        double s = 0;
+        for (size_t y = 0; y < 3; y++) for (size_t z = 0; z < 4; z++) s += hA3(x, y, z) * hB3(y, x, z);
+        for (size_t l0 = 0; l0 < 2; l0++) CHECK_CLOSE(hCb(x, l0), s, 1e-12);
+    }
+}
+
+TEST_CASE(gpu_complex_and_float) {
+    using namespace einsums::index;
+    using Z = std::complex<double>;
+    auto A = create_random_gpu_tensor<Z>("A", 5, 6), B = create_random_gpu_tensor<Z>("B", 6, 4);
+    DeviceTensor<Z, 2> C{"C", 5, 4};
+    AlgorithmChoice    alg;
+    einsum(Indices{i, j}, &C, Indices{i, k}, A, Indices{k, j}, B, &alg);
+    CHECK(alg == ta::GEMM);
+    auto hA = host(A), hB = host(B), hC = host(C);
+    for (size_t x = 0; x < 5; x++) for (size_t y = 0; y < 4; y++) {
+        Z s = 0;
+        for (size_t k0 = 0; k0 < 6; k0++) s += hA(x, k0) * hB(k0, y);
+        CHECK_CLOSE(hC(x, y), s, 1e-12);
+    }
+    einsum<true, false>(Indices{i, j}, &C, Indices{i, k}, A, Indices{k, j}, B, &alg); // conj(A): result must carry the conjugation
+    CHECK(alg == ta::GEMM);
+    hC = host(C);
+    for (size_t x = 0; x < 5; x++) for (size_t y = 0; y < 4; y++) {
+        Z s = 0;
+        for (size_t k0 = 0; k0 < 6; k0++) s += std::conj(hA(x, k0)) * hB(k0, y);
+        CHECK_CLOSE(hC(x, y), s, 1e-12);
+    }
+    auto Af = create_random_gpu_tensor<float>("Af", 33, 17), Bf = create_random_gpu_tensor<float>("Bf", 17, 29);
+    DeviceTensor<float, 2> Cf{"Cf", 33, 29};
+    einsum(Indices{i, j}, &Cf, Indices{i, k}, Af, Indices{k, j}, Bf, &alg);
+    CHECK(alg == ta::GEMM);
+    auto hAf = host(Af), hBf = host(Bf), hCf = host(Cf);
+    for (size_t x = 0; x < 33; x++) for (size_t y = 0; y < 29; y++) {
+        double s = 0;
+        for (size_t k0 = 0; k0 < 17; k0++) s += double(hAf(x, k0)) * double(hBf(k0, y));
+        CHECK_CLOSE(hCf(x, y), s, 1e-5 * 17);
+    }
+}
+
+TEST_CASE(gpu_permute) { // Sort.cpp:18-250, GPUTensorAlgebra.hip:591-838
+    using namespace einsums::index;
+    auto A = create_random_gpu_tensor("A", 3, 4, 5, 6);
+    auto hA = host(A);
+    DeviceTensor<double, 4> B{"B", 6, 5, 4, 3};
+    permute(Indices{l, k, j, i}, &B, Indices{i, j, k, l}, A);
+    auto hB = host(B);
+    for (size_t x = 0; x < 3; x++) for (size_t y = 0; y < 4; y++) for (size_t z = 0; z < 5; z++) for (size_t t = 0; t < 6; t++)
+        CHECK(hB(t, z, y, x) == hA(x, y, z, t));
+    // B[i,l,k,j] = 0.5 * A[k,j,l,i] (Sort.cpp:155-179) with accumulation
+    auto A2 = create_random_gpu_tensor("A2", 3, 3, 3, 3), B2 = create_random_gpu_tensor("B2", 3, 3, 3, 3);
+    auto hA2 = host(A2), h0 = host(B2);
+    permute(2.0, Indices{i, l, k, j}, &B2, 0.5, Indices{k, j, l, i}, A2);
+    auto h1 = host(B2);
+    for (size_t x = 0; x < 3; x++) for (size_t y = 0; y < 3; y++) for (size_t z = 0; z < 3; z++) for (size_t t = 0; t < 3; t++)
+        CHECK_CLOSE(h1(x, t, z, y), 2.0 * h0(x, t, z, y) + 0.5 * hA2(z, y, t, x), 1e-14);
+    // rank 2 transpose and rank 3
+    auto M = create_random_gpu_tensor("M", 37, 53);
+    DeviceTensor<double, 2> Mt{"Mt", 53, 37};
+    transpose(&Mt, M);
+    auto hM = host(M), hMt = host(Mt);
+    for (size_t x = 0; x < 37; x++) for (size_t y = 0; y < 53; y++) CHECK(hMt(y, x) == hM(x, y));
+    // output smaller than input -> dimension_error (DevicePermute.hpp:121-126)
+    DeviceTensor<double, 2> small{"small", 53, 36};
+    CHECK_THROWS_AS(transpose(&small, M), dimension_error);
+}
+
+TEST_CASE(gpu_linear_algebra) { // GPULinearAlgebra.hip: gemm / gemv / ger / scale / axpy / direct_product
+    auto A = create_random_gpu_tensor("A", 8, 6), B = create_random_gpu_tensor("B", 6, 7);
+    DeviceTensor<double, 2> C{"C", 8, 7};
+    C.set_all(1.0);
+    linear_algebra::gemm<false, false>(2.0, A, B, 0.5, &C);
+    auto hA = host(A), hB = host(B), hC = host(C);
+    for (size_t x = 0; x < 8; x++) for (size_t y = 0; y < 7; y++) {
+        double s = 0.5;
+        for (size_t k0 = 0; k0 < 6; k0++) s += 2.0 * hA(x, k0) * hB(k0, y);
+        CHECK_CLOSE(hC(x, y), s, 1e-12);
+    }
+    DeviceTensor<double, 2> Ct{"Ct", 6, 6};
+    linear_algebra::gemm<true, false>(1.0, A, A, 0.0, &Ct); // A^T A
+    auto hCt = host(Ct);
+    for (size_t x = 0; x < 6; x++) for (size_t y = 0; y < 6; y++) {
+        double s = 0;
+        for (size_t k0 = 0; k0 < 8; k0++) s += hA(k0, x) * hA(k0, y);
+        CHECK_CLOSE(hCt(x, y), s, 1e-12);
+    }
+    auto xv = create_random_gpu_tensor("x", 6), yv = create_random_gpu_tensor("y", 8);
+    auto hx = host(xv), hy0 = host(yv);
+    linear_algebra::gemv<false>(1.5, A, xv, 2.0, &yv);
+    auto hy = host(yv);
+    for (size_t r0 = 0; r0 < 8; r0++) {
+        double s = 2.0 * hy0(r0);
+        for (size_t k0 = 0; k0 < 6; k0++) s += 1.5 * hA(r0, k0) * hx(k0);
+        CHECK_CLOSE(hy(r0), s, 1e-12);
+    }
+    auto x8 = create_random_gpu_tensor("x8", 8);
+    DeviceTensor<double, 1> y6{"y6", 6};
+    linear_algebra::gemv<true>(1.0, A, x8, 0.0, &y6);
+    auto hx8 = host(x8), hy6 = host(y6);
+    for (size_t c0 = 0; c0 < 6; c0++) {
+        double s = 0;
+        for (size_t r0 = 0; r0 < 8; r0++) s += hA(r0, c0) * hx8(r0);
+        CHECK_CLOSE(hy6(c0), s, 1e-12);
+    }
+    auto G = create_random_gpu_tensor("G", 8, 6);
+    auto hG0 = host(G);
+    linear_algebra::ger(0.5, x8, xv, &G);
+    auto hG = host(G);
+    for (size_t r0 = 0; r0 < 8; r0++) for (size_t c0 = 0; c0 < 6; c0++) CHECK_CLOSE(hG(r0, c0), hG0(r0, c0) + 0.5 * hx8(r0) * hx(c0), 1e-14);
+    linear_algebra::scale(3.0, &G);
+    auto hG3 = host(G);
+    for (size_t x = 0; x < hG.v.size(); x++) CHECK(hG3.v[x] == 3.0 * hG.v[x]);
+    G *= 0.5;
+    G += A;
+    auto hG4 = host(G);
+    for (size_t x = 0; x < hG.v.size(); x++) CHECK_CLOSE(hG4.v[x], 1.5 * hG.v[x] + hA.v[x], 1e-14);
+    // vendor-layer argument errors keep the reference's exception classes (hipBLASVendor/src/gemm.hip:39-80)
+    double one = 1.0;
+    CHECK(eb200_dgemm(nullptr, 'x', 'n', 2, 2, 2, &one, A.gpu_data(), 2, A.gpu_data(), 2, &one, C.gpu_data(), 2) == EB200_ERR_INVALID_ARGUMENT);
+    CHECK_THROWS_AS(EB200_CHECK(eb200_dgemm(nullptr, 'n', 'n', 4, 2, 2, &one, A.gpu_data(), 2, A.gpu_data(), 2, &one, C.gpu_data(), 4)), std::domain_error);
+}
+
+TEST_CASE(gpu_dimension_errors_and_threads) {
+    using namespace einsums::index;
+    auto A = create_random_gpu_tensor("A", 4, 5), B = create_random_gpu_tensor("B", 6, 3);
+    DeviceTensor<double, 2> C{"C", 4, 3};
+    CHECK_THROWS_AS(einsum(Indices{i, j}, &C, Indices{i, k}, A, Indices{k, j}, B), dimension_error);
+    // concurrent einsum calls from different host threads, each on its own stream (GPUTensorAlgebraTasks.hip:37-52)
+    auto X = create_random_gpu_tensor("X", 64, 64), Y = create_random_gpu_tensor("Y", 64, 64);
+    DeviceTensor<double, 2> C1{"C1", 64, 64}, C2{"C2", 64, 64};
+    std::thread t1([&] { for (int r = 0; r < 20; r++) einsum(Indices{i, j}, &C1, Indices{i, k}, X, Indices{k, j}, Y); });
+    std::thread t2([&] { for (int r = 0; r < 20; r++) einsum(Indices{i, j}, &C2, Indices{i, k}, X, Indices{k, j}, Y); });
+    t1.join();
+    t2.join();
+    auto h1 = host(C1), h2 = host(C2);
+    bool same = true;
+    for (size_t x = 0; x < h1.v.size(); x++) same = same && (h1.v[x] == h2.v[x]);
+    CHECK(same);
+}
+
+int main() {
+    try {
+        einsums::initialize(0);
+    } catch (std::exception const &e) {
+        std::printf("FATAL: no usable device: %s\n", e.what());
+        return 2;
+    }
+    int rc = mini::run_all();
+    einsums::finalize();
+    return rc;
+}
