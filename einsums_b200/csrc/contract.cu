@@ -359,6 +359,7 @@ int full_c_group(const eb200_contract_desc &d, Grp &g) {
         g.n++;
         g.tot *= x.ext;
     }
+    grp_finalize(g);
     return EB200_OK;
 }
 

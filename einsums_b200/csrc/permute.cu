@@ -26,6 +26,7 @@ struct PermArgs {
     void       *C;
     double      alpha[2], beta[2];
     int64_t     tiles_a, tiles_c;
+    uint32_t    cpr_mul, cpr_shift; // fast division by chunks-per-row (row kernel)
 };
 
 template <typename T, bool CONJ> __device__ __forceinline__ T perm_out(T alpha, T a, T beta, T *dst, bool has_beta) {
@@ -83,7 +84,7 @@ template <typename T, bool CONJ, int TILE, int ROWS> __global__ void __launch_bo
 // axis c, 8 independent stores. Needs even extents/strides and 2-element-aligned bases (checked on the host).
 template <typename T> struct alignas(2 * sizeof(T)) Pair { T x, y; };
 
-template <typename T> __global__ void __launch_bounds__(256) permute_tile_vec(const __grid_constant__ PermArgs a) {
+template <typename T> __global__ void __launch_bounds__(256, 3) permute_tile_vec(const __grid_constant__ PermArgs a) {
     constexpr int TILE = 64;
     __shared__ __align__(16) T tile[TILE * TILE];
     const T      *A = reinterpret_cast<const T *>(a.A);
@@ -148,7 +149,7 @@ template <typename T> __global__ void __launch_bounds__(256) permute_tile_vec(co
 }
 
 // row kernel: the same axis is fastest on both sides. VEC elements per thread per step.
-template <typename T, bool CONJ, int VEC> __global__ void __launch_bounds__(256) permute_rows(const __grid_constant__ PermArgs a) {
+template <typename T, bool CONJ, int VEC> __global__ void __launch_bounds__(256, 3) permute_rows(const __grid_constant__ PermArgs a) {
     const T      *A = reinterpret_cast<const T *>(a.A);
     T            *C = reinterpret_cast<T *>(a.C);
     const T       alpha = make_scalar<T>(a.alpha[0], a.alpha[1]), beta = make_scalar<T>(a.beta[0], a.beta[1]);
@@ -161,7 +162,7 @@ template <typename T, bool CONJ, int VEC> __global__ void __launch_bounds__(256)
     auto locate = [&](int64_t x, int64_t &oa, int64_t &oc) {
         int64_t row, ch;
         if (a.rest.tot == 1) { row = 0; ch = x; }
-        else if (total <= 0x7fffffffLL) { uint32_t q = (uint32_t)x / (uint32_t)chunks_per_row; row = q; ch = (uint32_t)x - q * (uint32_t)chunks_per_row; }
+        else if (total <= 0x7fffffffLL) { uint32_t q = fastdiv((uint32_t)x, a.cpr_mul, a.cpr_shift); row = q; ch = (uint32_t)x - q * (uint32_t)chunks_per_row; }
         else { row = x / chunks_per_row; ch = x - row * chunks_per_row; }
         grp_offset2(a.rest, row, ROLE_A, ROLE_C, oa, oc);
         oa += ch * VEC * (VEC > 1 ? 1 : a.sa_a);
@@ -253,11 +254,13 @@ int permute_impl(void *stream, int rank, const int64_t *dimsA, const int64_t *st
         pa.ea = ax[ia].ext; pa.sa_a = ax[ia].sa; pa.sc_a = ax[ia].sc;
         for (size_t i = 0; i < ax.size(); i++)
             if (i != ia && !push_rest(ax[i])) return fail(EB200_ERR_UNSUPPORTED, "permute: more than %d non-mergeable axes", MAXG + 2);
+        grp_finalize(pa.rest);
         constexpr int VEC = 16 / sizeof(T) > 1 ? 16 / sizeof(T) : 1;
         bool          vec_ok = VEC > 1 && pa.sa_a == 1 && pa.sc_a == 1 && pa.ea % VEC == 0 && ((uintptr_t)A % 16 == 0) && ((uintptr_t)C % 16 == 0);
         for (int i = 0; i < pa.rest.n && vec_ok; i++)
             if (pa.rest.s[ROLE_A][i] % VEC || pa.rest.s[ROLE_C][i] % VEC) vec_ok = false;
         int64_t chunks = ((pa.ea + (vec_ok ? VEC : 1) - 1) / (vec_ok ? VEC : 1)) * pa.rest.tot;
+        fastdiv_init((pa.ea + (vec_ok ? VEC : 1) - 1) / (vec_ok ? VEC : 1), pa.cpr_mul, pa.cpr_shift);
         int     grid = (int)std::max<int64_t>(1, std::min<int64_t>((chunks + 255) / 256, (int64_t)sm_count() * 16));
         if (vec_ok) {
             if (cj) permute_rows<T, true, VEC><<<grid, 256, 0, s>>>(pa);
@@ -272,6 +275,7 @@ int permute_impl(void *stream, int rank, const int64_t *dimsA, const int64_t *st
         pa.ec = ax[ic].ext; pa.sa_c = ax[ic].sa; pa.sc_c = ax[ic].sc;
         for (size_t i = 0; i < ax.size(); i++)
             if (i != ia && i != ic && !push_rest(ax[i])) return fail(EB200_ERR_UNSUPPORTED, "permute: more than %d non-mergeable axes", MAXG + 2);
+        grp_finalize(pa.rest);
         if constexpr (!Scalar<T>::is_complex) {
             bool vec_ok = !cj && pa.sa_a == 1 && pa.sc_c == 1 && pa.ea % 2 == 0 && pa.ec % 2 == 0 && pa.sa_c % 2 == 0 && pa.sc_a % 2 == 0 &&
                           ((uintptr_t)A % (2 * sizeof(T)) == 0) && ((uintptr_t)C % (2 * sizeof(T)) == 0);

@@ -18,6 +18,7 @@ struct Idx {
 inline void grp_clear(Grp &g) {
     memset(&g, 0, sizeof(g));
     g.tot = 1;
+    grp_finalize(g);
 }
 
 inline bool grp_push(Grp &g, const Idx &x) {
@@ -62,6 +63,7 @@ bool build(Grp &g, std::vector<Idx> v, int r0, int r1) {
     grp_clear(g);
     for (auto &x : v)
         if (!grp_push(g, x)) return false;
+    grp_finalize(g);
     return true;
 }
 

@@ -20,7 +20,28 @@ struct Grp {
     int64_t tot;              // product of extents
     int64_t ext[MAXG];        // inner-first
     int64_t s[3][MAXG];       // element strides per tensor: [0]=A, [1]=B, [2]=C (0 when absent)
+    // division by ext[i] as multiply+shift, valid for dividends < 2^31 (used when tot < 2^31): q = (n * fmul) >> fshift
+    uint32_t fmul[MAXG];
+    uint32_t fshift[MAXG];
 };
+
+// Granlund-Montgomery round-up constants for n < 2^31: s = ceil(log2 d), M = ceil(2^(31+s) / d) < 2^32 + ...
+inline void fastdiv_init(int64_t d, uint32_t &mul, uint32_t &shift) {
+    if (d <= 0 || d > 0x7fffffffLL) { mul = 0; shift = 0; return; }
+    int s = 0;
+    while ((1LL << s) < d) s++;
+    shift = 31 + s;
+    unsigned __int128 num = (unsigned __int128)1 << shift;
+    mul = (uint32_t)((num + (unsigned __int128)d - 1) / (unsigned __int128)d);
+}
+inline void grp_finalize(Grp &g) {
+    for (int i = 0; i < MAXG; i++) {
+        g.fmul[i] = 0;
+        g.fshift[i] = 0;
+        if (i < g.n) fastdiv_init(g.ext[i], g.fmul[i], g.fshift[i]);
+    }
+}
+__host__ __device__ inline uint32_t fastdiv(uint32_t n, uint32_t mul, uint32_t shift) { return (uint32_t)(((uint64_t)n * mul) >> shift); }
 
 enum { ROLE_A = 0, ROLE_B = 1, ROLE_C = 2 };
 
@@ -62,7 +83,7 @@ __host__ __device__ inline void grp_offset2(const Grp &g, int64_t x, int r0, int
         uint32_t y = (uint32_t)x;
         for (int i = 0; i < g.n; i++) {
             uint32_t e = (uint32_t)g.ext[i];
-            uint32_t q = y / e;
+            uint32_t q = fastdiv(y, g.fmul[i], g.fshift[i]);
             uint32_t r = y - q * e;
             o0 += (int64_t)r * g.s[r0][i];
             o1 += (int64_t)r * g.s[r1][i];
@@ -85,7 +106,7 @@ __host__ __device__ inline void grp_offset3(const Grp &g, int64_t x, int64_t &oa
         uint32_t y = (uint32_t)x;
         for (int i = 0; i < g.n; i++) {
             uint32_t e = (uint32_t)g.ext[i];
-            uint32_t q = y / e;
+            uint32_t q = fastdiv(y, g.fmul[i], g.fshift[i]);
             uint32_t r = y - q * e;
             oa += (int64_t)r * g.s[0][i];
             ob += (int64_t)r * g.s[1][i];
