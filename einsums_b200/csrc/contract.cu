@@ -3,6 +3,7 @@
 // (reference: libs/Einsums/TensorAlgebra/include/Einsums/TensorAlgebra/Backends/GPUTensorAlgebra.hpp:200-342).
 #include "contract.cuh"
 #include "contract_kernels.cuh"
+#include "gemm_tma.cuh"
 
 #include <algorithm>
 #include <mutex>
@@ -129,6 +130,111 @@ template <typename T> int launch_simt_conj(cudaStream_t s, TileArgs &args, dim3 
     return launch_simt<T, false, false>(s, args, grid);
 }
 
+// ---------------------------------------------------------------- TMA fast path (plain FP64 GEMM)
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void                           *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+int g_use_tma = -1; // EB200_USE_TMA=0 disables the TMA path (A/B comparisons)
+
+// 2-D map over an operand: dim0 = the unit-stride direction, dim1 = the other one (ld elements apart)
+bool make_operand_map(CUtensorMap *map, const double *base, int64_t inner, int64_t outer, int64_t ld, uint32_t box_inner, uint32_t box_outer) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t es[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// returns 1 when the TMA kernel ran, 0 when the shape does not qualify, <0 on error
+int try_run_tma(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const double beta_eff[2]) {
+    if (g_use_tma < 0) {
+        const char *e = getenv("EB200_USE_TMA");
+        g_use_tma = e ? atoi(e) : 1;
+    }
+    if (!g_use_tma || d.force_kernel != 0 && d.force_kernel != EB200_KF_TILE_MMA) return 0;
+    if (p.b.n != 0 || p.m.n != 1 || p.n.n != 1 || p.k.n != 1) return 0;
+    const double *A = (const double *)d.A.data, *B = (const double *)d.B.data;
+    const int64_t M = p.m.tot, N = p.n.tot, K = p.k.tot;
+    const int64_t sAm = p.m.s[ROLE_A][0], sAk = p.k.s[ROLE_A][0], sBn = p.n.s[ROLE_B][0], sBk = p.k.s[ROLE_B][0];
+    const bool    ak = (sAk == 1), bk = (sBk == 1);
+    if (!ak && sAm != 1) return 0;
+    if (!bk && sBn != 1) return 0;
+    const int64_t lda = ak ? sAm : sAk, ldb = bk ? sBn : sBk;
+    if (lda <= 0 || ldb <= 0 || (lda & 1) || (ldb & 1) || ((uintptr_t)A % 16) || ((uintptr_t)B % 16)) return 0;
+    if (M >= (1LL << 31) || N >= (1LL << 31) || K >= (1LL << 31) || lda >= (1LL << 36) || ldb >= (1LL << 36)) return 0;
+    // an extent-1 "other" direction makes ld meaningless but harmless; TMA needs ld*8 to be a multiple of 16 (checked) and >= inner*8
+    if ((ak ? K : M) > lda && (ak ? M : K) > 1) return 0;
+    if ((bk ? K : N) > ldb && (bk ? N : K) > 1) return 0;
+
+    CUtensorMap tmA, tmB;
+    if (!(ak ? make_operand_map(&tmA, A, K, M, lda, 16, 128) : make_operand_map(&tmA, A, M, K, lda, 16, 16))) return 0;
+    if (!(bk ? make_operand_map(&tmB, B, K, N, ldb, 16, 64) : make_operand_map(&tmB, B, N, K, ldb, 16, 16))) return 0;
+
+    TmaGemmArgs a;
+    a.M = M; a.N = N; a.K = K;
+    a.sCm = p.m.s[ROLE_C][0]; a.sCn = p.n.s[ROLE_C][0];
+    a.C = (double *)d.C.data;
+    a.ws = nullptr;
+    a.alpha = d.alpha[0]; a.beta = beta_eff[0];
+    const int64_t tm = (M + 127) / 128, tn = (N + 63) / 64;
+    if (tm * tn > 0x7fffffffLL) return 0;
+    a.tiles_m = (int)tm; a.tiles_n = (int)tn;
+    a.vec_c = (a.sCn == 1 && !(N & 1) && !(a.sCm & 1) && ((uintptr_t)a.C % 16) == 0) ? 1 : 0;
+    const int64_t KT = (K + 15) / 16, tiles = tm * tn;
+    int           splits = 1;
+    if (d.split_k > 0) splits = d.split_k;
+    else {
+        const int64_t target = (int64_t)sm_count() * 2;
+        if (tiles * 2 <= target) splits = (int)std::min<int64_t>(target / tiles, std::max<int64_t>(1, KT / 8));
+    }
+    splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(splits, KT), 65535));
+    a.splits = splits;
+    d.split_k = splits;
+    void *ws = nullptr;
+    if (splits > 1) {
+        int rc = ws_alloc(&ws, (size_t)splits * M * N * sizeof(double), s);
+        if (rc) return -rc;
+        a.ws = (double *)ws;
+    }
+    static const size_t smem_pad = getenv("EB200_TMA_SMEM_PAD") ? (size_t)atoi(getenv("EB200_TMA_SMEM_PAD")) : 0; // debugging: forces 1 CTA/SM
+    const size_t        SMEM = 4 * (128 * 16 * 8 + 64 * 16 * 8) + 1024 + 64 + smem_pad;
+    dim3             grid((unsigned)tiles, (unsigned)splits, 1);
+#define EB_TMA_CASE(AK, BK_)                                                                                  \
+    {                                                                                                         \
+        auto        kern = gemm_tma_f64<AK, BK_>;                                                             \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);   \
+        if (e != cudaSuccess) return -cuda_fail(e, "cudaFuncSetAttribute(gemm_tma_f64)");                     \
+        kern<<<grid, 256, SMEM, s>>>(tmA, tmB, a);                                                            \
+    }
+    if (ak && bk) EB_TMA_CASE(true, true)
+    else if (ak && !bk) EB_TMA_CASE(true, false)
+    else if (!ak && bk) EB_TMA_CASE(false, true)
+    else EB_TMA_CASE(false, false)
+#undef EB_TMA_CASE
+    launch_counter()++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return -cuda_fail(e, "gemm_tma_f64");
+    d.launches++;
+    if (splits > 1) {
+        int rc = launch_finalize<double>(s, p.b, p.m, p.n, ws, d.C.data, d.alpha, beta_eff, splits, d);
+        if (rc) return -rc;
+        cudaError_t fe = cudaFreeAsync(ws, s);
+        if (fe != cudaSuccess) return -cuda_fail(fe, "cudaFreeAsync");
+    }
+    return 1;
+}
+
 template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const double beta_eff[2]) {
     TileArgs args;
     args.p = p;
@@ -142,6 +248,13 @@ template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract
     args.vec_ab = 0; args.vec_c = 0;
 
     const bool mma = (p.family == EB200_KF_TILE_MMA);
+    if constexpr (std::is_same_v<T, double>) {
+        if (mma) {
+            int r = try_run_tma(s, p, d, beta_eff);
+            if (r == 1) return EB200_OK;
+            if (r < 0) return -r;
+        }
+    }
     int bm, bn, bk, ctas_per_sm;
     std::call_once(g_cfg_once, [] {
         const char *e = getenv("EB200_MMA_CONFIG");
