@@ -341,6 +341,15 @@ template <typename T> int reduce_seg_mode(const ReduceArgs &a) {
 template <typename T, int NN, bool CA, bool CB> int launch_reduce_nn(cudaStream_t s, bool row, ReduceArgs &a, dim3 grid) {
     if (row) {
         int mode = reduce_seg_mode<T>(a);
+        a.flat_lanes = 0;
+        if (mode >= 1) {
+            const int64_t vec = (mode == 2) ? 2 : 1, ppr = a.k.ext[0] / vec;
+            // flat lane mapping only where whole-warp chunks would leave lanes idle (run length not a multiple of 32 packs)
+            if (a.k.tot / vec < 0x7fffffffLL && a.k.ext[0] % vec == 0 && (ppr % 32) != 0) {
+                a.flat_lanes = 1;
+                fastdiv_init(ppr, a.ppr_mul, a.ppr_shift);
+            }
+        }
         if (mode == 2) {
             if constexpr (sizeof(T) <= 8) row_reduce_seg<T, NN, 4, 2, CA, CB><<<grid, 256, 0, s>>>(a);
         } else if (mode == 1) {
@@ -512,12 +521,131 @@ template <typename T> int contract_typed(cudaStream_t s, eb200_contract_desc &d)
     }
 }
 
+// ---------------------------------------------------------------- mixed element types
+// The reference sends contractions whose tensors differ in value type (d<-f,d; f<-d,d; cd<-cd,d ...) to its generic kernel
+// (Dispatch.hpp:896-899) and multiplies in the wider type. Here the narrower operands are widened into dense scratch
+// copies (stream-ordered allocations) and the same-type engine runs in the promoted type; a narrower C is widened,
+// updated and narrowed back. Rare path (tests and MixedPrecision-style calls), two small extra kernels.
+template <typename S, typename D> __device__ __forceinline__ D convert_scalar(S v) {
+    if constexpr (Scalar<S>::is_complex && Scalar<D>::is_complex) return make_scalar<D>((double)v.x, (double)v.y);
+    else if constexpr (Scalar<S>::is_complex) return make_scalar<D>((double)v.x, 0.0); // complex -> real keeps the real part
+    else return make_scalar<D>((double)v, 0.0);
+}
+struct ConvArgs {
+    Grp         g; // ROLE_A = source strides, ROLE_C = destination strides
+    const void *src;
+    void       *dst;
+};
+template <typename S, typename D> __global__ void __launch_bounds__(256) convert_tensor(const __grid_constant__ ConvArgs a) {
+    const S *src = reinterpret_cast<const S *>(a.src);
+    D       *dst = reinterpret_cast<D *>(a.dst);
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < a.g.tot; x += (int64_t)gridDim.x * blockDim.x) {
+        int64_t os, od;
+        grp_offset2(a.g, x, ROLE_A, ROLE_C, os, od);
+        dst[od] = convert_scalar<S, D>(src[os]);
+    }
+}
+template <typename S, typename D> int launch_convert(cudaStream_t s, const ConvArgs &a) {
+    convert_tensor<S, D><<<grid_for(a.g.tot, 256), 256, 0, s>>>(a);
+    EB_POST_LAUNCH("convert_tensor");
+    return EB200_OK;
+}
+template <typename S> int launch_convert_to(cudaStream_t s, int dst_dtype, const ConvArgs &a) {
+    switch (dst_dtype) {
+    case EB200_F32: return launch_convert<S, float>(s, a);
+    case EB200_F64: return launch_convert<S, double>(s, a);
+    case EB200_C64: return launch_convert<S, float2>(s, a);
+    default: return launch_convert<S, double2>(s, a);
+    }
+}
+int launch_convert_any(cudaStream_t s, int src_dtype, int dst_dtype, const ConvArgs &a) {
+    switch (src_dtype) {
+    case EB200_F32: return launch_convert_to<float>(s, dst_dtype, a);
+    case EB200_F64: return launch_convert_to<double>(s, dst_dtype, a);
+    case EB200_C64: return launch_convert_to<float2>(s, dst_dtype, a);
+    default: return launch_convert_to<double2>(s, dst_dtype, a);
+    }
+}
+size_t dtype_size(int dt) { return dt == EB200_F32 ? 4 : (dt == EB200_C128 ? 16 : 8); }
+
+// dense row-major strides over the tensor's own axes; group for a strided<->dense copy
+int axes_group(const eb200_contract_desc &d, const eb200_tensor_desc &t, int64_t *dense, Grp &g, bool to_dense) {
+    memset(&g, 0, sizeof(g));
+    g.tot = 1;
+    if (t.rank > MAXG) return fail(EB200_ERR_UNSUPPORTED, "contract: mixed-type tensors of rank > %d are not supported", MAXG);
+    int64_t acc = 1;
+    for (int a = t.rank - 1; a >= 0; a--) {
+        dense[a] = acc;
+        acc *= d.extent[t.index[a]];
+    }
+    for (int a = t.rank - 1; a >= 0; a--) { // inner-first
+        int i = g.n++;
+        g.ext[i] = d.extent[t.index[a]];
+        g.s[ROLE_A][i] = to_dense ? t.stride[a] : dense[a];
+        g.s[ROLE_C][i] = to_dense ? dense[a] : t.stride[a];
+        g.tot *= g.ext[i];
+    }
+    grp_finalize(g);
+    return EB200_OK;
+}
+
+int contract_mixed(cudaStream_t s, eb200_contract_desc &d) {
+    const int  dts[3] = {d.C.dtype, d.A.dtype, d.B.dtype};
+    const bool any_c = dts[0] >= EB200_C64 || dts[1] >= EB200_C64 || dts[2] >= EB200_C64;
+    const bool any_d = (dts[0] & 1) || (dts[1] & 1) || (dts[2] & 1); // F64 = 1, C128 = 3
+    const int  W = any_c ? (any_d ? EB200_C128 : EB200_C64) : (any_d ? EB200_F64 : EB200_F32);
+    eb200_contract_desc w = d;
+    void               *tmp[3] = {nullptr, nullptr, nullptr};
+    eb200_tensor_desc  *ts[3] = {&w.C, &w.A, &w.B};
+    const eb200_tensor_desc *os[3] = {&d.C, &d.A, &d.B};
+    Grp                 back; // dense -> strided for C
+    int                 rc = EB200_OK;
+    for (int i = 0; i < 3 && rc == EB200_OK; i++) {
+        if (os[i]->dtype == W) continue;
+        int64_t dense[EB200_MAX_RANK];
+        Grp     g;
+        if ((rc = axes_group(d, *os[i], dense, g, true))) break;
+        if (g.tot == 0) continue;
+        cudaError_t e = cudaMallocAsync(&tmp[i], (size_t)g.tot * dtype_size(W), s);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMallocAsync(mixed)"); break; }
+        const bool need_values = (i != 0) || !(d.beta[0] == 0.0 && d.beta[1] == 0.0);
+        if (need_values) {
+            ConvArgs ca{g, os[i]->data, tmp[i]};
+            rc = launch_convert_any(s, os[i]->dtype, W, ca);
+            d.launches++;
+        }
+        ts[i]->data = tmp[i];
+        ts[i]->dtype = W;
+        for (int a = 0; a < os[i]->rank; a++) ts[i]->stride[a] = dense[a];
+        if (i == 0) axes_group(d, *os[i], dense, back, false);
+    }
+    if (rc == EB200_OK) {
+        int l0 = d.launches;
+        rc = contract_dispatch(s, w);
+        d.kernel_used = w.kernel_used;
+        d.split_k = w.split_k;
+        d.launches = l0 + w.launches;
+    }
+    if (rc == EB200_OK && tmp[0]) {
+        ConvArgs ca{back, tmp[0], d.C.data};
+        rc = launch_convert_any(s, W, d.C.dtype, ca);
+        d.launches++;
+    }
+    for (int i = 0; i < 3; i++)
+        if (tmp[i]) cudaFreeAsync(tmp[i], s);
+    return rc;
+}
+
 } // namespace
 
 int contract_dispatch(cudaStream_t s, eb200_contract_desc &d) {
-    if (d.A.dtype != d.C.dtype || d.B.dtype != d.C.dtype)
-        return fail(EB200_ERR_UNSUPPORTED, "contract: mixed element types (C=%d A=%d B=%d) are not supported by this build", d.C.dtype, d.A.dtype,
-                    d.B.dtype);
+    if (d.A.dtype != d.C.dtype || d.B.dtype != d.C.dtype) {
+        for (int dt : {d.C.dtype, d.A.dtype, d.B.dtype})
+            if (dt < EB200_F32 || dt > EB200_C128) return fail(EB200_ERR_INVALID_ARGUMENT, "contract: bad dtype %d", dt);
+        if (d.n_unique < 0 || d.n_unique > EB200_MAX_UNIQUE) return fail(EB200_ERR_INVALID_ARGUMENT, "contract: n_unique out of range");
+        d.launches = 0;
+        return contract_mixed(s, d);
+    }
     switch (d.C.dtype) {
     case EB200_F32: return contract_typed<float>(s, d);
     case EB200_F64: return contract_typed<double>(s, d);

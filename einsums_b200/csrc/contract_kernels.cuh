@@ -447,6 +447,8 @@ struct ReduceArgs {
     double      alpha[2], beta[2];
     int32_t     splits;
     int32_t     conj_a, conj_b;
+    uint32_t    ppr_mul, ppr_shift; // fast division by (k.ext[0] / VEC): packs per inner run (row_reduce_seg, flat lane mapping)
+    int32_t     flat_lanes;         // 1: lanes enumerate (ko, pack) pairs linearly (no idle lanes on short runs)
 };
 
 // row_reduce: block = RB consecutive rows x one K segment. Lanes run along k (contiguous in A).
@@ -610,23 +612,48 @@ __global__ void __launch_bounds__(256, (NN * RB * sizeof(T) <= 64 ? 3 : 1)) row_
 
     struct alignas(sizeof(T) * VEC) Pack { T v[VEC]; };
 
-    for (int64_t u = u_begin + warp; u < u_end; u += NW) {
-        int64_t ko, ch;
-        if (chunks == 1) { ko = u; ch = 0; }
-        else if (units <= 0x7fffffffLL) { uint32_t q = (uint32_t)u / (uint32_t)chunks; ko = q; ch = (uint32_t)u - q * (uint32_t)chunks; }
-        else { ko = u / chunks; ch = u - ko * chunks; }
+    // flat mapping: one "pack" (VEC elements) per lane, packs of all runs enumerated linearly; segmented mapping: a warp owns
+    // one 32-pack chunk of one run. Both share the body below.
+    const int64_t ppr = E0 / VEC;                                   // packs per run (flat mapping needs E0 % VEC == 0)
+    const int64_t total_packs = KO * ppr;
+    const int64_t it_begin = a.flat_lanes ? (total_packs + 31) / 32 * split / a.splits : u_begin;
+    const int64_t it_end = a.flat_lanes ? (total_packs + 31) / 32 * (split + 1) / a.splits : u_end;
+    for (int64_t u = it_begin + warp; u < it_end; u += NW) {
+        int64_t ko, ki;
+        if (a.flat_lanes) {
+            const int64_t idx = u * 32 + lane;
+            if (idx >= total_packs) continue;
+            const uint32_t q = fastdiv((uint32_t)idx, a.ppr_mul, a.ppr_shift);
+            ko = q;
+            ki = ((uint32_t)idx - q * (uint32_t)ppr) * VEC;
+        } else {
+            int64_t ch;
+            if (chunks == 1) { ko = u; ch = 0; }
+            else if (units <= 0x7fffffffLL) { uint32_t q = (uint32_t)u / (uint32_t)chunks; ko = q; ch = (uint32_t)u - q * (uint32_t)chunks; }
+            else { ko = u / chunks; ch = u - ko * chunks; }
+            ki = ch * CH + (int64_t)lane * VEC;
+            if (ki >= E0) continue;
+        }
         int64_t offA = 0, offB = 0;
         if (a.k.n > 1) { // decode the outer K indices (index 0 is the inner run)
-            int64_t x = ko;
-            for (int i = 1; i < a.k.n; i++) {
-                int64_t q = x / a.k.ext[i], r = x - q * a.k.ext[i];
-                offA += r * a.k.s[ROLE_A][i];
-                offB += r * a.k.s[ROLE_B][i];
-                x = q;
+            if (a.k.tot <= 0x7fffffffLL) {
+                uint32_t x = (uint32_t)ko;
+                for (int i = 1; i < a.k.n; i++) {
+                    uint32_t q = (i + 1 < a.k.n) ? fastdiv(x, a.k.fmul[i], a.k.fshift[i]) : 0u, r = x - q * (uint32_t)a.k.ext[i];
+                    offA += (int64_t)r * a.k.s[ROLE_A][i];
+                    offB += (int64_t)r * a.k.s[ROLE_B][i];
+                    x = q;
+                }
+            } else {
+                int64_t x = ko;
+                for (int i = 1; i < a.k.n; i++) {
+                    int64_t q = x / a.k.ext[i], r = x - q * a.k.ext[i];
+                    offA += r * a.k.s[ROLE_A][i];
+                    offB += r * a.k.s[ROLE_B][i];
+                    x = q;
+                }
             }
         }
-        const int64_t ki = ch * CH + (int64_t)lane * VEC;
-        if (ki >= E0) continue;
         Pack av[RB];
         if constexpr (VEC > 1) {
 #pragma unroll

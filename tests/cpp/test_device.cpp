@@ -311,6 +311,31 @@ TEST_CASE(gpu_complex_and_float) {
     }
 }
 
+TEST_CASE(gpu_mixed_precision) { // GPUTensorAlgebra.hip:2301-2354: d-f-d, d-f-f, f-d-d, cd-cd-d (always GENERIC)
+    using namespace einsums::index;
+    auto run = [&](auto tc, auto ta, auto tb) {
+        using TC = decltype(tc); using TA = decltype(ta); using TB = decltype(tb);
+        auto A = create_random_gpu_tensor<TA>("A", 10, 10);
+        auto B = create_random_gpu_tensor<TB>("B", 10, 10);
+        DeviceTensor<TC, 2> C{"C", 10, 10};
+        C.zero();
+        AlgorithmChoice alg;
+        einsum(Indices{i, j}, &C, Indices{i, k}, A, Indices{k, j}, B, &alg);
+        CHECK(alg == ((std::is_same_v<TC, TA> && std::is_same_v<TC, TB>) ? ta::GEMM : ta::GENERIC));
+        auto hA = host(A); auto hB = host(B); auto hC = host(C);
+        for (size_t x = 0; x < 10; x++) for (size_t y = 0; y < 10; y++) {
+            std::complex<double> s = 0;
+            for (size_t k0 = 0; k0 < 10; k0++) s += std::complex<double>(hA(x, k0)) * std::complex<double>(hB(k0, y));
+            CHECK_CLOSE(std::complex<double>(hC(x, y)), s, 1e-4);
+        }
+    };
+    run(double{}, float{}, double{});
+    run(double{}, float{}, float{});
+    run(float{}, double{}, double{});
+    run(std::complex<double>{}, std::complex<double>{}, double{});
+    run(double{}, double{}, double{});
+}
+
 TEST_CASE(gpu_permute) { // Sort.cpp:18-250, GPUTensorAlgebra.hip:591-838
     using namespace einsums::index;
     auto A = create_random_gpu_tensor("A", 3, 4, 5, 6);

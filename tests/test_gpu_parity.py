@@ -126,6 +126,29 @@ def test_contract_mid_other_types(gpu, oracle, dtype):
         run_case(gpu, oracle, c_idx, a_idx, b_idx, ext, dtype, 0.25, 1.0, seed=21)
 
 
+@pytest.mark.parametrize("tc,ta,tb", [(np.float64, np.float32, np.float64), (np.float64, np.float32, np.float32), (np.float32, np.float64, np.float64),
+                                      (np.complex128, np.complex128, np.float64), (np.complex64, np.float32, np.complex64)])
+def test_contract_mixed_types(gpu, tc, ta, tb):
+    """MixedPrecision.cpp:43-58 / GPUTensorAlgebra.hip:2334-2354 (d-f-d, d-f-f, f-d-d, cd-cd-d): operands are widened on the device,
+    the product is formed in the promoted type. Reference tolerance there is 1e-4 absolute; we hold 1e-5 relative."""
+    rng = np.random.default_rng(33)
+    for (c_idx, a_idx, b_idx, ext) in (("ij", "ik", "kj", dict(i=10, j=10, k=10)), ("pq", "prqs", "rs", dict(p=6, q=7, r=5, s=9)),
+                                       ("", "ij", "ij", dict(i=7, j=9)), ("ij", "ij", "ij", dict(i=7, j=9))):
+        A = rand(rng, tuple(ext[x] for x in a_idx), ta)
+        B = rand(rng, tuple(ext[x] for x in b_idx), tb)
+        C0 = rand(rng, tuple(ext[x] for x in c_idx), tc)
+        for alpha, beta in ((1.0, 0.0), (0.5, 2.0)):
+            wide = np.result_type(tc, ta, tb, np.float64)
+            ref = (beta * C0.astype(wide) if beta else 0) + alpha * np.einsum(f"{a_idx},{b_idx}->{c_idx}", A.astype(wide), B.astype(wide))
+            if np.dtype(tc).kind != "c":
+                ref = np.real(ref)
+            Cd = dev(C0)
+            gpu.contract(c_idx, Cd, a_idx, dev(A), b_idx, dev(B), alpha, beta)
+            got = Cd.cpu().numpy()
+            assert got.dtype == np.dtype(tc)
+            assert rel_err(got.astype(wide), np.asarray(ref)) <= 1e-5, f"{np.dtype(tc)}<-{np.dtype(ta)},{np.dtype(tb)} {c_idx}<-{a_idx},{b_idx}"
+
+
 def test_contract_strided_views(gpu, oracle):
     """Views with padding (Einsum1.cpp:96-140, Einsum7.cpp:195-210): strides are honoured, bytes outside the view untouched."""
     rng = np.random.default_rng(4)
