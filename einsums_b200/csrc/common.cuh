@@ -114,6 +114,12 @@ template <bool CONJ, typename T> __device__ __forceinline__ T maybe_conj(T a) {
     else return a;
 }
 
+// run-time conjugation switch (uniform flag); identity for real types
+template <typename T> __device__ __forceinline__ T conj_if(T a, bool flag) {
+    if constexpr (Scalar<T>::is_complex) return flag ? conj_(a) : a;
+    else return a;
+}
+
 // out = alpha*v (+ beta*old when beta != 0). `has_beta` is uniform.
 template <typename T> __device__ __forceinline__ T axpby_(T alpha, T v, T beta, T old, bool has_beta) {
     T r = mul_(alpha, v);

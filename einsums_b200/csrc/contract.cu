@@ -4,6 +4,7 @@
 #include "contract.cuh"
 #include "contract_kernels.cuh"
 #include "gemm_tma.cuh"
+#include "launch_api.cuh"
 
 #include <algorithm>
 #include <mutex>
@@ -49,8 +50,7 @@ template <typename T> int launch_scale(cudaStream_t s, const Grp &t, void *C, co
     a.beta[0] = beta[0];
     a.beta[1] = beta[1];
     if (t.tot == 0) return EB200_OK;
-    scale_tensor<T><<<grid_for(t.tot, 256), 256, 0, s>>>(a);
-    EB_POST_LAUNCH("scale_tensor");
+    { int rc_ = k_launch_scale(Scalar<T>::dtype, s, a, grid_for(t.tot, 256)); if (rc_) return rc_; }
     d.launches++;
     return EB200_OK;
 }
@@ -65,39 +65,13 @@ int launch_finalize(cudaStream_t s, const Grp &gb, const Grp &gm, const Grp &gn,
     a.beta[0] = beta[0];   a.beta[1] = beta[1];
     a.splits = splits;
     int64_t total = gb.tot * gm.tot * gn.tot;
-    splitk_finalize<T><<<grid_for(total, 256), 256, 0, s>>>(a);
-    EB_POST_LAUNCH("splitk_finalize");
+    { int rc_ = k_launch_finalize(Scalar<T>::dtype, s, a, grid_for(total, 256)); if (rc_) return rc_; }
     d.launches++;
     return EB200_OK;
 }
 
 // ---------------------------------------------------------------- tile kernels
 struct TileChoice { int bm, bn, bk, per_sm; };
-
-template <int BM, int BN, int BK, int WM, int WN, int STAGES, int MINB, bool VEC>
-int launch_mma_vec(cudaStream_t s, TileArgs &args, dim3 grid) {
-    const bool ak = args.p.a_kmajor, bk = args.p.b_kmajor;
-#define EB_MMA_CASE(AK, BKM)                                                                          \
-    {                                                                                                 \
-        using Cfg = TileCfg<BM, BN, BK, WM, WN, STAGES, AK, BKM>;                                     \
-        auto kern = tile_mma_f64<BM, BN, BK, WM, WN, STAGES, AK, BKM, MINB, VEC>;                     \
-        int  rc = set_smem(kern, Cfg::SMEM);                                                          \
-        if (rc) return rc;                                                                            \
-        kern<<<grid, Cfg::NT, Cfg::SMEM, s>>>(args);                                                  \
-    }
-    if (ak && bk) EB_MMA_CASE(true, true)
-    else if (ak && !bk) EB_MMA_CASE(true, false)
-    else if (!ak && bk) EB_MMA_CASE(false, true)
-    else EB_MMA_CASE(false, false)
-#undef EB_MMA_CASE
-    EB_POST_LAUNCH("tile_mma_f64");
-    return EB200_OK;
-}
-template <int BM, int BN, int BK, int WM, int WN, int STAGES, int MINB>
-int launch_mma_cfg(cudaStream_t s, TileArgs &args, dim3 grid) {
-    if (args.vec_ab) return launch_mma_vec<BM, BN, BK, WM, WN, STAGES, MINB, true>(s, args, grid);
-    return launch_mma_vec<BM, BN, BK, WM, WN, STAGES, MINB, false>(s, args, grid);
-}
 
 inline bool even(int64_t x) { return (x & 1) == 0; }
 // every stride of `role` in group g is even, except index `skip` (-1: none)
@@ -115,20 +89,6 @@ bool operand_pairs_ok(const Plan &p, int role, const Grp &fast, const Grp &other
 
 int g_mma_config = 0; // 0 = auto; 1 = 128x128 (1 CTA/SM); 2 = 128x64 (2 CTA/SM). Tuning hook (EB200_MMA_CONFIG).
 std::once_flag g_cfg_once;
-
-template <typename T, bool CA, bool CB> int launch_simt(cudaStream_t s, TileArgs &args, dim3 grid) {
-    tile_simt<T, CA, CB><<<grid, 256, 0, s>>>(args);
-    EB_POST_LAUNCH("tile_simt");
-    return EB200_OK;
-}
-template <typename T> int launch_simt_conj(cudaStream_t s, TileArgs &args, dim3 grid) {
-    if constexpr (Scalar<T>::is_complex) {
-        if (args.conj_a && args.conj_b) return launch_simt<T, true, true>(s, args, grid);
-        if (args.conj_a) return launch_simt<T, true, false>(s, args, grid);
-        if (args.conj_b) return launch_simt<T, false, true>(s, args, grid);
-    }
-    return launch_simt<T, false, false>(s, args, grid);
-}
 
 // ---------------------------------------------------------------- TMA fast path (plain FP64 GEMM)
 using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -210,21 +170,10 @@ int try_run_tma(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const dou
     static const size_t smem_pad = getenv("EB200_TMA_SMEM_PAD") ? (size_t)atoi(getenv("EB200_TMA_SMEM_PAD")) : 0; // debugging: forces 1 CTA/SM
     const size_t        SMEM = 4 * (128 * 16 * 8 + 64 * 16 * 8) + 1024 + 64 + smem_pad;
     dim3             grid((unsigned)tiles, (unsigned)splits, 1);
-#define EB_TMA_CASE(AK, BK_)                                                                                  \
-    {                                                                                                         \
-        auto        kern = gemm_tma_f64<AK, BK_>;                                                             \
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);   \
-        if (e != cudaSuccess) return -cuda_fail(e, "cudaFuncSetAttribute(gemm_tma_f64)");                     \
-        kern<<<grid, 256, SMEM, s>>>(tmA, tmB, a);                                                            \
+    {
+        int rc_ = k_launch_tma(s, tmA, tmB, a, grid, SMEM, ak, bk);
+        if (rc_) return -rc_;
     }
-    if (ak && bk) EB_TMA_CASE(true, true)
-    else if (ak && !bk) EB_TMA_CASE(true, false)
-    else if (!ak && bk) EB_TMA_CASE(false, true)
-    else EB_TMA_CASE(false, false)
-#undef EB_TMA_CASE
-    launch_counter()++;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return -cuda_fail(e, "gemm_tma_f64");
     d.launches++;
     if (splits > 1) {
         int rc = launch_finalize<double>(s, p.b, p.m, p.n, ws, d.C.data, d.alpha, beta_eff, splits, d);
@@ -262,9 +211,7 @@ template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract
     });
     int cfg = 0;
     if (mma) {
-        cfg = g_mma_config ? g_mma_config : 2;
-        if (cfg == 1) { bm = 128; bn = 128; bk = 16; ctas_per_sm = 1; }
-        else { cfg = 2; bm = 128; bn = 64; bk = 16; ctas_per_sm = 2; }
+        cfg = 2; bm = 128; bn = 64; bk = 16; ctas_per_sm = 2;
         args.vec_ab = operand_pairs_ok(p, ROLE_A, p.a_kmajor ? p.k : p.m, p.a_kmajor ? p.m : p.k, args.A) &&
                       operand_pairs_ok(p, ROLE_B, p.b_kmajor ? p.k : p.n, p.b_kmajor ? p.n : p.k, args.B);
         args.vec_c = operand_pairs_ok(p, ROLE_C, p.n, p.m, args.C);
@@ -301,14 +248,10 @@ template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract
     dim3 grid((unsigned)(tm * tn), (unsigned)splits, (unsigned)p.b.tot);
     int  rc;
     if (mma) {
-        if constexpr (std::is_same_v<T, double>) {
-            if (cfg == 1) rc = launch_mma_cfg<128, 128, 16, 64, 32, 4, 1>(s, args, grid);
-            else rc = launch_mma_cfg<128, 64, 16, 32, 32, 3, 2>(s, args, grid);
-        } else {
-            rc = fail(EB200_ERR_UNSUPPORTED, "tile_mma is FP64 only");
-        }
+        if constexpr (std::is_same_v<T, double>) rc = k_launch_mma(s, args, grid);
+        else rc = fail(EB200_ERR_UNSUPPORTED, "tile_mma is FP64 only");
     } else {
-        rc = launch_simt_conj<T>(s, args, grid);
+        rc = k_launch_simt(Scalar<T>::dtype, s, args, grid);
     }
     if (rc) return rc;
     d.launches++;
@@ -321,65 +264,6 @@ template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract
 }
 
 // ---------------------------------------------------------------- streaming reductions
-// 0: flat kernel; 1: segmented, scalar loads; 2: segmented, 16-byte pairs
-template <typename T> int reduce_seg_mode(const ReduceArgs &a) {
-    if (a.k.n == 0 || a.k.ext[0] < 32) return 0;
-    if (sizeof(T) > 8 || a.k.s[ROLE_A][0] != 1 || a.k.s[ROLE_B][0] != 1 || (a.k.ext[0] & 1)) return 1;
-    auto all_even = [](const Grp &g, int role, int skip) {
-        for (int i = 0; i < g.n; i++)
-            if (i != skip && (g.s[role][i] & 1)) return false;
-        return true;
-    };
-    if (!all_even(a.k, ROLE_A, 0) || !all_even(a.k, ROLE_B, 0) || !all_even(a.rows, ROLE_A, -1) || !all_even(a.rows, ROLE_B, -1) ||
-        !all_even(a.n, ROLE_B, -1))
-        return 1;
-    constexpr uintptr_t AL = 2 * sizeof(T);
-    if ((uintptr_t)a.A % AL || (uintptr_t)a.B % AL) return 1;
-    return 2;
-}
-
-template <typename T, int NN, bool CA, bool CB> int launch_reduce_nn(cudaStream_t s, bool row, ReduceArgs &a, dim3 grid) {
-    if (row) {
-        int mode = reduce_seg_mode<T>(a);
-        a.flat_lanes = 0;
-        if (mode >= 1) {
-            const int64_t vec = (mode == 2) ? 2 : 1, ppr = a.k.ext[0] / vec;
-            // flat lane mapping only where whole-warp chunks would leave lanes idle (run length not a multiple of 32 packs)
-            if (a.k.tot / vec < 0x7fffffffLL && a.k.ext[0] % vec == 0 && (ppr % 32) != 0) {
-                a.flat_lanes = 1;
-                fastdiv_init(ppr, a.ppr_mul, a.ppr_shift);
-            }
-        }
-        if (mode == 2) {
-            if constexpr (sizeof(T) <= 8) row_reduce_seg<T, NN, 4, 2, CA, CB><<<grid, 256, 0, s>>>(a);
-        } else if (mode == 1) {
-            row_reduce_seg<T, NN, 4, 1, CA, CB><<<grid, 256, 0, s>>>(a);
-        } else {
-            row_reduce<T, NN, 4, CA, CB><<<grid, 256, 0, s>>>(a);
-        }
-        EB_POST_LAUNCH("row_reduce");
-    } else {
-        col_reduce<T, NN, 2, CA, CB><<<grid, 256, 0, s>>>(a);
-        EB_POST_LAUNCH("col_reduce");
-    }
-    return EB200_OK;
-}
-template <typename T, bool CA, bool CB> int launch_reduce_c(cudaStream_t s, bool row, ReduceArgs &a, dim3 grid) {
-    int nn = (int)a.n.tot;
-    if (nn <= 1) return launch_reduce_nn<T, 1, CA, CB>(s, row, a, grid);
-    if (nn <= 2) return launch_reduce_nn<T, 2, CA, CB>(s, row, a, grid);
-    if (nn <= 4) return launch_reduce_nn<T, 4, CA, CB>(s, row, a, grid);
-    return launch_reduce_nn<T, 8, CA, CB>(s, row, a, grid);
-}
-template <typename T> int launch_reduce(cudaStream_t s, bool row, ReduceArgs &a, dim3 grid) {
-    if constexpr (Scalar<T>::is_complex) {
-        if (a.conj_a && a.conj_b) return launch_reduce_c<T, true, true>(s, row, a, grid);
-        if (a.conj_a) return launch_reduce_c<T, true, false>(s, row, a, grid);
-        if (a.conj_b) return launch_reduce_c<T, false, true>(s, row, a, grid);
-    }
-    return launch_reduce_c<T, false, false>(s, row, a, grid);
-}
-
 template <typename T> int run_reduce(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const double beta_eff[2]) {
     ReduceArgs a;
     a.rows = p.rows; a.n = p.n; a.k = p.k;
@@ -414,7 +298,7 @@ template <typename T> int run_reduce(cudaStream_t s, const Plan &p, eb200_contra
         a.ws = ws;
     }
     dim3 grid((unsigned)row_blocks, (unsigned)splits, 1);
-    int  rc = launch_reduce<T>(s, row, a, grid);
+    int  rc = k_launch_reduce(Scalar<T>::dtype, s, row, a, grid);
     if (rc) return rc;
     d.launches++;
     if (splits > 1) {
@@ -429,26 +313,13 @@ template <typename T> int run_reduce(cudaStream_t s, const Plan &p, eb200_contra
 }
 
 // ---------------------------------------------------------------- elementwise
-template <typename T, bool CA, bool CB> int launch_elem(cudaStream_t s, ElemArgs &a) {
-    elementwise<T, CA, CB><<<grid_for(a.t.tot, 256, 16), 256, 0, s>>>(a);
-    EB_POST_LAUNCH("elementwise");
-    return EB200_OK;
-}
 template <typename T> int run_elementwise(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const double beta_eff[2]) {
     ElemArgs a;
     a.t = p.t;
     a.A = d.A.data; a.B = d.B.data; a.C = d.C.data;
     a.alpha[0] = d.alpha[0]; a.alpha[1] = d.alpha[1];
     a.beta[0] = beta_eff[0]; a.beta[1] = beta_eff[1];
-    int rc;
-    if constexpr (Scalar<T>::is_complex) {
-        if (d.conj_a && d.conj_b) rc = launch_elem<T, true, true>(s, a);
-        else if (d.conj_a) rc = launch_elem<T, true, false>(s, a);
-        else if (d.conj_b) rc = launch_elem<T, false, true>(s, a);
-        else rc = launch_elem<T, false, false>(s, a);
-    } else {
-        rc = launch_elem<T, false, false>(s, a);
-    }
+    int rc = k_launch_elem(Scalar<T>::dtype, s, a, d.conj_a, d.conj_b, grid_for(a.t.tot, 256, 16));
     if (rc) return rc;
     d.launches++;
     return EB200_OK;
@@ -526,46 +397,6 @@ template <typename T> int contract_typed(cudaStream_t s, eb200_contract_desc &d)
 // (Dispatch.hpp:896-899) and multiplies in the wider type. Here the narrower operands are widened into dense scratch
 // copies (stream-ordered allocations) and the same-type engine runs in the promoted type; a narrower C is widened,
 // updated and narrowed back. Rare path (tests and MixedPrecision-style calls), two small extra kernels.
-template <typename S, typename D> __device__ __forceinline__ D convert_scalar(S v) {
-    if constexpr (Scalar<S>::is_complex && Scalar<D>::is_complex) return make_scalar<D>((double)v.x, (double)v.y);
-    else if constexpr (Scalar<S>::is_complex) return make_scalar<D>((double)v.x, 0.0); // complex -> real keeps the real part
-    else return make_scalar<D>((double)v, 0.0);
-}
-struct ConvArgs {
-    Grp         g; // ROLE_A = source strides, ROLE_C = destination strides
-    const void *src;
-    void       *dst;
-};
-template <typename S, typename D> __global__ void __launch_bounds__(256) convert_tensor(const __grid_constant__ ConvArgs a) {
-    const S *src = reinterpret_cast<const S *>(a.src);
-    D       *dst = reinterpret_cast<D *>(a.dst);
-    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < a.g.tot; x += (int64_t)gridDim.x * blockDim.x) {
-        int64_t os, od;
-        grp_offset2(a.g, x, ROLE_A, ROLE_C, os, od);
-        dst[od] = convert_scalar<S, D>(src[os]);
-    }
-}
-template <typename S, typename D> int launch_convert(cudaStream_t s, const ConvArgs &a) {
-    convert_tensor<S, D><<<grid_for(a.g.tot, 256), 256, 0, s>>>(a);
-    EB_POST_LAUNCH("convert_tensor");
-    return EB200_OK;
-}
-template <typename S> int launch_convert_to(cudaStream_t s, int dst_dtype, const ConvArgs &a) {
-    switch (dst_dtype) {
-    case EB200_F32: return launch_convert<S, float>(s, a);
-    case EB200_F64: return launch_convert<S, double>(s, a);
-    case EB200_C64: return launch_convert<S, float2>(s, a);
-    default: return launch_convert<S, double2>(s, a);
-    }
-}
-int launch_convert_any(cudaStream_t s, int src_dtype, int dst_dtype, const ConvArgs &a) {
-    switch (src_dtype) {
-    case EB200_F32: return launch_convert_to<float>(s, dst_dtype, a);
-    case EB200_F64: return launch_convert_to<double>(s, dst_dtype, a);
-    case EB200_C64: return launch_convert_to<float2>(s, dst_dtype, a);
-    default: return launch_convert_to<double2>(s, dst_dtype, a);
-    }
-}
 size_t dtype_size(int dt) { return dt == EB200_F32 ? 4 : (dt == EB200_C128 ? 16 : 8); }
 
 // dense row-major strides over the tensor's own axes; group for a strided<->dense copy
@@ -611,7 +442,7 @@ int contract_mixed(cudaStream_t s, eb200_contract_desc &d) {
         const bool need_values = (i != 0) || !(d.beta[0] == 0.0 && d.beta[1] == 0.0);
         if (need_values) {
             ConvArgs ca{g, os[i]->data, tmp[i]};
-            rc = launch_convert_any(s, os[i]->dtype, W, ca);
+            rc = k_launch_convert(s, os[i]->dtype, W, ca, grid_for(ca.g.tot, 256));
             d.launches++;
         }
         ts[i]->data = tmp[i];
@@ -628,7 +459,7 @@ int contract_mixed(cudaStream_t s, eb200_contract_desc &d) {
     }
     if (rc == EB200_OK && tmp[0]) {
         ConvArgs ca{back, tmp[0], d.C.data};
-        rc = launch_convert_any(s, W, d.C.dtype, ca);
+        rc = k_launch_convert(s, W, d.C.dtype, ca, grid_for(ca.g.tot, 256));
         d.launches++;
     }
     for (int i = 0; i < 3; i++)

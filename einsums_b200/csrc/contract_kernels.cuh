@@ -453,7 +453,7 @@ struct ReduceArgs {
 
 // row_reduce: block = RB consecutive rows x one K segment. Lanes run along k (contiguous in A).
 // Each B value is loaded once and reused by the RB rows, so B traffic is 1/RB of A traffic.
-template <typename T, int NN, int RB, bool CONJ_A, bool CONJ_B>
+template <typename T, int NN, int RB>
 __global__ void __launch_bounds__(256) row_reduce(const __grid_constant__ ReduceArgs a) {
     constexpr int NT = 256, NW = NT / 32, UNR = 4;
     __shared__ T  red[NW][RB * NN];
@@ -518,9 +518,9 @@ __global__ void __launch_bounds__(256) row_reduce(const __grid_constant__ Reduce
 #pragma unroll
                 for (int c = 0; c < NN; c++) {
                     if (c >= ncols) break;
-                    T bv = maybe_conj<CONJ_B>(B[ob[u] + colB[c]]);
+                    T bv = conj_if(B[ob[u] + colB[c]], a.conj_b != 0);
 #pragma unroll
-                    for (int j = 0; j < RB; j++) acc[j][c] = fma_(maybe_conj<CONJ_A>(av[u][j]), bv, acc[j][c]);
+                    for (int j = 0; j < RB; j++) acc[j][c] = fma_(conj_if(av[u][j], a.conj_a != 0), bv, acc[j][c]);
                 }
             } else {
 #pragma unroll
@@ -529,8 +529,8 @@ __global__ void __launch_bounds__(256) row_reduce(const __grid_constant__ Reduce
 #pragma unroll
                     for (int c = 0; c < NN; c++) {
                         if (c >= ncols) break;
-                        T bv = maybe_conj<CONJ_B>(B[rowB[j] + ob[u] + colB[c]]);
-                        acc[j][c] = fma_(maybe_conj<CONJ_A>(av[u][j]), bv, acc[j][c]);
+                        T bv = conj_if(B[rowB[j] + ob[u] + colB[c]], a.conj_b != 0);
+                        acc[j][c] = fma_(conj_if(av[u][j], a.conj_a != 0), bv, acc[j][c]);
                     }
                 }
             }
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(256) row_reduce(const __grid_constant__ Reduce
 // per unit (no per-element division), lanes stream A with VEC*sizeof(T)-byte loads for RB rows at a
 // time and reuse each B value RB times. Units are split over blockIdx.y; partial sums are combined
 // in a fixed order (deterministic).
-template <typename T, int NN, int RB, int VEC, bool CONJ_A, bool CONJ_B>
+template <typename T, int NN, int RB, int VEC>
 __global__ void __launch_bounds__(256, (NN * RB * sizeof(T) <= 64 ? 3 : 1)) row_reduce_seg(const __grid_constant__ ReduceArgs a) {
     constexpr int NT = 256, NW = NT / 32;
     __shared__ T  red[NW][RB * NN];
@@ -671,9 +671,9 @@ __global__ void __launch_bounds__(256, (NN * RB * sizeof(T) <= 64 ? 3 : 1)) row_
                 else bv.v[0] = B[offB + ki * sB0 + colB[c]];
 #pragma unroll
                 for (int e = 0; e < VEC; e++) {
-                    T b = maybe_conj<CONJ_B>(bv.v[e]);
+                    T b = conj_if(bv.v[e], a.conj_b != 0);
 #pragma unroll
-                    for (int j = 0; j < RB; j++) acc[j][c] = fma_(maybe_conj<CONJ_A>(av[j].v[e]), b, acc[j][c]);
+                    for (int j = 0; j < RB; j++) acc[j][c] = fma_(conj_if(av[j].v[e], a.conj_a != 0), b, acc[j][c]);
                 }
             }
         } else {
@@ -684,8 +684,8 @@ __global__ void __launch_bounds__(256, (NN * RB * sizeof(T) <= 64 ? 3 : 1)) row_
                     if (c >= ncols) break;
 #pragma unroll
                     for (int e = 0; e < VEC; e++) {
-                        T b = maybe_conj<CONJ_B>(B[rowB[j] + offB + (ki + e) * sB0 + colB[c]]);
-                        acc[j][c] = fma_(maybe_conj<CONJ_A>(av[j].v[e]), b, acc[j][c]);
+                        T b = conj_if(B[rowB[j] + offB + (ki + e) * sB0 + colB[c]], a.conj_b != 0);
+                        acc[j][c] = fma_(conj_if(av[j].v[e], a.conj_a != 0), b, acc[j][c]);
                     }
                 }
         }
@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(256, (NN * RB * sizeof(T) <= 64 ? 3 : 1)) row_
 }
 
 // col_reduce: threads run along rows (contiguous in A); each thread owns RT rows and walks a K segment.
-template <typename T, int NN, int RT, bool CONJ_A, bool CONJ_B>
+template <typename T, int NN, int RT>
 __global__ void __launch_bounds__(256) col_reduce(const __grid_constant__ ReduceArgs a) {
     constexpr int NT = 256;
     const int     tid = threadIdx.x;
@@ -765,13 +765,13 @@ __global__ void __launch_bounds__(256) col_reduce(const __grid_constant__ Reduce
     for (int64_t k = k_begin; k < k_end; k++) {
         T av[RT];
 #pragma unroll
-        for (int j = 0; j < RT; j++) av[j] = (rowA[j] != OFF_INVALID) ? maybe_conj<CONJ_A>(A[rowA[j] + offA]) : zero_of<T>();
+        for (int j = 0; j < RT; j++) av[j] = (rowA[j] != OFF_INVALID) ? conj_if(A[rowA[j] + offA], a.conj_a != 0) : zero_of<T>();
 #pragma unroll
         for (int c = 0; c < NN; c++) {
             if (c >= ncols) break;
 #pragma unroll
             for (int j = 0; j < RT; j++) {
-                T bv = maybe_conj<CONJ_B>(B[rowB[j] + offB + colB[c]]);
+                T bv = conj_if(B[rowB[j] + offB + colB[c]], a.conj_b != 0);
                 acc[j][c] = fma_(av[j], bv, acc[j][c]);
             }
         }

@@ -1,0 +1,28 @@
+// launch_api.cuh — kernel launch entry points, one translation unit per kernel family so that the library builds in
+// parallel (contract.cu holds only host logic).
+#pragma once
+#include "contract_kernels.cuh"
+#include "gemm_tma.cuh"
+
+namespace eb200 {
+struct ConvArgs {
+    Grp         g; // ROLE_A = source strides, ROLE_C = destination strides
+    const void *src;
+    void       *dst;
+};
+int k_launch_mma(cudaStream_t s, TileArgs &args, dim3 grid);                                    // k_tile_mma.cu
+int k_launch_simt(int dtype, cudaStream_t s, TileArgs &args, dim3 grid);                         // k_tile_simt.cu
+int k_launch_tma(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB, const TmaGemmArgs &a, dim3 grid, size_t smem, bool ak,
+                 bool bk);                                                                       // k_tile_tma.cu
+int k_launch_reduce(int dtype, cudaStream_t s, bool row, ReduceArgs &a, dim3 grid);              // k_reduce_{real,cplx}.cu
+int k_launch_reduce_real(int dtype, cudaStream_t s, bool row, ReduceArgs &a, dim3 grid);
+int k_launch_reduce_cplx(int dtype, cudaStream_t s, bool row, ReduceArgs &a, dim3 grid);
+int k_launch_elem(int dtype, cudaStream_t s, ElemArgs &a, int conj_a, int conj_b, int grid);     // k_misc.cu
+int k_launch_scale(int dtype, cudaStream_t s, ScaleArgs &a, int grid);
+int k_launch_finalize(int dtype, cudaStream_t s, FinalizeArgs &a, int grid);
+int k_launch_convert(cudaStream_t s, int src_dtype, int dst_dtype, const ConvArgs &a, int grid);
+template <typename K> inline int set_smem_attr(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) EB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return EB200_OK;
+}
+} // namespace eb200

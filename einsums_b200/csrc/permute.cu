@@ -285,7 +285,7 @@ int permute_impl(void *stream, int rank, const int64_t *dimsA, const int64_t *st
                 pa.tiles_a = (pa.ea + 63) / 64;
                 pa.tiles_c = (pa.ec + 63) / 64;
                 int64_t ntiles = pa.tiles_a * pa.tiles_c * pa.rest.tot;
-                int     grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)sm_count() * 24));
+                int     grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, 0x3fffffffLL)); // one tile per CTA: the hardware scheduler balances the tail
                 permute_tile_vec<T><<<grid, 256, 0, s>>>(pa);
                 EB_POST_LAUNCH("permute_tile_vec");
                 return EB200_OK;
@@ -295,7 +295,7 @@ int permute_impl(void *stream, int rank, const int64_t *dimsA, const int64_t *st
         pa.tiles_a = (pa.ea + TILE - 1) / TILE;
         pa.tiles_c = (pa.ec + TILE - 1) / TILE;
         int64_t ntiles = pa.tiles_a * pa.tiles_c * pa.rest.tot;
-        int     grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, (int64_t)sm_count() * 32));
+        int     grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, 0x3fffffffLL));
         dim3    block(TILE, ROWS);
         if (cj) permute_tile<T, true, TILE, ROWS><<<grid, block, 0, s>>>(pa);
         else permute_tile<T, false, TILE, ROWS><<<grid, block, 0, s>>>(pa);
