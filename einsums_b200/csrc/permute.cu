@@ -148,12 +148,56 @@ template <typename T> __global__ void __launch_bounds__(256, 3) permute_tile_vec
     }
 }
 
-// row kernel: the same axis is fastest on both sides. VEC elements per thread per step.
-template <typename T, bool CONJ, int VEC> __global__ void __launch_bounds__(256, 3) permute_rows(const __grid_constant__ PermArgs a) {
+// Row-type permutations (the same axis is fastest in A and in C) with at least one more axis: a CTA copies a 64 x 64 patch of the
+// plane (fastest axis, one other axis). Every thread issues 8 independent 2-element loads, then 8 stores; the only index decode
+// is one per CTA for the remaining axes. No shared memory: nothing is transposed inside a row.
+template <typename T, bool HAS_BETA> __global__ void __launch_bounds__(256, 4) permute_rows2d(const __grid_constant__ PermArgs a) {
     const T      *A = reinterpret_cast<const T *>(a.A);
     T            *C = reinterpret_cast<T *>(a.C);
     const T       alpha = make_scalar<T>(a.alpha[0], a.alpha[1]), beta = make_scalar<T>(a.beta[0], a.beta[1]);
-    const bool    has_beta = !is_zero(beta);
+    const bool    plain = is_one(alpha) && !HAS_BETA;
+    const int     lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int64_t per_rest = a.tiles_a * a.tiles_c;
+    const int64_t t = blockIdx.x;
+    int64_t       rest, ta, tc;
+    {
+        uint32_t tt = (uint32_t)t, pr = (uint32_t)per_rest, r_ = tt / pr, in = tt - r_ * pr;
+        uint32_t c_ = in / (uint32_t)a.tiles_a;
+        rest = r_; tc = c_; ta = in - c_ * (uint32_t)a.tiles_a;
+    }
+    int64_t offA, offC;
+    grp_offset2(a.rest, rest, ROLE_A, ROLE_C, offA, offC);
+    const int64_t ia = ta * 64 + 2 * lx, c0 = tc * 64 + ly;
+    if (ia >= a.ea) return;
+    Pair<T> v[8], o[HAS_BETA ? 8 : 1];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int64_t ic = c0 + 8 * i;
+        if (ic < a.ec) {
+            v[i] = *reinterpret_cast<const Pair<T> *>(A + offA + ia + ic * a.sa_c);
+            if constexpr (HAS_BETA) o[i] = *reinterpret_cast<const Pair<T> *>(C + offC + ia + ic * a.sc_c);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int64_t ic = c0 + 8 * i;
+        if (ic < a.ec) {
+            Pair<T> w = v[i];
+            if (!plain) {
+                w.x = mul_(alpha, w.x); w.y = mul_(alpha, w.y);
+                if constexpr (HAS_BETA) { w.x = fma_(beta, o[i].x, w.x); w.y = fma_(beta, o[i].y, w.y); }
+            }
+            *reinterpret_cast<Pair<T> *>(C + offC + ia + ic * a.sc_c) = w;
+        }
+    }
+}
+
+// row kernel: the same axis is fastest on both sides. VEC elements per thread per step.
+template <typename T, bool CONJ, int VEC, bool HAS_BETA> __global__ void __launch_bounds__(256, 3) permute_rows(const __grid_constant__ PermArgs a) {
+    const T      *A = reinterpret_cast<const T *>(a.A);
+    T            *C = reinterpret_cast<T *>(a.C);
+    const T       alpha = make_scalar<T>(a.alpha[0], a.alpha[1]), beta = make_scalar<T>(a.beta[0], a.beta[1]);
+    constexpr bool has_beta = HAS_BETA;
     const int64_t chunks_per_row = (a.ea + VEC - 1) / VEC;
     const int64_t total = chunks_per_row * a.rest.tot;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -170,14 +214,14 @@ template <typename T, bool CONJ, int VEC> __global__ void __launch_bounds__(256,
     };
     for (int64_t x0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x0 < total; x0 += stride * UNR) {
         int64_t oa[UNR], oc[UNR];
-        Pack    in[UNR], old[UNR];
+        Pack    in[UNR], old[HAS_BETA ? UNR : 1];
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
             int64_t x = x0 + u * stride;
             if (x < total) {
                 locate(x, oa[u], oc[u]);
                 in[u] = *reinterpret_cast<const Pack *>(A + oa[u]);
-                if (has_beta) old[u] = *reinterpret_cast<const Pack *>(C + oc[u]);
+                if constexpr (HAS_BETA) old[u] = *reinterpret_cast<const Pack *>(C + oc[u]);
             }
         }
 #pragma unroll
@@ -188,7 +232,7 @@ template <typename T, bool CONJ, int VEC> __global__ void __launch_bounds__(256,
 #pragma unroll
                 for (int e = 0; e < VEC; e++) {
                     T v = mul_(alpha, maybe_conj<CONJ>(in[u].v[e]));
-                    if (has_beta) v = fma_(beta, old[u].v[e], v);
+                    if constexpr (HAS_BETA) v = fma_(beta, old[u].v[e], v);
                     out.v[e] = v;
                 }
                 *reinterpret_cast<Pack *>(C + oc[u]) = out;
@@ -254,6 +298,43 @@ int permute_impl(void *stream, int rank, const int64_t *dimsA, const int64_t *st
         pa.ea = ax[ia].ext; pa.sa_a = ax[ia].sa; pa.sc_a = ax[ia].sc;
         for (size_t i = 0; i < ax.size(); i++)
             if (i != ia && !push_rest(ax[i])) return fail(EB200_ERR_UNSUPPORTED, "permute: more than %d non-mergeable axes", MAXG + 2);
+        if constexpr (!Scalar<T>::is_complex) {
+            // 2-D patch kernel: needs a second axis, pairs along the fastest axis, everything 2-element aligned
+            bool ok2d = !cj && ax.size() >= 2 && pa.sa_a == 1 && pa.sc_a == 1 && pa.ea % 2 == 0 && ((uintptr_t)A % (2 * sizeof(T)) == 0) &&
+                        ((uintptr_t)C % (2 * sizeof(T)) == 0);
+            for (size_t i = 0; i < ax.size() && ok2d; i++)
+                if (i != ia && (ax[i].sa % 2 || ax[i].sc % 2)) ok2d = false;
+            if (ok2d) {
+                // second axis: the remaining axis with the smallest C stride (keeps the written rows close together)
+                size_t i2 = (ia == 0) ? 1 : 0;
+                for (size_t i = 0; i < ax.size(); i++)
+                    if (i != ia && std::llabs(ax[i].sc) < std::llabs(ax[i2].sc)) i2 = i;
+                PermArgs pb = pa;
+                memset(&pb.rest, 0, sizeof(pb.rest));
+                pb.rest.tot = 1;
+                pb.ec = ax[i2].ext; pb.sa_c = ax[i2].sa; pb.sc_c = ax[i2].sc;
+                bool fits = true;
+                for (size_t i = 0; i < ax.size(); i++)
+                    if (i != ia && i != i2) {
+                        if (pb.rest.n >= MAXG) { fits = false; break; }
+                        pb.rest.ext[pb.rest.n] = ax[i].ext;
+                        pb.rest.s[ROLE_A][pb.rest.n] = ax[i].sa;
+                        pb.rest.s[ROLE_C][pb.rest.n] = ax[i].sc;
+                        pb.rest.n++;
+                        pb.rest.tot *= ax[i].ext;
+                    }
+                pb.tiles_a = (pb.ea + 63) / 64;
+                pb.tiles_c = (pb.ec + 63) / 64;
+                const int64_t ntiles = pb.tiles_a * pb.tiles_c * pb.rest.tot;
+                if (fits && ntiles < 0x7fffffffLL) {
+                    grp_finalize(pb.rest);
+                    if (!is_zero(beta)) permute_rows2d<T, true><<<(unsigned)ntiles, 256, 0, s>>>(pb);
+                    else permute_rows2d<T, false><<<(unsigned)ntiles, 256, 0, s>>>(pb);
+                    EB_POST_LAUNCH("permute_rows2d");
+                    return EB200_OK;
+                }
+            }
+        }
         grp_finalize(pa.rest);
         constexpr int VEC = 16 / sizeof(T) > 1 ? 16 / sizeof(T) : 1;
         bool          vec_ok = VEC > 1 && pa.sa_a == 1 && pa.sc_a == 1 && pa.ea % VEC == 0 && ((uintptr_t)A % 16 == 0) && ((uintptr_t)C % 16 == 0);
@@ -262,13 +343,18 @@ int permute_impl(void *stream, int rank, const int64_t *dimsA, const int64_t *st
         int64_t chunks = ((pa.ea + (vec_ok ? VEC : 1) - 1) / (vec_ok ? VEC : 1)) * pa.rest.tot;
         fastdiv_init((pa.ea + (vec_ok ? VEC : 1) - 1) / (vec_ok ? VEC : 1), pa.cpr_mul, pa.cpr_shift);
         int     grid = (int)std::max<int64_t>(1, std::min<int64_t>((chunks + 255) / 256, (int64_t)sm_count() * 16));
+        const bool hb = !is_zero(beta);
+#define EB_ROWS(CJ, V)                                                            \
+    {                                                                             \
+        if (hb) permute_rows<T, CJ, V, true><<<grid, 256, 0, s>>>(pa);            \
+        else permute_rows<T, CJ, V, false><<<grid, 256, 0, s>>>(pa);              \
+    }
         if (vec_ok) {
-            if (cj) permute_rows<T, true, VEC><<<grid, 256, 0, s>>>(pa);
-            else permute_rows<T, false, VEC><<<grid, 256, 0, s>>>(pa);
+            if (cj) EB_ROWS(true, VEC) else EB_ROWS(false, VEC)
         } else {
-            if (cj) permute_rows<T, true, 1><<<grid, 256, 0, s>>>(pa);
-            else permute_rows<T, false, 1><<<grid, 256, 0, s>>>(pa);
+            if (cj) EB_ROWS(true, 1) else EB_ROWS(false, 1)
         }
+#undef EB_ROWS
         EB_POST_LAUNCH("permute_rows");
     } else {
         pa.ea = ax[ia].ext; pa.sa_a = ax[ia].sa; pa.sc_a = ax[ia].sc;

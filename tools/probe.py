@@ -7,14 +7,23 @@ from einsums_b200 import ops, KF_NAMES
 ops.init(0)
 torch.cuda.set_device(0)
 
-def timeit(fn, reps=5, warm=2):
+def timeit(fn, reps=5, warm=2, inner=None):
+    """median over `reps` of the per-call device time; `inner` calls are enqueued back to back between the two events so that
+    host launch latency (~20-30 us through Python/ctypes) does not pollute sub-millisecond kernels."""
     for _ in range(warm): fn()
     torch.cuda.synchronize()
+    if inner is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        one = e0.elapsed_time(e1)
+        inner = 1 if one > 5.0 else (4 if one > 1.0 else 20)
     ts = []
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        e0.record()
+        for _ in range(inner): fn()
+        e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / inner)
     ts.sort()
     return ts[len(ts)//2]
 
