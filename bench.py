@@ -4,7 +4,7 @@
 Workload (BASELINE.json configs[1]): CCD W intermediates, o=20, v=200, FP64, one step =
     Wmnij[m,n,i,j] = 1.0*Wmnij + 0.25 * sum_ef g[m,n,e,f] t[i,j,e,f]      (M=N=400,   K=40000, split-K)
     Wabef[a,b,e,f] = 1.0*Wabef + 0.25 * sum_mn g[m,n,e,f] t[m,n,a,b]      (M=N=40000, K=400, C = 12.8 GB)
-both through the C ABI (eb200_contract -> tile_mma_f64). flops/step = 2*o^4*v^2 + 2*v^4*o^2 = 1.2928e12.
+both through the C ABI (eb200_contract -> gemm_tma_f64: TMA + mbarrier + DMMA). flops/step = 2*o^4*v^2 + 2*v^4*o^2 = 1.2928e12.
 
 N > 1 (torchrun, one rank per GPU): the `a` index of Wabef is sharded — rank r owns the slab a in [r*v,(r+1)*v) of a
 W with N*v values of `a` (per-GPU work fixed => weak scaling); no collective on the data path.
@@ -274,7 +274,7 @@ def run_ours(args):
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("tile_mma_f64_wabef_dram_bytes")
+            traffic = json.load(open(prof)).get("gemm_tma_f64_wabef_dram_bytes")
         except Exception:
             traffic = None
     line = {
@@ -284,7 +284,7 @@ def run_ours(args):
         "config": {"workload": f"CCD Wmnij+Wabef o={O} v={V} FP64 (BASELINE configs[1])", "o": O, "v": V,
                    "flops_per_step_per_gpu": FLOPS_STEP, "l2": "per-step traffic (25.9 GB) exceeds the 126 MB L2; no flush needed",
                    "sharding": "none" if world == 1 else f"a-index of Wabef sharded over {world} ranks, no collective"},
-        "roofline": {"bound": "tensor", "kernel": "tile_mma_f64 (Wabef, M=N=40000 K=400)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "roofline": {"bound": "tensor", "kernel": "gemm_tma_f64 (Wabef, M=N=40000 K=400)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "ms_per_launch": ms_wabef,
                      "algorithmic_flops_per_launch": FLOPS_WABEF},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

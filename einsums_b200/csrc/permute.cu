@@ -84,13 +84,14 @@ template <typename T, bool CONJ, int TILE, int ROWS> __global__ void __launch_bo
 // axis c, 8 independent stores. Needs even extents/strides and 2-element-aligned bases (checked on the host).
 template <typename T> struct alignas(2 * sizeof(T)) Pair { T x, y; };
 
-template <typename T> __global__ void __launch_bounds__(256, 3) permute_tile_vec(const __grid_constant__ PermArgs a) {
+template <typename T, bool HAS_BETA> __global__ void __launch_bounds__(256, HAS_BETA ? 2 : 3) permute_tile_vec(const __grid_constant__ PermArgs a) {
     constexpr int TILE = 64;
     __shared__ __align__(16) T tile[TILE * TILE];
     const T      *A = reinterpret_cast<const T *>(a.A);
     T            *C = reinterpret_cast<T *>(a.C);
     const T       alpha = make_scalar<T>(a.alpha[0], a.alpha[1]), beta = make_scalar<T>(a.beta[0], a.beta[1]);
-    const bool    has_beta = !is_zero(beta), plain = is_one(alpha) && !has_beta;
+    constexpr bool has_beta = HAS_BETA;
+    const bool    plain = is_one(alpha) && !has_beta;
     const int     tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
     const int64_t per_rest = a.tiles_a * a.tiles_c;
     const int64_t ntiles = per_rest * a.rest.tot;
@@ -111,7 +112,15 @@ template <typename T> __global__ void __launch_bounds__(256, 3) permute_tile_vec
         int64_t offA, offC;
         grp_offset2(a.rest, rest, ROLE_A, ROLE_C, offA, offC);
         const int64_t a0 = ta * TILE, c0 = tc * TILE;
-        Pair<T> v[8];
+        Pair<T> v[8], old[HAS_BETA ? 8 : 1];
+        if constexpr (HAS_BETA) { // the old C values of this thread's phase-2 pairs are fetched together with the A tile
+            const int64_t ic = c0 + 2 * lx;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int64_t ia = a0 + ly + 8 * i;
+                if (ia < a.ea && ic < a.ec) old[i] = *reinterpret_cast<const Pair<T> *>(C + offC + ia * a.sc_a + ic);
+            }
+        }
         {
             const int64_t ia = a0 + 2 * lx;
 #pragma unroll
@@ -138,7 +147,7 @@ template <typename T> __global__ void __launch_bounds__(256, 3) permute_tile_vec
                     Pair<T> *dst = reinterpret_cast<Pair<T> *>(C + offC + ia * a.sc_a + ic);
                     if (!plain) {
                         w.x = mul_(alpha, w.x); w.y = mul_(alpha, w.y);
-                        if (has_beta) { Pair<T> o = *dst; w.x = fma_(beta, o.x, w.x); w.y = fma_(beta, o.y, w.y); }
+                        if constexpr (HAS_BETA) { w.x = fma_(beta, old[i].x, w.x); w.y = fma_(beta, old[i].y, w.y); }
                     }
                     *dst = w;
                 }
@@ -372,7 +381,8 @@ int permute_impl(void *stream, int rank, const int64_t *dimsA, const int64_t *st
                 pa.tiles_c = (pa.ec + 63) / 64;
                 int64_t ntiles = pa.tiles_a * pa.tiles_c * pa.rest.tot;
                 int     grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, 0x3fffffffLL)); // one tile per CTA: the hardware scheduler balances the tail
-                permute_tile_vec<T><<<grid, 256, 0, s>>>(pa);
+                if (!is_zero(beta)) permute_tile_vec<T, true><<<grid, 256, 0, s>>>(pa);
+                else permute_tile_vec<T, false><<<grid, 256, 0, s>>>(pa);
                 EB_POST_LAUNCH("permute_tile_vec");
                 return EB200_OK;
             }

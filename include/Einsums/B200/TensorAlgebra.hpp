@@ -276,6 +276,44 @@ void einsum(std::tuple<CIndices...> const &C_indices, CType *C, std::tuple<AIndi
     einsum<ConjA, ConjB>(S(0), C_indices, C, S(1), A_indices, A, B_indices, B, algorithm_choice);
 }
 
+/// Batched containers (std::vector<DeviceTensor>...): the same contraction on every element triple
+/// (reference: TensorAlgebra/Backends/Dispatch.hpp:1264-1286, one einsum per item under `omp parallel for`). Here all items are
+/// enqueued back to back on the calling thread's stream with a single wait at the end.
+template <typename X>
+concept DeviceTensorContainer = requires(X const &x) {
+    typename std::remove_cvref_t<X>::value_type;
+    requires DeviceTensorLike<typename std::remove_cvref_t<X>::value_type>;
+    { x.size() } -> std::convertible_to<size_t>;
+    { x.at(0) };
+};
+template <bool ConjA = false, bool ConjB = false, DeviceTensorContainer CList, DeviceTensorContainer AList, DeviceTensorContainer BList, typename U,
+          typename... CIndices, typename... AIndices, typename... BIndices>
+    requires(std::is_arithmetic_v<U> || IsComplexV<U>)
+void einsum(U const C_prefactor, std::tuple<CIndices...> const &C_indices, CList *C_list, U const AB_prefactor,
+            std::tuple<AIndices...> const &A_indices, AList const &A_list, std::tuple<BIndices...> const &B_indices, BList const &B_list,
+            detail::AlgorithmChoice *algorithm_choice = nullptr) {
+    if (C_list->size() != A_list.size() || C_list->size() != B_list.size())
+        throw bad_logic("Lists passed to batched einsum call do not have the same size!");
+    if (C_list->size() == 0) return;
+    const bool was_async = gpu::is_async();
+    gpu::set_async(true);
+    try {
+        for (size_t i = 0; i < C_list->size(); i++)
+            einsum<ConjA, ConjB>(C_prefactor, C_indices, &C_list->at(i), AB_prefactor, A_indices, A_list.at(i), B_indices, B_list.at(i), algorithm_choice);
+    } catch (...) {
+        gpu::set_async(was_async);
+        throw;
+    }
+    gpu::set_async(was_async);
+    gpu::op_wait();
+}
+template <bool ConjA = false, bool ConjB = false, DeviceTensorContainer CList, DeviceTensorContainer AList, DeviceTensorContainer BList,
+          typename... CIndices, typename... AIndices, typename... BIndices>
+void einsum(std::tuple<CIndices...> const &C_indices, CList *C_list, std::tuple<AIndices...> const &A_indices, AList const &A_list,
+            std::tuple<BIndices...> const &B_indices, BList const &B_list, detail::AlgorithmChoice *algorithm_choice = nullptr) {
+    einsum<ConjA, ConjB>(0.0, C_indices, C_list, 1.0, A_indices, A_list, B_indices, B_list, algorithm_choice);
+}
+
 /// The analyser's decision alone (DryRun of the reference): no data is touched.
 template <bool ConjA = false, bool ConjB = false, typename CV = double, typename AV = double, typename BV = double, typename... CIndices,
           typename... AIndices, typename... BIndices>

@@ -336,6 +336,29 @@ TEST_CASE(gpu_mixed_precision) { // GPUTensorAlgebra.hip:2301-2354: d-f-d, d-f-f
     run(double{}, double{}, double{});
 }
 
+TEST_CASE(gpu_batched_containers) { // Batched.cpp:13-100
+    using namespace einsums::index;
+    std::vector<DeviceTensor<double, 2>> As, Bs, Cs;
+    for (int b = 0; b < 5; b++) {
+        As.push_back(create_random_gpu_tensor("A", 7, 9));
+        Bs.push_back(create_random_gpu_tensor("B", 9, 6));
+        Cs.emplace_back("C", 7, 6);
+    }
+    AlgorithmChoice alg;
+    einsum(Indices{i, j}, &Cs, Indices{i, k}, As, Indices{k, j}, Bs, &alg);
+    CHECK(alg == ta::GEMM);
+    for (int b = 0; b < 5; b++) {
+        auto hA = host(As[b]), hB = host(Bs[b]), hC = host(Cs[b]);
+        for (size_t x = 0; x < 7; x++) for (size_t y = 0; y < 6; y++) {
+            double s = 0;
+            for (size_t k0 = 0; k0 < 9; k0++) s += hA(x, k0) * hB(k0, y);
+            CHECK_CLOSE(hC(x, y), s, 1e-12);
+        }
+    }
+    Bs.pop_back();
+    CHECK_THROWS_AS(einsum(Indices{i, j}, &Cs, Indices{i, k}, As, Indices{k, j}, Bs), bad_logic);
+}
+
 TEST_CASE(gpu_permute) { // Sort.cpp:18-250, GPUTensorAlgebra.hip:591-838
     using namespace einsums::index;
     auto A = create_random_gpu_tensor("A", 3, 4, 5, 6);
