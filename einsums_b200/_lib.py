@@ -20,7 +20,7 @@ MAX_UNIQUE = 24
 
 F32, F64, C64, C128 = 0, 1, 2, 3
 ALG_NAMES = ["GENERIC", "DOT", "DIRECT", "GER", "GEMV", "GEMM", "INDETERMINATE"]
-KF_NAMES = ["NONE", "TILE_MMA", "TILE_SIMT", "ROWREDUCE", "COLREDUCE", "FULLREDUCE", "ELEMENTWISE", "SCALE_ONLY"]
+KF_NAMES = ["NONE", "TILE_MMA", "TILE_SIMT", "ROWREDUCE", "COLREDUCE", "FULLREDUCE", "ELEMENTWISE", "SCALE_ONLY", "TILE_TCGEN05"]
 KF = {n: i for i, n in enumerate(KF_NAMES)}
 
 STATUS_NAMES = {

@@ -81,7 +81,8 @@ typedef enum eb200_kernel_family {
     EB200_KF_COLREDUCE = 4,   /* streaming reduction, target index contiguous in A (gemv-T)    */
     EB200_KF_FULLREDUCE = 5,  /* dot-like: everything is contracted                             */
     EB200_KF_ELEMENTWISE = 6, /* no contracted index: outer / direct / broadcast products      */
-    EB200_KF_SCALE_ONLY = 7   /* empty contraction space: C = beta*C only                       */
+    EB200_KF_SCALE_ONLY = 7,  /* empty contraction space: C = beta*C only                       */
+    EB200_KF_TILE_TCGEN05 = 8 /* FP32 plain GEMM on tcgen05/TMEM with 3xTF32 split accumulation  */
 } eb200_kernel_family;
 
 /* ------------------------------------------------------------------------------------------

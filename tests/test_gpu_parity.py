@@ -232,6 +232,61 @@ def test_dgemm_tma_path(gpu, oracle, ta, tb, shape):
         assert_close(Cd.cpu().numpy(), ref)
 
 
+def test_gemm_strided_batched_and_copy_strided(gpu, oracle):
+    """eb200_dgemm_strided_batched (column-major, per-batch strides) and eb200_copy_strided (layout-changing copy used for
+    host column-major -> device row-major conversion, Tensor/Backends/DeviceTensor.hpp:1054-1072 in the reference)."""
+    import ctypes as C
+    from einsums_b200 import _lib
+    rng = np.random.default_rng(91)
+    m, n, k, nb = 37, 29, 41, 5
+    lda, ldb, ldc = m + 1, k + 3, m + 2
+    A, B, Cm = rand(rng, (nb, k, lda)), rand(rng, (nb, n, ldb)), rand(rng, (nb, n, ldc))
+    ref = Cm.copy()
+    for b in range(nb):
+        oracle.lib().orc_dgemm(b"n", b"n", m, n, k, 0.5, A[b].ctypes.data, lda, B[b].ctypes.data, ldb, 2.0, ref[b].ctypes.data, ldc)
+    Ad, Bd, Cd = dev(A), dev(B), dev(Cm)
+    one = lambda v: (C.c_double * 1)(v)
+    rc = _lib.lib().eb200_dgemm_strided_batched(torch.cuda.current_stream().cuda_stream, b"n", b"n", m, n, k, one(0.5), Ad.data_ptr(), lda, k * lda,
+                                               Bd.data_ptr(), ldb, n * ldb, one(2.0), Cd.data_ptr(), ldc, n * ldc, nb)
+    assert rc == 0
+    assert_close(Cd.cpu().numpy(), ref)
+    # column-major host layout -> row-major device tensor
+    H = rand(rng, (6, 7, 8))
+    src = dev(np.asfortranarray(H).ravel(order="K"))          # Fortran-ordered bytes
+    dst = torch.empty(6, 7, 8, dtype=torch.float64, device="cuda")
+    i64 = C.c_int64 * 3
+    rc = _lib.lib().eb200_copy_strided(torch.cuda.current_stream().cuda_stream, _lib.F64, 3, i64(6, 7, 8), src.data_ptr(), i64(1, 6, 42),
+                                      dst.data_ptr(), i64(56, 8, 1))
+    assert rc == 0
+    assert np.array_equal(dst.cpu().numpy(), H)
+
+
+@pytest.mark.parametrize("shape", [(256, 256, 64), (300, 260, 100), (1000, 520, 260), (513, 384, 768), (128, 1024, 36)])
+def test_sgemm_tcgen05_3xtf32(gpu, oracle, shape):
+    """FP32 plain GEMM with both operands K-major takes the tcgen05/TMEM kernel (3xTF32 split accumulation). 1e-5 relative against a
+    float64 reference; ragged M/N/K edges (TMA zero fill), alpha/beta, transposed C."""
+    from einsums_b200 import KF
+    m, n, k = shape
+    rng = np.random.default_rng(55)
+    A, B, C0 = rand(rng, (m, k), np.float32), rand(rng, (n, k), np.float32), rand(rng, (m, n), np.float32)
+    for alpha, beta in ((1.0, 0.0), (0.5, 2.0)):
+        ref = alpha * (A.astype(np.float64) @ B.astype(np.float64).T) + beta * C0
+        Cd = dev(C0)
+        d = gpu.contract("ij", Cd, "ik", dev(A), "jk", dev(B), alpha, beta)
+        assert d.kernel_used == KF["TILE_TCGEN05"], d.kernel_used
+        assert rel_err(Cd.cpu().numpy().astype(np.float64), ref) <= 1e-5
+    Ct = dev(np.ascontiguousarray(C0.T))
+    d = gpu.contract("ji", Ct, "ik", dev(A), "jk", dev(B), 1.0, 0.0)    # C stored transposed: strided epilogue
+    assert d.kernel_used == KF["TILE_TCGEN05"]
+    assert rel_err(Ct.cpu().numpy().astype(np.float64).T, A.astype(np.float64) @ B.astype(np.float64).T) <= 1e-5
+    # long contractions stay on the FMA kernel (accumulator truncation grows with K)
+    A2, B2 = rand(rng, (256, 2048), np.float32), rand(rng, (256, 2048), np.float32)
+    C2 = torch.zeros(256, 256, dtype=torch.float32, device="cuda")
+    d = gpu.contract("ij", C2, "ik", dev(A2), "jk", dev(B2))
+    assert d.kernel_used == KF["TILE_SIMT"]
+    assert rel_err(C2.cpu().numpy().astype(np.float64), A2.astype(np.float64) @ B2.astype(np.float64).T) <= 1e-5
+
+
 def test_sgemm_zgemm(gpu, oracle):
     import ctypes as C
     rng = np.random.default_rng(9)
