@@ -12,7 +12,8 @@
 //   warp 1, one lane : tcgen05.mma issuer — 4 k-slices x 3 products per stage, kind::tf32, M=128 N=128 K=8, cta_group::1;
 //                      tcgen05.commit releases the stage to the producer and finally signals the epilogue
 //   epilogue         : tcgen05.ld 32x32b (each warp its own TMEM lane quadrant) -> alpha*acc + beta*C -> global
-// Accumulators never touch registers or shared memory during the main loop (TMEM, 128 columns).
+// Two 128-column TMEM accumulators alternate between chunks of 512 k; finished chunks are added into registers with
+// round-to-nearest (the tensor core's own FP32 accumulation truncates).
 #pragma once
 #include <cuda.h>
 
@@ -55,7 +56,8 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32x3_tcgen05(const __grid_const
     constexpr uint32_t TILE_BYTES = BM * BK * 4;                 // 16 KB per operand tile
     constexpr uint32_t RAW_BYTES = 2 * TILE_BYTES;               // A_raw | B_raw
     constexpr uint32_t STAGE_BYTES = 2 * RAW_BYTES;              // + A_lo | B_lo
-    constexpr uint32_t TMEM_COLS = 128;
+    constexpr uint32_t TMEM_COLS = 256;                          // two 128-column accumulators (ping-pong between K chunks)
+    constexpr int      KCB = 16;                                 // k-blocks per accumulation chunk (512 k)
     // instruction descriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
@@ -65,8 +67,9 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32x3_tcgen05(const __grid_const
     auto full_raw = [&](int s) { return bars + 8u * s; };
     auto full_lo = [&](int s) { return bars + 8u * (STAGES + s); };
     auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
-    const uint32_t tmem_full = bars + 8u * (3 * STAGES);
-    const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 1);    // 4 bytes: TMEM base address written by tcgen05.alloc
+    auto chunk_full = [&](int b) { return bars + 8u * (3 * STAGES + b); };
+    auto chunk_drained = [&](int b) { return bars + 8u * (3 * STAGES + 2 + b); };
+    const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4);    // 4 bytes: TMEM base address written by tcgen05.alloc
     unsigned char *smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -79,7 +82,10 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32x3_tcgen05(const __grid_const
             mbar_init(full_lo(s), 128);
             mbar_init(empty(s), 1);
         }
-        mbar_init(tmem_full, 1);
+        for (int b = 0; b < 2; b++) {
+            mbar_init(chunk_full(b), 1);
+            mbar_init(chunk_drained(b), 128);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -107,25 +113,62 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32x3_tcgen05(const __grid_const
         if (lane == 0) {
             for (int it = 0; it < nsteps; it++) {
                 const int s = it % STAGES;
+                const int c = it / KCB, cb = c & 1;               // accumulation chunk and its TMEM accumulator
+                if (it % KCB == 0 && c >= 2) {                     // the accumulator must have been drained (chunk c-2)
+                    mbar_wait(chunk_drained(cb), ((c >> 1) - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
                 mbar_wait(full_lo(s), (it / STAGES) & 1);   // splitters are done => the raw tile landed too
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_hi = smem_base + s * STAGE_BYTES, b_hi = a_hi + TILE_BYTES, a_lo = a_hi + RAW_BYTES, b_lo = a_lo + TILE_BYTES;
+                const uint32_t tacc = tmem_base + (uint32_t)cb * 128u;
 #pragma unroll
                 for (int kk = 0; kk < BK / 8; kk++) {
                     const uint32_t ko = kk * 32; // 8 tf32 = 32 bytes along K inside the 128-byte swizzle row
                     const uint64_t dah = umma_smem_desc_kmajor_sw128(a_hi + ko), dbh = umma_smem_desc_kmajor_sw128(b_hi + ko);
                     const uint64_t dal = umma_smem_desc_kmajor_sw128(a_lo + ko), dbl = umma_smem_desc_kmajor_sw128(b_lo + ko);
-                    umma_tf32(tmem_base, dal, dbh, IDESC, (it | kk) != 0);
-                    umma_tf32(tmem_base, dah, dbl, IDESC, 1);
-                    umma_tf32(tmem_base, dah, dbh, IDESC, 1);
+                    umma_tf32(tacc, dal, dbh, IDESC, ((it % KCB) | kk) != 0);
+                    umma_tf32(tacc, dah, dbl, IDESC, 1);
+                    umma_tf32(tacc, dah, dbh, IDESC, 1);
                 }
                 umma_commit(empty(s));
+                if (it % KCB == KCB - 1 || it == nsteps - 1) umma_commit(chunk_full(cb));
             }
-            umma_commit(tmem_full);
         }
     } else {
-        // ===================== splitters (warps 2..5, 128 threads) =====================
-        const int t = tid - 64;
+        // ===================== splitters (warps 2..5, 128 threads); they also drain finished K chunks =====================
+        const int     t = tid - 64;
+        const int     quad = warp & 3;                       // TMEM lane quadrant of this warp: warps 2,3,4,5 -> 2,3,0,1
+        const int     nchunks = (nsteps + KCB - 1) / KCB;
+        float         acc[BN];                               // this thread's output row (TMEM lane), summed over chunks in FP32 RN
+#pragma unroll
+        for (int j = 0; j < BN; j++) acc[j] = 0.f;
+        int drained = 0;
+        // The tensor core accumulates into TMEM with truncation, so the error of one accumulator grows linearly with the number of
+        // k-steps it has absorbed. Every KCB k-blocks the issuer switches to the other accumulator and the finished one is added
+        // into registers with round-to-nearest here; signs of the chunk biases are independent, so the total stays at the one-chunk level.
+        auto drain = [&](int d) {
+            const int db = d & 1;
+            mbar_wait(chunk_full(db), (d >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t       r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(db * 128 + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                      "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+                      "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+                      "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; j++) acc[c0 + j] += __uint_as_float(r[j]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(chunk_drained(db));
+        };
         for (int it = 0; it < nsteps; it++) {
             const int s = it % STAGES;
             mbar_wait(full_raw(s), (it / STAGES) & 1);
@@ -135,8 +178,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32x3_tcgen05(const __grid_const
             for (int i = 0; i < (int)(RAW_BYTES / 16 / 128); i++) {
                 const int idx = i * 128 + t;
                 float4    x = raw[idx], h, l;
-                // hi = x rounded to nearest TF32 (10-bit mantissa), lo = x - hi (exact) rounded to nearest TF32 as well: the hardware
-                // would truncate, which biases every product the same way and lets the error grow linearly with K
+                // hi = x rounded to nearest TF32 (10-bit mantissa), lo = x - hi (exact) rounded to nearest TF32 as well
                 auto rn_tf32 = [](float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); };
                 h.x = rn_tf32(x.x); l.x = rn_tf32(x.x - h.x);
                 h.y = rn_tf32(x.y); l.y = rn_tf32(x.y - h.y);
@@ -147,32 +189,24 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32x3_tcgen05(const __grid_const
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy stores -> visible to the tensor core's async proxy
             mbar_arrive(full_lo(s));
+            // a chunk is drained two k-blocks after its last k-block was split: its MMAs have normally completed by then, so neither
+            // side waits; the issuer only re-uses an accumulator after this drain (chunk_drained)
+            if (drained < nchunks - 1 && it >= (drained + 1) * KCB + 1) drain(drained++);
         }
-        // ===================== epilogue: each warp reads its own TMEM lane quadrant =====================
-        mbar_wait(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int     quad = warp & 3;                       // warps 2,3,4,5 -> quadrants 2,3,0,1
+        while (drained < nchunks) drain(drained++);
+
+        // ===================== epilogue: alpha*acc + beta*C, one output row per thread =====================
         const int64_t m = (int64_t)tile_m * BM + quad * 32 + lane;
         const float   alpha = args.alpha, beta = args.beta;
-#pragma unroll 1
+        float        *patch = reinterpret_cast<float *>(smem_gen) + (warp - 2) * (32 * 33);
+#pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t       r[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-                  "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-                  "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
-                  "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             const int64_t n0 = (int64_t)tile_n * BN + c0;
             if (args.sCn == 1) {
                 // C rows are contiguous along n: transpose the 32x32 chunk through a warp-private shared-memory patch (the pipeline
                 // stages are idle by now) so that every store/load instruction covers one 128-byte row segment
-                float *patch = reinterpret_cast<float *>(smem_gen) + (warp - 2) * (32 * 33);
 #pragma unroll
-                for (int j = 0; j < 32; j++) patch[lane * 33 + j] = __uint_as_float(r[j]);
+                for (int j = 0; j < 32; j++) patch[lane * 33 + j] = acc[c0 + j];
                 __syncwarp();
                 const int64_t n = n0 + lane, mrow0 = (int64_t)tile_m * BM + quad * 32;
                 if (n < args.N) {
@@ -198,7 +232,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32x3_tcgen05(const __grid_const
                 for (int j = 0; j < 32; j++) {
                     const int64_t n = n0 + j;
                     if (n < args.N) {
-                        float v = alpha * __uint_as_float(r[j]);
+                        float v = alpha * acc[c0 + j];
                         if (beta != 0.f) v = fmaf(beta, crow[n * args.sCn], v);
                         crow[n * args.sCn] = v;
                     }

@@ -4,7 +4,7 @@ import torch
 from einsums_b200 import ops, KF_NAMES
 ops.init(0)
 torch.manual_seed(0)
-for (M, N, K) in ((256, 256, 64), (256, 384, 512), (1000, 520, 260), (4096, 4096, 4096)):
+for (M, N, K) in ((256, 256, 64), (256, 384, 512), (1000, 520, 260), (512, 512, 1100), (512, 384, 16384), (400, 400, 40000), (4096, 4096, 4096)):
     A = torch.rand(M, K, dtype=torch.float32, device="cuda") * 2 - 1
     B = torch.rand(N, K, dtype=torch.float32, device="cuda") * 2 - 1
     C0 = torch.rand(M, N, dtype=torch.float32, device="cuda") * 2 - 1
