@@ -186,14 +186,20 @@ int try_run_tma(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const dou
 
 // ---------------------------------------------------------------- tcgen05 3xTF32 path (plain FP32 GEMM, both operands K-major)
 int g_use_tcgen05 = -1; // EB200_USE_TCGEN05=0 falls back to the FMA tile kernel
-bool make_operand_map_f32(CUtensorMap *map, const float *base, int64_t inner, int64_t outer, int64_t ld, uint32_t box_inner, uint32_t box_outer) {
+int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+bool make_operand_map_f32(CUtensorMap *map, const float *base, int64_t inner, int64_t outer, int64_t ld, uint32_t box_inner, uint32_t box_outer,
+                          bool mn = false) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return false;
     cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t es[2] = {1, 1};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    CUtensorMapSwizzle sw = mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B; // see gemm_tf32x3.cuh
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 int try_run_tf32x3(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const double beta_eff[2]) {
@@ -205,13 +211,18 @@ int try_run_tf32x3(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const 
     if (p.b.n != 0 || p.m.n != 1 || p.n.n != 1 || p.k.n != 1) return 0;
     const float  *A = (const float *)d.A.data, *B = (const float *)d.B.data;
     const int64_t M = p.m.tot, N = p.n.tot, K = p.k.tot;
-    if (p.k.s[ROLE_A][0] != 1 || p.k.s[ROLE_B][0] != 1) return 0; // both operands K-major
-    const int64_t lda = p.m.s[ROLE_A][0], ldb = p.n.s[ROLE_B][0];
+    const int64_t sAm = p.m.s[ROLE_A][0], sAk = p.k.s[ROLE_A][0], sBn = p.n.s[ROLE_B][0], sBk = p.k.s[ROLE_B][0];
+    const bool    a_mn = (sAk != 1), b_mn = (sBk != 1); // MN-major: the target index is the contiguous one
+    if (a_mn && sAm != 1) return 0;
+    if (b_mn && sBn != 1) return 0;
+    const int64_t lda = a_mn ? sAk : sAm, ldb = b_mn ? sBk : sBn;
     if (lda <= 0 || ldb <= 0 || (lda & 3) || (ldb & 3) || ((uintptr_t)A % 16) || ((uintptr_t)B % 16)) return 0;
-    if (M >= (1LL << 31) || N >= (1LL << 31) || K >= (1LL << 31) || lda >= (1LL << 36) || ldb >= (1LL << 36) || K > lda || K > ldb) return 0;
+    if (M >= (1LL << 31) || N >= (1LL << 31) || K >= (1LL << 31) || lda >= (1LL << 36) || ldb >= (1LL << 36)) return 0;
+    if ((a_mn ? M : K) > lda || (b_mn ? N : K) > ldb) return 0;
     if (M * N < 128 * 128 * 4) return 0; // tiny outputs: the FMA kernel (with split-K) is the better fit
     CUtensorMap tmA, tmB;
-    if (!make_operand_map_f32(&tmA, A, K, M, lda, 32, 128) || !make_operand_map_f32(&tmB, B, K, N, ldb, 32, 128)) return 0;
+    if (!(a_mn ? make_operand_map_f32(&tmA, A, M, K, lda, 32, 32, true) : make_operand_map_f32(&tmA, A, K, M, lda, 32, 128))) return 0;
+    if (!(b_mn ? make_operand_map_f32(&tmB, B, N, K, ldb, 32, 32, true) : make_operand_map_f32(&tmB, B, K, N, ldb, 32, 128))) return 0;
     Tf32GemmArgs a;
     a.M = M; a.N = N; a.K = K;
     a.sCm = p.m.s[ROLE_C][0]; a.sCn = p.n.s[ROLE_C][0];
@@ -221,7 +232,7 @@ int try_run_tf32x3(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const 
     if (tm * tn > 0x7fffffffLL) return 0;
     a.tiles_m = (int)tm; a.tiles_n = (int)tn;
     constexpr size_t SMEM = 3 * 65536 + 1024 + 128;
-    int rc = k_launch_tf32x3(s, tmA, tmB, a, dim3((unsigned)(tm * tn), 1, 1), SMEM);
+    int rc = k_launch_tf32x3(s, tmA, tmB, a, dim3((unsigned)(tm * tn), 1, 1), SMEM, a_mn, b_mn);
     if (rc) return -rc;
     d.launches++;
     d.split_k = 1;

@@ -30,10 +30,16 @@ struct Tf32GemmArgs {
 };
 
 #ifdef EB200_TF32_KERNEL_IMPL // the kernel itself is compiled by k_tile_tf32.cu only
-__device__ __forceinline__ uint64_t umma_smem_desc_kmajor_sw128(uint32_t smem_addr) {
-    // canonical K-major SWIZZLE_128B layout: 128-byte rows, 8-row atoms 1024 bytes apart:
-    //   start address >> 4 | LBO (16 B units) = 1 at bit 16 | SBO = 1024 B >> 4 = 64 at bit 32 | version 1 at bit 46 | layout SWIZZLE_128B (2) at bit 61
-    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+// Shared-memory matrix descriptor, SWIZZLE_128B (layout type 2), descriptor version 1 (Blackwell):
+//   start address >> 4 at bit 0 | leading byte offset >> 4 at bit 16 | stride byte offset >> 4 at bit 32 | version at bit 46 | layout at bit 61
+// K-major tile  (128-byte rows run along K, row = m; TMA SWIZZLE_128B):
+//     layout type 2 (SWIZZLE_128B), LBO = 16 B (unused), SBO = 1024 B (next 8 rows of m)
+// MN-major tile (128-byte rows run along M/N, row = k; 32-bit elements need the 32-byte-atom swizzle, TMA SWIZZLE_128B_ATOM_32B):
+//     layout type 1 (SWIZZLE_128B_BASE32B), LBO = 4096 B (next 32 m = next TMA box), SBO = 512 B (next 4 k: the swizzle atom is 4 rows)
+// (the MN-major field values were confirmed by a parameter sweep on the B200, tools/dbg_tf32_mn.py)
+template <bool MN_MAJOR> __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
+    constexpr uint64_t LBO = MN_MAJOR ? (4096 >> 4) : 1, SBO = MN_MAJOR ? (512 >> 4) : (1024 >> 4), LT = MN_MAJOR ? 1 : 2;
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (LBO << 16) | (SBO << 32) | ((uint64_t)1 << 46) | (LT << 61);
 }
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -50,6 +56,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(192, 1) gemm_tf32x3_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                              const __grid_constant__ Tf32GemmArgs args) {
     constexpr int      BM = 128, BN = 128, BK = 32, STAGES = 3;
@@ -59,7 +66,8 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32x3_tcgen05(const __grid_const
     constexpr uint32_t TMEM_COLS = 256;                          // two 128-column accumulators (ping-pong between K chunks)
     constexpr int      KCB = 16;                                 // k-blocks per accumulation chunk (512 k)
     // instruction descriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)(BM >> 4) << 24);
 
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -105,8 +113,14 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32x3_tcgen05(const __grid_const
                 if (it >= STAGES) mbar_wait(empty(s), ((it / STAGES) - 1) & 1);
                 const uint32_t a_dst = smem_base + s * STAGE_BYTES, b_dst = a_dst + TILE_BYTES;
                 mbar_expect_tx(full_raw(s), RAW_BYTES);
-                tma_load_2d(a_dst, &tmA, full_raw(s), it * BK, tile_m * BM);
-                tma_load_2d(b_dst, &tmB, full_raw(s), it * BK, tile_n * BN);
+                if constexpr (A_MN) { // box {32 m, 32 k}: four boxes cover the 128 rows of the tile
+#pragma unroll
+                    for (int b = 0; b < 4; b++) tma_load_2d(a_dst + b * 4096, &tmA, full_raw(s), tile_m * BM + 32 * b, it * BK);
+                } else tma_load_2d(a_dst, &tmA, full_raw(s), it * BK, tile_m * BM); // box {32 k, 128 m}
+                if constexpr (B_MN) {
+#pragma unroll
+                    for (int b = 0; b < 4; b++) tma_load_2d(b_dst + b * 4096, &tmB, full_raw(s), tile_n * BN + 32 * b, it * BK);
+                } else tma_load_2d(b_dst, &tmB, full_raw(s), it * BK, tile_n * BN);
             }
         }
     } else if (warp == 1) {
@@ -124,9 +138,10 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32x3_tcgen05(const __grid_const
                 const uint32_t tacc = tmem_base + (uint32_t)cb * 128u;
 #pragma unroll
                 for (int kk = 0; kk < BK / 8; kk++) {
-                    const uint32_t ko = kk * 32; // 8 tf32 = 32 bytes along K inside the 128-byte swizzle row
-                    const uint64_t dah = umma_smem_desc_kmajor_sw128(a_hi + ko), dbh = umma_smem_desc_kmajor_sw128(b_hi + ko);
-                    const uint64_t dal = umma_smem_desc_kmajor_sw128(a_lo + ko), dbl = umma_smem_desc_kmajor_sw128(b_lo + ko);
+                    // one MMA consumes 8 k: 32 bytes along the swizzle row of a K-major tile, one 8-row (1024-byte) atom of an MN-major tile
+                    const uint32_t koa = kk * (A_MN ? 1024 : 32), kob = kk * (B_MN ? 1024 : 32);
+                    const uint64_t dah = umma_smem_desc_sw128<A_MN>(a_hi + koa), dbh = umma_smem_desc_sw128<B_MN>(b_hi + kob);
+                    const uint64_t dal = umma_smem_desc_sw128<A_MN>(a_lo + koa), dbl = umma_smem_desc_sw128<B_MN>(b_lo + kob);
                     umma_tf32(tacc, dal, dbh, IDESC, ((it % KCB) | kk) != 0);
                     umma_tf32(tacc, dah, dbl, IDESC, 1);
                     umma_tf32(tacc, dah, dbh, IDESC, 1);
@@ -227,13 +242,19 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32x3_tcgen05(const __grid_const
                 }
                 __syncwarp();
             } else if (m < args.M) {
+                // lanes are consecutive rows m: coalesced when C is contiguous along m (the "transposed C" case, e.g. Wabef)
                 float *crow = args.C + m * args.sCm;
+                float  old[32];
+                if (beta != 0.f) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) old[j] = (n0 + j < args.N) ? crow[(n0 + j) * args.sCn] : 0.f;
+                }
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
                     const int64_t n = n0 + j;
                     if (n < args.N) {
                         float v = alpha * acc[c0 + j];
-                        if (beta != 0.f) v = fmaf(beta, crow[n * args.sCn], v);
+                        if (beta != 0.f) v = fmaf(beta, old[j], v);
                         crow[n * args.sCn] = v;
                     }
                 }

@@ -289,6 +289,32 @@ def test_sgemm_tcgen05_3xtf32(gpu, oracle, shape):
         assert rel_err(C2.cpu().numpy().astype(np.float64), A2.astype(np.float64) @ B2.astype(np.float64).T) <= 1e-5, kk
 
 
+@pytest.mark.parametrize("a_idx,b_idx", [("ik", "jk"), ("ki", "jk"), ("ik", "kj"), ("ki", "kj")])
+def test_sgemm_tcgen05_layouts(gpu, a_idx, b_idx):
+    """All four operand layouts of the tcgen05 kernel: K-major tiles (one TMA box, descriptor advance inside the swizzle row) and
+    MN-major tiles (four 32x32 boxes, descriptor advance by 8-row atoms), incl. the FP32 Wabef pattern (both MN-major)."""
+    from einsums_b200 import KF
+    rng = np.random.default_rng(77)
+    m, n, k = 260, 392, 200
+    ext = dict(i=m, j=n, k=k)
+    A = rand(rng, tuple(ext[x] for x in a_idx), np.float32)
+    B = rand(rng, tuple(ext[x] for x in b_idx), np.float32)
+    C0 = rand(rng, (m, n), np.float32)
+    ref = 0.5 * np.einsum(f"{a_idx},{b_idx}->ij", A.astype(np.float64), B.astype(np.float64)) + 2.0 * C0
+    Cd = dev(C0)
+    d = gpu.contract("ij", Cd, a_idx, dev(A), b_idx, dev(B), 0.5, 2.0)
+    assert d.kernel_used == KF["TILE_TCGEN05"], d.kernel_used
+    assert rel_err(Cd.cpu().numpy().astype(np.float64), ref) <= 1e-5
+    # CCD Wabef in FP32: abef <- mnef, mnab (both operands MN-major after index fusion)
+    o, v = 6, 24
+    g, t, W0 = rand(rng, (o, o, v, v), np.float32), rand(rng, (o, o, v, v), np.float32), rand(rng, (v, v, v, v), np.float32)
+    refW = W0 + 0.25 * np.einsum("mnef,mnab->abef", g.astype(np.float64), t.astype(np.float64))
+    Wd = dev(W0)
+    d = gpu.contract("abef", Wd, "mnef", dev(g), "mnab", dev(t), 0.25, 1.0)
+    assert d.kernel_used == KF["TILE_TCGEN05"], d.kernel_used
+    assert rel_err(Wd.cpu().numpy().astype(np.float64), refW) <= 1e-5
+
+
 def test_sgemm_zgemm(gpu, oracle):
     import ctypes as C
     rng = np.random.default_rng(9)
