@@ -281,9 +281,8 @@ template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract
     } else { bm = 64; bn = 64; bk = 8; ctas_per_sm = 4; }
 
     const int64_t tm = (p.m.tot + bm - 1) / bm, tn = (p.n.tot + bn - 1) / bn;
-    if (tm * tn > 0x7fffffffLL || p.b.tot > 65535)
-        return fail(EB200_ERR_UNSUPPORTED, "contract: tile grid too large (%lld x %lld tiles, %lld batches)", (long long)tm, (long long)tn,
-                    (long long)p.b.tot);
+    if (tm * tn > 0x7fffffffLL)
+        return fail(EB200_ERR_UNSUPPORTED, "contract: tile grid too large (%lld x %lld tiles)", (long long)tm, (long long)tn);
     args.tiles_m = (int)tm;
     args.tiles_n = (int)tn;
 
@@ -308,16 +307,19 @@ template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract
         if (rc) return rc;
         args.ws = ws;
     }
-    dim3 grid((unsigned)(tm * tn), (unsigned)splits, (unsigned)p.b.tot);
-    int  rc;
-    if (mma) {
-        if constexpr (std::is_same_v<T, double>) rc = k_launch_mma(s, args, grid);
-        else rc = fail(EB200_ERR_UNSUPPORTED, "tile_mma is FP64 only");
-    } else {
-        rc = k_launch_simt(Scalar<T>::dtype, s, args, grid);
+    int rc = EB200_OK;
+    for (int64_t b0 = 0; b0 < p.b.tot && rc == EB200_OK; b0 += 65535) { // grid.z holds at most 65535 batches per launch
+        dim3 grid((unsigned)(tm * tn), (unsigned)splits, (unsigned)std::min<int64_t>(65535, p.b.tot - b0));
+        args.batch0 = b0;
+        if (mma) {
+            if constexpr (std::is_same_v<T, double>) rc = k_launch_mma(s, args, grid);
+            else rc = fail(EB200_ERR_UNSUPPORTED, "tile_mma is FP64 only");
+        } else {
+            rc = k_launch_simt(Scalar<T>::dtype, s, args, grid);
+        }
+        if (rc == EB200_OK) d.launches++;
     }
     if (rc) return rc;
-    d.launches++;
     if (splits > 1) {
         rc = launch_finalize<T>(s, p.b, p.m, p.n, ws, d.C.data, d.alpha, beta_eff, splits, d);
         if (rc) return rc;

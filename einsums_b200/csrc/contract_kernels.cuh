@@ -45,6 +45,7 @@ struct TileArgs {
     int32_t       conj_a, conj_b;
     int32_t       vec_ab;    // A and B tiles can be fetched as aligned 16-byte pairs along their fast direction
     int32_t       vec_c;     // C pairs (n, n+1) are adjacent and 16-byte aligned
+    int64_t       batch0;    // first batch of this launch (grid.z is limited to 65535)
 };
 
 // 16-byte async copy global->shared (L2 only); src_bytes == 0 zero-fills
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) tile_mma_f64
         tile_n = in_g / gsize;
     }
     const int     split = blockIdx.y;
-    const int64_t batch = blockIdx.z;
+    const int64_t batch = blockIdx.z + args.batch0;
 
     int64_t baseA, baseB, baseC;
     grp_offset3(p.b, batch, baseA, baseB, baseC);
@@ -310,7 +311,7 @@ template <typename T, bool CONJ_A, bool CONJ_B> __global__ void __launch_bounds_
     const int   tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
     const int   tile_m = blockIdx.x % args.tiles_m, tile_n = blockIdx.x / args.tiles_m;
     const int   split = blockIdx.y;
-    const int64_t batch = blockIdx.z;
+    const int64_t batch = blockIdx.z + args.batch0;
 
     int64_t baseA, baseB, baseC;
     grp_offset3(p.b, batch, baseA, baseB, baseC);

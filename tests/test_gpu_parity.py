@@ -167,6 +167,21 @@ def test_contract_strided_views(gpu, oracle):
     assert np.array_equal(cd.cpu().numpy()[mask], Cfull[mask])
 
 
+def test_contract_many_batches(gpu):
+    """More batches than grid.z can hold (65535): the launcher walks the batch index in chunks."""
+    nb = 70001
+    A = torch.rand(nb, 9, 10, dtype=torch.float64, device="cuda") - 0.5
+    B = torch.rand(nb, 10, 11, dtype=torch.float64, device="cuda") - 0.5
+    C = torch.zeros(nb, 9, 11, dtype=torch.float64, device="cuda")
+    d = gpu.contract("bij", C, "bik", A, "bkj", B)
+    assert d.launches == 2
+    ref = torch.bmm(A, B)
+    assert rel_err(C.cpu().numpy(), ref.cpu().numpy()) <= 1e-12
+    Cf = torch.zeros(nb, 9, 11, dtype=torch.float32, device="cuda")
+    gpu.contract("bij", Cf, "bik", A.float(), "bkj", B.float())
+    assert rel_err(Cf.cpu().numpy(), ref.cpu().numpy()) <= 1e-5
+
+
 def test_beta_zero_never_reads_c(gpu):
     A = torch.rand(70, 50, dtype=torch.float64, device="cuda")
     B = torch.rand(50, 90, dtype=torch.float64, device="cuda")
