@@ -278,7 +278,7 @@ template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract
         args.vec_ab = operand_pairs_ok(p, ROLE_A, p.a_kmajor ? p.k : p.m, p.a_kmajor ? p.m : p.k, args.A) &&
                       operand_pairs_ok(p, ROLE_B, p.b_kmajor ? p.k : p.n, p.b_kmajor ? p.n : p.k, args.B);
         args.vec_c = operand_pairs_ok(p, ROLE_C, p.n, p.m, args.C);
-    } else { bm = 64; bn = 64; bk = 8; ctas_per_sm = 4; }
+    } else { bm = SimtCfg<T>::BM; bn = SimtCfg<T>::BN; bk = SimtCfg<T>::BK; ctas_per_sm = 2; }
 
     const int64_t tm = (p.m.tot + bm - 1) / bm, tn = (p.n.tot + bn - 1) / bn;
     if (tm * tn > 0x7fffffffLL)

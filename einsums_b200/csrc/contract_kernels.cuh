@@ -52,6 +52,11 @@ struct TileArgs {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes));
 }
+// element-sized async copy (4, 8 or 16 bytes); valid == false zero-fills
+template <int BYTES> __device__ __forceinline__ void cp_async_elem(uint32_t dst, const void *src, bool valid) {
+    static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async size");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;\n" ::"r"(dst), "l"(src), "n"(BYTES), "r"(valid ? BYTES : 0));
+}
 
 // ------------------------------------------------------------------------------------------
 // FP64 tensor-pipe tile kernel
@@ -299,13 +304,26 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) tile_mma_f64
 }
 
 // ------------------------------------------------------------------------------------------
-// FMA-pipe tile kernel (f32, complex, and f64 for cross-checks): 64x64x8 tile, 4x4 per thread
+// FMA-pipe tile kernel (f32 generic contractions, complex, and f64 for cross-checks).
+// 256 threads as 16 x 16, TM x TN outputs per thread (8x8 for 4-byte types, 4x4 otherwise), BK = 16 (8 for 16-byte types),
+// double-buffered shared memory filled by cp.async: the gathers of step it+1 are in flight while step it is multiplied.
+// Same fused-permutation addressing as tile_mma_f64: base + moff[m] + koff[k].
 // ------------------------------------------------------------------------------------------
-template <typename T, bool CONJ_A, bool CONJ_B> __global__ void __launch_bounds__(256) tile_simt(const __grid_constant__ TileArgs args) {
-    constexpr int BM = 64, BN = 64, BK = 8, NT = 256;
-    __shared__ T       As[BK][BM + 1];
-    __shared__ T       Bs[BK][BN + 1];
-    __shared__ int64_t moffA[BM], moffC[BM], noffB[BN], noffC[BN];
+template <typename T> struct SimtCfg {
+    static constexpr int TM = sizeof(T) == 4 ? 8 : 4, TN = TM;
+    static constexpr int BM = 16 * TM, BN = 16 * TN;
+    static constexpr int BK = sizeof(T) == 16 ? 8 : 16;
+};
+
+template <typename T, bool CONJ_A, bool CONJ_B> __global__ void __launch_bounds__(256, 2) tile_simt(const __grid_constant__ TileArgs args) {
+    using Cfg = SimtCfg<T>;
+    constexpr int TM = Cfg::TM, TN = Cfg::TN, BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, NT = 256;
+    constexpr int EA = BM * BK / NT, EB = BN * BK / NT;
+    constexpr bool V4 = sizeof(T) == 4; // 4-byte types read their 8 + 8 operands as four 16-byte shared loads
+    constexpr int  PAD = V4 ? 4 : 1;
+    __shared__ __align__(16) T As[2][BK][BM + PAD];
+    __shared__ __align__(16) T Bs[2][BK][BN + PAD];
+    __shared__ int64_t moffA[BM], moffC[BM], noffB[BN], noffC[BN], koffA[3][BK], koffB[3][BK];
 
     const Plan &p = args.p;
     const int   tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
@@ -321,6 +339,7 @@ template <typename T, bool CONJ_A, bool CONJ_B> __global__ void __launch_bounds_
     const int64_t Mtot = p.m.tot, Ntot = p.n.tot, Ktot = p.k.tot;
     const int     KT = (int)((Ktot + BK - 1) / BK);
     const int     ks0 = (int)((int64_t)KT * split / args.splits), ks1 = (int)((int64_t)KT * (split + 1) / args.splits);
+    const int     nsteps = ks1 - ks0;
 
     for (int i = tid; i < BM; i += NT) {
         int64_t m = (int64_t)tile_m * BM + i, oa = OFF_INVALID, oc = OFF_INVALID;
@@ -332,49 +351,91 @@ template <typename T, bool CONJ_A, bool CONJ_B> __global__ void __launch_bounds_
         if (n < Ntot) grp_offset2(p.n, n, ROLE_B, ROLE_C, ob, oc);
         noffB[i] = ob; noffC[i] = oc;
     }
+    auto compute_koff = [&](int step) { // threads < BK
+        int64_t k = (int64_t)(ks0 + step) * BK + tid, oa = OFF_INVALID, ob = OFF_INVALID;
+        if (k < Ktot) grp_offset2(p.k, k, ROLE_A, ROLE_B, oa, ob);
+        koffA[step % 3][tid] = oa;
+        koffB[step % 3][tid] = ob;
+    };
+    if (tid < BK) {
+        compute_koff(0);
+        if (nsteps > 1) compute_koff(1);
+    }
     __syncthreads();
 
-    T acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j] = zero_of<T>();
+    // Each thread's EA (EB) elements share one coordinate (k when the operand is k-major, else m/n) and step through the
+    // other, so one offset is hoisted and the other comes from a single table walk.
+    constexpr int PA = BM + PAD, PB = BN + PAD;
+    const bool    akm = p.a_kmajor, bkm = p.b_kmajor;
+    const int     a_fix = akm ? tid % BK : tid % BM, a_v0 = akm ? tid / BK : tid / BM, a_vs = akm ? NT / BK : NT / BM;
+    const int     b_fix = bkm ? tid % BK : tid % BN, b_v0 = bkm ? tid / BK : tid / BN, b_vs = bkm ? NT / BK : NT / BN;
+    const int     a_s0 = akm ? a_fix * PA + a_v0 : a_v0 * PA + a_fix, a_ss = akm ? a_vs : a_vs * PA;
+    const int     b_s0 = bkm ? b_fix * PB + b_v0 : b_v0 * PB + b_fix, b_ss = bkm ? b_vs : b_vs * PB;
+    const int64_t a_mfix = akm ? 0 : moffA[a_fix], b_nfix = bkm ? 0 : noffB[b_fix];
 
-    // loader mapping: 512 elements per operand per step, 2 per thread; lanes run along the
-    // direction that is contiguous in global memory
-    for (int ks = ks0; ks < ks1; ks++) {
+    auto issue = [&](int step) { // global -> shared, asynchronously; out-of-range elements are zero-filled
+        const int64_t *ka = koffA[step % 3], *kb = koffB[step % 3];
+        {
+            const int64_t  ofix = akm ? ka[a_fix] : a_mfix;
+            const int64_t *tab  = akm ? moffA : ka;
+            const uint32_t dst  = smem_u32(&As[step & 1][0][0] + a_s0);
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            int e = tid + j * NT, ml, kl;
-            if (p.a_kmajor) { kl = e % BK; ml = e / BK; } else { ml = e % BM; kl = e / BM; }
-            int64_t k = (int64_t)ks * BK + kl, om = moffA[ml];
-            T       v = zero_of<T>();
-            if (k < Ktot && om != OFF_INVALID) v = maybe_conj<CONJ_A>(A[om + grp_offset(p.k, k, ROLE_A)]);
-            As[kl][ml] = v;
+            for (int j = 0; j < EA; j++) {
+                int64_t ov = tab[a_v0 + j * a_vs];
+                bool    v  = ofix != OFF_INVALID && ov != OFF_INVALID;
+                cp_async_elem<sizeof(T)>(dst + (uint32_t)(j * a_ss * sizeof(T)), v ? (const void *)(A + ofix + ov) : (const void *)A, v);
+            }
         }
+        {
+            const int64_t  ofix = bkm ? kb[b_fix] : b_nfix;
+            const int64_t *tab  = bkm ? noffB : kb;
+            const uint32_t dst  = smem_u32(&Bs[step & 1][0][0] + b_s0);
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            int e = tid + j * NT, nl, kl;
-            if (p.b_kmajor) { kl = e % BK; nl = e / BK; } else { nl = e % BN; kl = e / BN; }
-            int64_t k = (int64_t)ks * BK + kl, on = noffB[nl];
-            T       v = zero_of<T>();
-            if (k < Ktot && on != OFF_INVALID) v = maybe_conj<CONJ_B>(B[on + grp_offset(p.k, k, ROLE_B)]);
-            Bs[kl][nl] = v;
+            for (int j = 0; j < EB; j++) {
+                int64_t ov = tab[b_v0 + j * b_vs];
+                bool    v  = ofix != OFF_INVALID && ov != OFF_INVALID;
+                cp_async_elem<sizeof(T)>(dst + (uint32_t)(j * b_ss * sizeof(T)), v ? (const void *)(B + ofix + ov) : (const void *)B, v);
+            }
         }
-        __syncthreads();
+    };
+
+    // tile-local row of accumulator i / column of accumulator j
+    auto row_of = [&](int i) { return V4 ? 64 * (i >> 2) + 4 * ty + (i & 3) : ty + 16 * i; };
+    auto col_of = [&](int j) { return V4 ? 64 * (j >> 2) + 4 * tx + (j & 3) : tx + 16 * j; };
+
+    T acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) acc[i][j] = zero_of<T>();
+
+    if (nsteps > 0) issue(0);
+    cp_async_commit();
+    for (int it = 0; it < nsteps; it++) {
+        cp_async_wait<0>();
+        __syncthreads(); // step `it` has landed; every thread is done with step it-1, so its buffer and k-offset slot are free
+        if (tid < BK && it + 2 < nsteps) compute_koff(it + 2);
+        if (it + 1 < nsteps) issue(it + 1); // in flight during the multiply below
+        cp_async_commit();
 #pragma unroll
         for (int kk = 0; kk < BK; kk++) {
-            T a[4], b[4];
+            T a[TM], b[TN];
+            if constexpr (V4) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) a[i] = As[kk][ty + 16 * i];
+                for (int h = 0; h < TM / 4; h++) *reinterpret_cast<float4 *>(&a[4 * h]) = *reinterpret_cast<const float4 *>(&As[it & 1][kk][64 * h + 4 * ty]);
 #pragma unroll
-            for (int j = 0; j < 4; j++) b[j] = Bs[kk][tx + 16 * j];
+                for (int h = 0; h < TN / 4; h++) *reinterpret_cast<float4 *>(&b[4 * h]) = *reinterpret_cast<const float4 *>(&Bs[it & 1][kk][64 * h + 4 * tx]);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+                for (int i = 0; i < TM; i++) a[i] = maybe_conj<CONJ_A>(As[it & 1][kk][ty + 16 * i]);
 #pragma unroll
-                for (int j = 0; j < 4; j++) acc[i][j] = fma_(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < TN; j++) b[j] = maybe_conj<CONJ_B>(Bs[it & 1][kk][tx + 16 * j]);
+            }
+#pragma unroll
+            for (int i = 0; i < TM; i++)
+#pragma unroll
+                for (int j = 0; j < TN; j++) acc[i][j] = fma_(a[i], b[j], acc[i][j]);
         }
-        __syncthreads();
     }
 
     if (args.splits == 1) {
@@ -382,12 +443,12 @@ template <typename T, bool CONJ_A, bool CONJ_B> __global__ void __launch_bounds_
         const T    alpha = make_scalar<T>(args.alpha[0], args.alpha[1]), beta = make_scalar<T>(args.beta[0], args.beta[1]);
         const bool has_beta = !is_zero(beta);
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            int64_t om = moffC[ty + 16 * i];
+        for (int i = 0; i < TM; i++) {
+            int64_t om = moffC[row_of(i)];
             if (om == OFF_INVALID) continue;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                int64_t on = noffC[tx + 16 * j];
+            for (int j = 0; j < TN; j++) {
+                int64_t on = noffC[col_of(j)];
                 if (on == OFF_INVALID) continue;
                 T *dst = C + om + on;
                 *dst = axpby_(alpha, acc[i][j], beta, has_beta ? *dst : zero_of<T>(), has_beta);
@@ -396,12 +457,12 @@ template <typename T, bool CONJ_A, bool CONJ_B> __global__ void __launch_bounds_
     } else {
         T *ws = reinterpret_cast<T *>(args.ws) + (((int64_t)split * p.b.tot + batch) * Mtot) * Ntot;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            int64_t m = (int64_t)tile_m * BM + ty + 16 * i;
+        for (int i = 0; i < TM; i++) {
+            int64_t m = (int64_t)tile_m * BM + row_of(i);
             if (m >= Mtot) continue;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                int64_t n = (int64_t)tile_n * BN + tx + 16 * j;
+            for (int j = 0; j < TN; j++) {
+                int64_t n = (int64_t)tile_n * BN + col_of(j);
                 if (n < Ntot) ws[m * Ntot + n] = acc[i][j];
             }
         }
