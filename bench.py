@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-v", type=int, default=0, help="v for the CPU sample (0 = full config)")
+    ap.add_argument("--cpu-configs", action="store_true",
+                    help="with --impl reference: also time the CPU port on the other BASELINE configs at host-sized samples (one JSON line each)")
     return ap.parse_args()
 
 
@@ -130,6 +132,48 @@ def cpu_reference(steps, warmup, v_sample=0, threads=None):
                       f", {steps} steps after {warmup} warm-up; oracle analyser -> {info}", "ms_per_step": dt * 1e3}
 
 
+def cpu_other_configs():
+    """SURVEY.md section 8(d) 'CPU baseline beside it' for the non-headline configs, at sizes that fit the host: the oracle's
+    analyser + OpenBLAS routes / OpenMP generic loops / blocked transpose, all host threads, median of 3 after one warm-up."""
+    import numpy as np
+    from oracle import binding as orc
+    info = orc.load_openblas()
+    ncores = os.cpu_count() or 1
+    orc.lib().orc_blas_set_threads(ncores)
+    rng = np.random.default_rng(20251017)
+
+    def med(fn, reps=3):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return sorted(ts)[len(ts) // 2]
+
+    def emit(cfg, what, value, unit, route, sample):
+        print(json.dumps({"impl": "reference", "config": {"workload": cfg}, "op": what, "value": value, "unit": unit, "route": route,
+                          "cpu_baseline": {"value": value, "unit": unit, "cores": ncores, "kind": "port", "sample": sample + f"; {info}"}}), flush=True)
+
+    n = 100
+    g = rng.uniform(-1, 1, (n, n, n, n)); D = rng.uniform(-1, 1, (n, n)); J = np.zeros((n, n)); K = np.zeros((n, n))
+    route = [None]
+    t = med(lambda: route.__setitem__(0, orc.einsum_f64("pq", J, "pqrs", g, "rs", D, 2.0, 0.0)))
+    emit("cfg1 Fock J n=100", "pq<-pqrs,rs", 8.0 * n**4 / t / 1e9, "GB/s", route[0], "full size")
+    t = med(lambda: route.__setitem__(0, orc.einsum_f64("pq", K, "prqs", g, "rs", D, -1.0, 0.0)))
+    emit("cfg1/cfg3b Fock K n=100", "pq<-prqs,rs", 8.0 * n**4 / t / 1e9, "GB/s", route[0], "full size for cfg1; cfg3b (n=300, 64.8 GB) not sampled")
+    del g
+    o, v = 30, 120
+    t2 = rng.uniform(-1, 1, (o, o, v, v)); gg = rng.uniform(-1, 1, (o, o, v, v)); W = rng.uniform(-1, 1, (o, v, v, o))
+    t = med(lambda: route.__setitem__(0, orc.einsum_f64("mbej", W, "jnfb", t2, "mnef", gg, -0.5, 1.0)), reps=1)
+    emit("cfg3a Wmbej", "mbej<-jnfb,mnef", 2.0 * o**3 * v**3 / t / 1e12, "TFLOP/s", route[0], f"reduced sample o={o} v={v} (config: o=60 v=240), 1 rep")
+    for n in (64, 96):
+        A = rng.uniform(-1, 1, (n, n, n, n)); Cn = np.empty_like(A)
+        for order in ("lkji", "ikjl", "jilk"):
+            t = med(lambda: orc.permute(order, Cn, "ijkl", A, 1.0, 0.0, fast=True))
+            emit(f"cfg4 permute n={n}", f"{order}<-ijkl", 16.0 * n**4 / t / 1e9, "GB/s", "blocked transpose", "full size, 3 of the 24 orders")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -146,6 +190,8 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+    if args.cpu_configs:
+        cpu_other_configs()
 
 
 # ------------------------------------------------------------------------------------------------ our arm
