@@ -85,6 +85,7 @@ def _declare(lib):
     lib.eb200_launch_count_reset.restype = None
     lib.eb200_contract.argtypes = [vp, C.POINTER(ContractDesc)]
     lib.eb200_contract_plan.argtypes = [C.POINTER(ContractDesc)]
+    lib.eb200_contract_grouped.argtypes = [vp, C.c_int64, C.POINTER(ContractDesc), C.POINTER(C.c_int32)]
     lib.eb200_malloc.argtypes = [C.POINTER(vp), C.c_size_t]
     lib.eb200_free.argtypes = [vp]
     lib.eb200_malloc_host.argtypes = [C.POINTER(vp), C.c_size_t]
@@ -116,6 +117,8 @@ def _declare(lib):
         getattr(lib, f"eb200_{p}copy").argtypes = [vp, i64, vp, i64, vp, i64]
         getattr(lib, f"eb200_{p}fill").argtypes = [vp, i64, sp, vp, i64]
         getattr(lib, f"eb200_{p}dirprod").argtypes = [vp, i64, sp, vp, i64, vp, i64, vp, i64]
+        getattr(lib, f"eb200_{p}dirdiv").argtypes = [vp, i64, vp, i64, vp, i64]
+        getattr(lib, f"eb200_{p}dirmul").argtypes = [vp, i64, vp, i64, vp, i64]
         getattr(lib, f"eb200_{p}permute").argtypes = [vp, ci, C.POINTER(i64), C.POINTER(i64), C.POINTER(ci), C.POINTER(i64), sp, vp, sp, vp, ci]
     for p, rt in (("c", C.c_float), ("z", C.c_double)):
         sp = C.POINTER(rt)

@@ -17,7 +17,11 @@ int grid_for_n(int64_t n, int threads, int per_thread) {
 }
 
 // ---------------------------------------------------------------- level-1 kernels
-enum L1Op { L1_AXPY, L1_AXPBY, L1_SCAL, L1_COPY, L1_FILL, L1_DIRPROD, L1_CONJ };
+enum L1Op { L1_AXPY, L1_AXPBY, L1_SCAL, L1_COPY, L1_FILL, L1_DIRPROD, L1_CONJ, L1_DIRDIV, L1_DIRMUL };
+__device__ __forceinline__ float   div_(float a, float b) { return a / b; }
+__device__ __forceinline__ double  div_(double a, double b) { return a / b; }
+__device__ __forceinline__ float2  div_(float2 a, float2 b) { float d = b.x * b.x + b.y * b.y; return make_float2((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d); }
+__device__ __forceinline__ double2 div_(double2 a, double2 b) { double d = b.x * b.x + b.y * b.y; return make_double2((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d); }
 
 template <typename T, int OP> __device__ __forceinline__ void l1_apply(T alpha, T beta, const T *x, int64_t ix, const T *y, int64_t iy, T *z, int64_t iz) {
     if constexpr (OP == L1_AXPY) z[iz] = fma_(alpha, x[ix], z[iz]);
@@ -27,6 +31,8 @@ template <typename T, int OP> __device__ __forceinline__ void l1_apply(T alpha, 
     else if constexpr (OP == L1_FILL) z[iz] = alpha;
     else if constexpr (OP == L1_DIRPROD) z[iz] = fma_(mul_(alpha, x[ix]), y[iy], z[iz]);
     else if constexpr (OP == L1_CONJ) z[iz] = conj_(z[iz]);
+    else if constexpr (OP == L1_DIRDIV) z[iz] = div_(z[iz], x[ix]);
+    else if constexpr (OP == L1_DIRMUL) z[iz] = mul_(z[iz], x[ix]);
 }
 
 template <typename T, int OP>
@@ -273,6 +279,14 @@ using namespace eb200;
         if (!alpha) return fail(EB200_ERR_INVALID_ARGUMENT, "dirprod: alpha is NULL");                                                    \
         return l1_launch<KT, L1_DIRPROD>(stream, n, *(const KT *)alpha, zero_of<KT>(), blas_base((const KT *)x, n, incx), incx,           \
                                          blas_base((const KT *)y, n, incy), incy, blas_base((KT *)z, n, incz), incz, "dirprod");          \
+    }                                                                                                                                     \
+    extern "C" int eb200_##P##dirdiv(void *stream, int64_t n, const CT *x, int64_t incx, CT *y, int64_t incy) {                          \
+        return l1_launch<KT, L1_DIRDIV>(stream, n, zero_of<KT>(), zero_of<KT>(), blas_base((const KT *)x, n, incx), incx, nullptr, 0,     \
+                                        blas_base((KT *)y, n, incy), incy, "dirdiv");                                                     \
+    }                                                                                                                                     \
+    extern "C" int eb200_##P##dirmul(void *stream, int64_t n, const CT *x, int64_t incx, CT *y, int64_t incy) {                          \
+        return l1_launch<KT, L1_DIRMUL>(stream, n, zero_of<KT>(), zero_of<KT>(), blas_base((const KT *)x, n, incx), incx, nullptr, 0,     \
+                                        blas_base((KT *)y, n, incy), incy, "dirmul");                                                     \
     }
 
 EB200_DEF_BLAS(s, float, float)

@@ -560,6 +560,78 @@ int eb200_contract(void *stream, eb200_contract_desc *desc) {
     return eb200::contract_dispatch(eb200::as_stream(stream), *desc);
 }
 
+// Grouped contraction (the per-block loops of TA/Backends/BlockAlgebra.hpp:36-47 and TileAlgebra.hpp).
+// Consecutive descriptors that differ only by a constant pointer step are folded into ONE contraction by giving them an
+// extra unique index whose stride is that step (a batch index; or an M/N index when one operand is shared), so a
+// block-diagonal tensor with equal block sizes runs as a single launch. Whatever does not fold is enqueued back to back on
+// the stream with no host synchronisation in between.
+int eb200_contract_grouped(void *stream, int64_t n, eb200_contract_desc *descs, int32_t *n_launched_groups) {
+    using namespace eb200;
+    if (n < 0 || (n > 0 && !descs)) return fail(EB200_ERR_INVALID_ARGUMENT, "eb200_contract_grouped: bad arguments");
+    auto same_shape = [](const eb200_contract_desc &x, const eb200_contract_desc &y) {
+        if (x.n_unique != y.n_unique || x.conj_a != y.conj_a || x.conj_b != y.conj_b || x.force_kernel != y.force_kernel || x.split_k != y.split_k) return false;
+        for (int k = 0; k < 2; k++)
+            if (x.alpha[k] != y.alpha[k] || x.beta[k] != y.beta[k]) return false;
+        for (int u = 0; u < x.n_unique; u++)
+            if (x.extent[u] != y.extent[u]) return false;
+        const eb200_tensor_desc *tx[3] = {&x.C, &x.A, &x.B}, *ty[3] = {&y.C, &y.A, &y.B};
+        for (int t = 0; t < 3; t++) {
+            if (tx[t]->dtype != ty[t]->dtype || tx[t]->rank != ty[t]->rank) return false;
+            for (int i = 0; i < tx[t]->rank; i++)
+                if (tx[t]->index[i] != ty[t]->index[i] || tx[t]->stride[i] != ty[t]->stride[i]) return false;
+        }
+        return true;
+    };
+    auto step_of = [](const eb200_tensor_desc &x, const eb200_tensor_desc &y, int64_t &step) { // element step y - x, if whole
+        ptrdiff_t d = (const char *)y.data - (const char *)x.data;
+        ptrdiff_t es = (ptrdiff_t)dtype_size(x.dtype);
+        if (d % es) return false;
+        step = d / es;
+        return true;
+    };
+    int32_t groups = 0;
+    int64_t i = 0;
+    while (i < n) {
+        eb200_contract_desc &first = descs[i];
+        int64_t              cnt = 1, sC = 0, sA = 0, sB = 0;
+        bool                 room = first.n_unique < EB200_MAX_UNIQUE && first.C.rank < EB200_MAX_RANK && first.A.rank < EB200_MAX_RANK && first.B.rank < EB200_MAX_RANK;
+        if (room && i + 1 < n && same_shape(first, descs[i + 1]) && step_of(first.C, descs[i + 1].C, sC) && step_of(first.A, descs[i + 1].A, sA) &&
+            step_of(first.B, descs[i + 1].B, sB) && sC > 0 && sA >= 0 && sB >= 0 && (sA > 0 || sB > 0)) {
+            cnt = 2;
+            while (i + cnt < n && same_shape(first, descs[i + cnt])) {
+                int64_t c, a, b;
+                if (!step_of(descs[i + cnt - 1].C, descs[i + cnt].C, c) || !step_of(descs[i + cnt - 1].A, descs[i + cnt].A, a) ||
+                    !step_of(descs[i + cnt - 1].B, descs[i + cnt].B, b) || c != sC || a != sA || b != sB)
+                    break;
+                cnt++;
+            }
+        }
+        int rc;
+        if (cnt == 1) {
+            rc = contract_dispatch(as_stream(stream), first);
+        } else {
+            eb200_contract_desc m = first;
+            const int           g = m.n_unique++;
+            m.extent[g] = cnt;
+            auto prepend = [&](eb200_tensor_desc &t, int64_t step) {
+                if (step == 0) return; // shared by every member of the group: the new index does not address it
+                for (int k = t.rank; k > 0; k--) { t.index[k] = t.index[k - 1]; t.stride[k] = t.stride[k - 1]; }
+                t.index[0] = g;
+                t.stride[0] = step;
+                t.rank++;
+            };
+            prepend(m.C, sC); prepend(m.A, sA); prepend(m.B, sB);
+            rc = contract_dispatch(as_stream(stream), m);
+            for (int64_t k = 0; k < cnt; k++) { descs[i + k].kernel_used = m.kernel_used; descs[i + k].launches = k == 0 ? m.launches : 0; }
+        }
+        if (rc) return rc;
+        groups++;
+        i += cnt;
+    }
+    if (n_launched_groups) *n_launched_groups = groups;
+    return EB200_OK;
+}
+
 int eb200_contract_plan(eb200_contract_desc *desc) {
     if (!desc) return eb200::fail(EB200_ERR_INVALID_ARGUMENT, "eb200_contract_plan: desc is NULL");
     eb200::Plan p;

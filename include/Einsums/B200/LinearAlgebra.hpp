@@ -36,7 +36,14 @@ namespace detail {
     inline int xscal(void *s, int64_t n, T alpha, T *x, int64_t incx) { return eb200_##P##scal(s, n, (R const *)&alpha, (R *)x, incx); }        \
     inline int xdirprod(void *s, int64_t n, T alpha, T const *x, int64_t incx, T const *y, int64_t incy, T *z, int64_t incz) {                  \
         return eb200_##P##dirprod(s, n, (R const *)&alpha, (R const *)x, incx, (R const *)y, incy, (R *)z, incz);                                \
-    }
+    }                                                                                                                                            \
+    inline int xdirdiv(void *s, int64_t n, T const *x, int64_t incx, T *y, int64_t incy) {                                                      \
+        return eb200_##P##dirdiv(s, n, (R const *)x, incx, (R *)y, incy);                                                                        \
+    }                                                                                                                                            \
+    inline int xdirmul(void *s, int64_t n, T const *x, int64_t incx, T *y, int64_t incy) {                                                      \
+        return eb200_##P##dirmul(s, n, (R const *)x, incx, (R *)y, incy);                                                                        \
+    }                                                                                                                                            \
+    inline int xfill(void *s, int64_t n, T value, T *x, int64_t incx) { return eb200_##P##fill(s, n, (R const *)&value, (R *)x, incx); }
 EB200_TYPED(s, float, float)
 EB200_TYPED(d, double, double)
 EB200_TYPED(c, std::complex<float>, float)

@@ -64,7 +64,7 @@ template <typename V> void fill_tensor_desc(eb200_tensor_desc &td, V *data, int 
 
 /// Build the descriptor the reference's device launcher builds (GPUTensorAlgebra.hpp:225-239) and run the engine.
 template <bool ConjA, bool ConjB, typename CType, typename AType, typename BType, typename CV>
-void run_contract(Analysis const &z, CV beta, CType *C, CV alpha, AType const &A, BType const &B, CV *c_data) {
+eb200_contract_desc make_contract_desc(Analysis const &z, CV beta, CType *C, CV alpha, AType const &A, BType const &B, CV *c_data) {
     using AV = typename AType::ValueType;
     using BV = typename BType::ValueType;
     eb200_contract_desc d{};
@@ -112,6 +112,11 @@ void run_contract(Analysis const &z, CV beta, CType *C, CV alpha, AType const &A
     d.beta[0] = b.real();  d.beta[1] = b.imag();
     d.conj_a = ConjA && IsComplexV<AV>;
     d.conj_b = ConjB && IsComplexV<BV>;
+    return d;
+}
+template <bool ConjA, bool ConjB, typename CType, typename AType, typename BType, typename CV>
+void run_contract(Analysis const &z, CV beta, CType *C, CV alpha, AType const &A, BType const &B, CV *c_data) {
+    eb200_contract_desc d = make_contract_desc<ConjA, ConjB>(z, beta, C, alpha, A, B, c_data);
     EB200_CHECK(eb200_contract(gpu::get_stream(), &d));
 }
 

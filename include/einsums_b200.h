@@ -171,7 +171,10 @@ int eb200_copy_strided(void *stream, int dtype, int rank, const int64_t *dims, c
     int eb200_##P##fill(void *stream, int64_t n, const T *value, T *x, int64_t incx);                         \
     /* z += alpha * x * y elementwise */                                                                       \
     int eb200_##P##dirprod(void *stream, int64_t n, const T *alpha, const T *x, int64_t incx, const T *y,     \
-                           int64_t incy, T *z, int64_t incz);
+                           int64_t incy, T *z, int64_t incz);                                                  \
+    /* y /= x and y *= x elementwise (BlockTensor operator/= and operator*=, Tensor/BlockTensor.hpp) */        \
+    int eb200_##P##dirdiv(void *stream, int64_t n, const T *x, int64_t incx, T *y, int64_t incy);             \
+    int eb200_##P##dirmul(void *stream, int64_t n, const T *x, int64_t incx, T *y, int64_t incy);
 
 EB200_DECL_BLAS(s, float)
 EB200_DECL_BLAS(d, double)
@@ -250,6 +253,14 @@ typedef struct eb200_contract_desc {
 } eb200_contract_desc;
 
 int eb200_contract(void *stream, eb200_contract_desc *desc);
+
+/* Grouped contraction: n descriptors enqueued on `stream` with no host synchronisation between them. Replaces the
+ * per-block `einsum` loops of the reference's block / tiled tensor algebra
+ * (libs/Einsums/TensorAlgebra/include/Einsums/TensorAlgebra/Backends/BlockAlgebra.hpp:36-47, TileAlgebra.hpp).
+ * Runs of consecutive descriptors that are identical except for base pointers advancing by a constant step (equal-size
+ * blocks of one allocation) are folded into a single launch by turning the step into an extra batch index.
+ * *n_launched_groups (optional) receives the number of contractions actually dispatched (<= n). */
+int eb200_contract_grouped(void *stream, int64_t n, eb200_contract_desc *descs, int32_t *n_launched_groups);
 
 /* Host-side only (no device needed): classification the engine would pick for this
  * descriptor, written to desc->kernel_used. Lets CPU tests pin the planner. */

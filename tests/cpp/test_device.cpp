@@ -3,6 +3,7 @@
 // this backend. Expected values come from hand loops on host copies, as the reference tests do; tolerances: 1e-12
 // relative (FP64), exact where the reference asserts exact integers.
 #include <Einsums/LinearAlgebra.hpp>
+#include <Einsums/Tensor/BlockTensor.hpp>
 #include <Einsums/Tensor/DeviceTensor.hpp>
 #include <Einsums/TensorAlgebra.hpp>
 
@@ -457,6 +458,174 @@ TEST_CASE(gpu_dimension_errors_and_threads) {
     bool same = true;
     for (size_t x = 0; x < h1.v.size(); x++) same = same && (h1.v[x] == h2.v[x]);
     CHECK(same);
+}
+
+// ---- block-diagonal tensors ------------------------------------------------------------------
+TEST_CASE(gpu_block_tensor_creation_and_ops) { // Tensor/tests/unit/BlockDeviceTensor.hip:14-195
+    BlockDeviceTensor<double, 2> A("A", einsums::detail::DEV_ONLY, 3, 3), B("B", einsums::detail::DEV_ONLY, 3, 3), C;
+    CHECK(A.dim(0) == 6 && A.dim(1) == 6 && A.num_blocks() == 2);
+    A.zero();
+    B.zero();
+    for (int i = 0; i < 6; i++) {
+        A(i, i) = 1.0;
+        B(i, i) = 1.0;
+    }
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) CHECK((double)A(i, j) == (i == j ? 1.0 : 0.0));
+    A(0, 5) = 7.0; // outside the blocks: swallowed
+    CHECK((double)A(0, 5) == 0.0);
+
+    C.push_block(DeviceTensor<double, 2>("block2", einsums::detail::DEV_ONLY, 3, 3));
+    C.insert_block(0, DeviceTensor<double, 2>("block1", einsums::detail::DEV_ONLY, 3, 3));
+    C.set_name("C");
+    linear_algebra::gemm<false, false>(1.0, A, B, 0.0, &C);
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) CHECK((double)C(i, j) == (i == j ? 1.0 : 0.0));
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            CHECK((double)A[0](i, j) == (i == j ? 1.0 : 0.0));
+            CHECK((double)C["block1"](i, j) == (i == j ? 1.0 : 0.0));
+            CHECK((double)C["block2"](i, j) == (i == j ? 1.0 : 0.0));
+        }
+    CHECK_THROWS_AS(C["block3"], std::out_of_range);
+
+    A.set_all(2.0);
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) {
+            CHECK((A.block_of(i) == A.block_of(j)) == (i / 3 == j / 3));
+            CHECK((double)A(i, j) == (i / 3 == j / 3 ? 2.0 : 0.0));
+        }
+    for (int i = 0; i < 6; i++) CHECK(A.block_of(i) == i / 3);
+    CHECK_THROWS_AS(A.block_of(6), std::out_of_range);
+    CHECK_THROWS_AS(A.block_of(-1), std::out_of_range);
+
+    // arithmetic (:121-181)
+    A.zero();
+    for (int i = 0; i < 6; i++) A(i, i) = 1.0;
+    A *= 2.0; A += 2.0; A /= 2.0; A -= 2.0;
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) CHECK((double)A(i, j) == (i == j ? 0.0 : (i / 3 == j / 3 ? -1.0 : 0.0)));
+    A += B; B *= A; B /= A; B -= A;
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) {
+            CHECK((double)A(i, j) == (i == j ? 1.0 : (i / 3 == j / 3 ? -1.0 : 0.0)));
+            CHECK((double)B(i, j) == (i == j ? 0.0 : (i / 3 == j / 3 ? 1.0 : 0.0)));
+        }
+    // dense copy
+    DeviceTensor<double, 2> D = (DeviceTensor<double, 2>)A;
+    for (int i = 0; i < 6; i++)
+        for (int j = 0; j < 6; j++) CHECK((double)D(i, j) == (double)A(i, j));
+}
+
+TEST_CASE(gpu_block_tensor_einsum) { // BlockAlgebra.hpp: block x block -> block / dense / scalar, vector x block
+    using namespace einsums::index;
+    std::vector<int64_t> sizes{5, 0, 17, 17, 17, 33};
+    BlockDeviceTensor<double, 2> A("A", sizes), B("B", sizes), C("C", sizes);
+    int64_t n = A.dim();
+    std::mt19937_64 eng(7);
+    std::uniform_real_distribution<double> dist(-1, 1);
+    for (size_t b = 0; b < A.num_blocks(); b++) {
+        if (!A.block_dim(b)) continue;
+        std::vector<double> ha(size_t(A[b].size())), hb(ha.size()), hc(ha.size());
+        for (auto &v : ha) v = dist(eng);
+        for (auto &v : hb) v = dist(eng);
+        for (auto &v : hc) v = dist(eng);
+        A[b].read(ha); B[b].read(hb); C[b].read(hc);
+    }
+    auto Ad = (DeviceTensor<double, 2>)A, Bd = (DeviceTensor<double, 2>)B, Cd0 = (DeviceTensor<double, 2>)C;
+    auto ha = host(Ad), hb = host(Bd), hc0 = host(Cd0);
+
+    // block x block -> block, with prefactors
+    einsum(0.5, Indices{i, j}, &C, 2.0, Indices{i, k}, A, Indices{j, k}, B);
+    auto Cd = (DeviceTensor<double, 2>)C;
+    auto hc = host(Cd);
+    double worst = 0;
+    for (int64_t x = 0; x < n; x++)
+        for (int64_t y = 0; y < n; y++) {
+            double ref = 0.5 * hc0(x, y);
+            if (A.block_of(x) == A.block_of(y))
+                for (int64_t z = 0; z < n; z++) ref += 2.0 * ha(x, z) * hb(y, z);
+            worst = std::max(worst, std::abs(ref - hc(x, y)));
+        }
+    CHECK(worst <= 1e-12);
+
+    // block x block -> dense C: only the diagonal sub-blocks are touched (BlockAlgebra.hpp:52-88)
+    DeviceTensor<double, 2> F("F", n, n);
+    F.set_all(3.0);
+    einsum(Indices{i, j}, &F, Indices{i, k}, A, Indices{k, j}, B);
+    auto hf = host(F);
+    worst = 0;
+    for (int64_t x = 0; x < n; x++)
+        for (int64_t y = 0; y < n; y++) {
+            double ref = 3.0;
+            if (A.block_of(x) == A.block_of(y)) {
+                ref = 0;
+                for (int64_t z = 0; z < n; z++) ref += ha(x, z) * hb(z, y);
+            }
+            worst = std::max(worst, std::abs(ref - hf(x, y)));
+        }
+    CHECK(worst <= 1e-12);
+
+    // block x block -> scalar, host value and rank-0 device tensor (:108-180)
+    double s = 4.0, ref = 0;
+    for (int64_t x = 0; x < n; x++)
+        for (int64_t y = 0; y < n; y++) ref += ha(x, y) * hb(x, y);
+    einsum(0.5, Indices{}, &s, 1.0, Indices{i, j}, A, Indices{i, j}, B);
+    CHECK_CLOSE(s, 2.0 + ref, 1e-12 * (1 + std::abs(ref)));
+    DeviceTensor<double, 0> s0("s0");
+    s0 = 1.0;
+    einsum(0.0, Indices{}, &s0, 2.0, Indices{i, j}, A, Indices{i, j}, B);
+    CHECK_CLOSE((double)s0, 2.0 * ref, 1e-12 * (1 + std::abs(ref)));
+    CHECK_CLOSE(linear_algebra::dot(A, B), ref, 1e-12 * (1 + std::abs(ref)));
+
+    // vector x block -> dense vector (:217-238) and block x vector -> vector through gemv
+    auto x = create_random_gpu_tensor("x", n);
+    DeviceTensor<double, 1> y("y", n), y2("y2", n);
+    y.zero();
+    einsum(Indices{j}, &y, Indices{i}, x, Indices{i, j}, A);
+    auto hx = host(x), hy = host(y);
+    worst = 0;
+    for (int64_t c = 0; c < n; c++) {
+        double r = 0;
+        for (int64_t rw = 0; rw < n; rw++) r += hx(rw) * ha(rw, c);
+        worst = std::max(worst, std::abs(r - hy(c)));
+    }
+    CHECK(worst <= 1e-12);
+    y2.zero();
+    linear_algebra::gemv<true>(1.0, A, x, 0.0, &y2);
+    auto hy2 = host(y2);
+    worst = 0;
+    for (int64_t c = 0; c < n; c++) worst = std::max(worst, std::abs(hy2(c) - hy(c)));
+    CHECK(worst <= 1e-12);
+
+    // rank-3 blocks, equal sizes: folds into one batched launch
+    BlockDeviceTensor<double, 3> T3("T3", 8, 8, 8, 8);
+    BlockDeviceTensor<double, 2> M2("M2", 8, 8, 8, 8), R2("R2", 8, 8, 8, 8);
+    for (size_t b = 0; b < 4; b++) {
+        std::vector<double> t(512), m(64);
+        for (auto &v : t) v = dist(eng);
+        for (auto &v : m) v = dist(eng);
+        T3[b].read(t); M2[b].read(m);
+    }
+    eb200_launch_count_reset();
+    einsum(Indices{i, l}, &R2, Indices{i, k, l}, T3, Indices{k, l}, M2);
+    for (size_t b = 0; b < 4; b++) {
+        auto t = T3[b].to_host(), m = M2[b].to_host(), r = R2[b].to_host();
+        double w = 0;
+        for (int a = 0; a < 8; a++)
+            for (int c = 0; c < 8; c++) {
+                double e = 0;
+                for (int k2 = 0; k2 < 8; k2++) e += t[(a * 8 + k2) * 8 + c] * m[k2 * 8 + c];
+                w = std::max(w, std::abs(e - r[a * 8 + c]));
+            }
+        CHECK(w <= 1e-12);
+    }
+
+    // mismatched block structures
+    BlockDeviceTensor<double, 2> P("P", 3, 4), Q("Q", 4, 3), Rr("R", 3, 4, 5);
+    BlockDeviceTensor<double, 2> O("O", 3, 4);
+    CHECK_THROWS_AS(einsum(Indices{i, j}, &O, Indices{i, k}, P, Indices{k, j}, Q), dimension_error);
+    CHECK_THROWS_AS(einsum(Indices{i, j}, &O, Indices{i, k}, P, Indices{k, j}, Rr), tensor_compat_error);
 }
 
 int main() {

@@ -182,6 +182,61 @@ def test_contract_many_batches(gpu):
     assert rel_err(Cf.cpu().numpy(), ref.cpu().numpy()) <= 1e-5
 
 
+# ---------------------------------------------------------------------------------------------
+# grouped contraction = the per-block einsum loop of block-diagonal tensors (BlockAlgebra.hpp:36-47)
+def _block_views(flat, sizes, rank):
+    """Rank-`rank` hypercubic blocks packed back to back in one allocation (how BlockDeviceTensor stores them)."""
+    out, off = [], 0
+    for n in sizes:
+        out.append(flat[off:off + n**rank].view(*([n] * rank)))
+        off += n**rank
+    return out
+
+
+@pytest.mark.parametrize("sizes,expect_groups", [((48,) * 6, 1), ((5, 17, 64, 33, 1), 5), ((16, 16, 16, 40, 40, 7), 3)])
+@pytest.mark.parametrize("dtype", [np.float64, np.complex64])
+def test_grouped_block_diagonal(gpu, oracle, sizes, expect_groups, dtype):
+    rng = np.random.default_rng(11)
+    tot = sum(n * n for n in sizes)
+    Ah, Bh, Ch = rand(rng, (tot,), dtype), rand(rng, (tot,), dtype), rand(rng, (tot,), dtype)
+    Ad, Bd, Cd = dev(Ah), dev(Bh), dev(Ch)
+    descs, groups = gpu.contract_grouped("ij", _block_views(Cd, sizes, 2), "ik", _block_views(Ad, sizes, 2), "jk", _block_views(Bd, sizes, 2), 0.5, 2.0)
+    torch.cuda.synchronize()
+    assert groups == expect_groups
+    assert sum(d.launches for d in descs) >= groups
+    ref, off = Ch.copy(), 0
+    for n in sizes:  # the reference: one einsum per block
+        sl = slice(off, off + n * n)
+        blk = np.ascontiguousarray(ref[sl].reshape(n, n))
+        oracle.einsum_generic("ij", blk, "ik", np.ascontiguousarray(Ah[sl].reshape(n, n)), "jk", np.ascontiguousarray(Bh[sl].reshape(n, n)), 0.5, 2.0)
+        ref[sl] = blk.reshape(-1)
+        off += n * n
+    assert_close(Cd.cpu().numpy(), ref, dtype, f"grouped {sizes}")
+
+
+def test_grouped_shared_operand_and_rank3(gpu, oracle):
+    """A vector shared by every block (BlockAlgebra.hpp:185-214) folds into an N index; rank-3 blocks fold into a batch."""
+    rng = np.random.default_rng(12)
+    nb, n = 5, 24
+    Ah, Ch = rand(rng, (nb, n, n, n), np.float64), np.zeros((nb, n, n), np.float64)
+    Mh = rand(rng, (n, n), np.float64)
+    Ad, Cd, Md = dev(Ah), dev(Ch), dev(Mh)
+    descs, groups = gpu.contract_grouped("ij", [Cd[b] for b in range(nb)], "ikl", [Ad[b] for b in range(nb)], "lkj", [Md.view(n, 1, n).expand(n, n, n)] * nb)
+    torch.cuda.synchronize()
+    assert groups == 1
+    ref = np.einsum("bikl,lj->bij", Ah, Mh)
+    assert rel_err(Cd.cpu().numpy(), ref) <= 1e-12
+    # outputs at irregular distances: only pairs share a step (any two equal-shape neighbours do) -> 2 + 2 + 1 dispatches
+    pool = torch.zeros(nb * (n * n + 7) + 64, dtype=torch.float64, device="cuda")
+    Cs = [pool[b * (n * n + 7) + b * b:][:n * n].view(n, n) for b in range(nb)]
+    descs, groups = gpu.contract_grouped("ij", Cs, "ikl", [Ad[b] for b in range(nb)], "lkj", [Md.view(n, 1, n).expand(n, n, n)] * nb)
+    torch.cuda.synchronize()
+    assert groups == 3
+    assert rel_err(torch.stack(Cs).cpu().numpy(), ref) <= 1e-12
+    with pytest.raises(ValueError, match="same number of blocks"):
+        gpu.contract_grouped("ij", Cs, "ikl", [Ad[0]], "lkj", [Md] * nb)
+
+
 def test_beta_zero_never_reads_c(gpu):
     A = torch.rand(70, 50, dtype=torch.float64, device="cuda")
     B = torch.rand(50, 90, dtype=torch.float64, device="cuda")
