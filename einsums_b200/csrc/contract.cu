@@ -560,6 +560,47 @@ int eb200_contract(void *stream, eb200_contract_desc *desc) {
     return eb200::contract_dispatch(eb200::as_stream(stream), *desc);
 }
 
+namespace eb200 {
+// Auxiliary streams of eb200_contract_grouped: per host thread, created on first use for the current device.
+struct GroupStreams {
+    static constexpr int N = 3;
+    int          device = -1;
+    cudaStream_t aux[N] = {};
+    cudaEvent_t  fork = nullptr, join[N] = {};
+    int ensure() {
+        int dev = -1;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        if (dev == device) return N;
+        release();
+        for (int i = 0; i < N; i++)
+            if (cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming) != cudaSuccess) {
+                release();
+                return 0;
+            }
+        if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) {
+            release();
+            return 0;
+        }
+        device = dev;
+        return N;
+    }
+    void release() {
+        for (int i = 0; i < N; i++) {
+            if (aux[i]) cudaStreamDestroy(aux[i]);
+            if (join[i]) cudaEventDestroy(join[i]);
+            aux[i] = nullptr; join[i] = nullptr;
+        }
+        if (fork) cudaEventDestroy(fork);
+        fork = nullptr;
+        device = -1;
+    }
+};
+static GroupStreams &group_streams() {
+    static thread_local GroupStreams gs; // not destroyed at thread exit on purpose: the context may already be gone
+    return gs;
+}
+} // namespace eb200
+
 // Grouped contraction (the per-block loops of TA/Backends/BlockAlgebra.hpp:36-47 and TileAlgebra.hpp).
 // Consecutive descriptors that differ only by a constant pointer step are folded into ONE contraction by giving them an
 // extra unique index whose stride is that step (a batch index; or an M/N index when one operand is shared), so a
@@ -589,9 +630,10 @@ int eb200_contract_grouped(void *stream, int64_t n, eb200_contract_desc *descs, 
         step = d / es;
         return true;
     };
-    int32_t groups = 0;
-    int64_t i = 0;
-    while (i < n) {
+    // pass 1: cut the list into runs that fold
+    struct Run { int64_t first, cnt, sC, sA, sB; };
+    std::vector<Run> runs;
+    for (int64_t i = 0; i < n;) {
         eb200_contract_desc &first = descs[i];
         int64_t              cnt = 1, sC = 0, sA = 0, sB = 0;
         bool                 room = first.n_unique < EB200_MAX_UNIQUE && first.C.rank < EB200_MAX_RANK && first.A.rank < EB200_MAX_RANK && first.B.rank < EB200_MAX_RANK;
@@ -606,13 +648,32 @@ int eb200_contract_grouped(void *stream, int64_t n, eb200_contract_desc *descs, 
                 cnt++;
             }
         }
-        int rc;
-        if (cnt == 1) {
-            rc = contract_dispatch(as_stream(stream), first);
+        runs.push_back({i, cnt, sC, sA, sB});
+        i += cnt;
+    }
+    // pass 2: dispatch. Several runs (ragged blocks: each too small to fill 148 SMs) are spread over a few auxiliary
+    // streams forked from, and joined back into, the caller's stream, so their kernels overlap on the device.
+    // The members of a group must be independent (distinct outputs, no output aliasing an input), as blocks are.
+    cudaStream_t  user = as_stream(stream);
+    GroupStreams &gs = group_streams();
+    const int     naux = runs.size() > 1 ? gs.ensure() : 0;
+    if (naux > 0) {
+        EB_CUDA(cudaEventRecord(gs.fork, user));
+        for (int a = 0; a < naux; a++) EB_CUDA(cudaStreamWaitEvent(gs.aux[a], gs.fork, 0));
+    }
+    int32_t groups = 0;
+    int     rc = EB200_OK;
+    for (size_t r = 0; r < runs.size() && rc == EB200_OK; r++) {
+        const Run           &run = runs[r];
+        eb200_contract_desc &first = descs[run.first];
+        const int            lane = naux > 0 ? int(r % size_t(naux + 1)) : 0;
+        cudaStream_t         s = lane == 0 ? user : gs.aux[lane - 1];
+        if (run.cnt == 1) {
+            rc = contract_dispatch(s, first);
         } else {
             eb200_contract_desc m = first;
             const int           g = m.n_unique++;
-            m.extent[g] = cnt;
+            m.extent[g] = run.cnt;
             auto prepend = [&](eb200_tensor_desc &t, int64_t step) {
                 if (step == 0) return; // shared by every member of the group: the new index does not address it
                 for (int k = t.rank; k > 0; k--) { t.index[k] = t.index[k - 1]; t.stride[k] = t.stride[k - 1]; }
@@ -620,14 +681,19 @@ int eb200_contract_grouped(void *stream, int64_t n, eb200_contract_desc *descs, 
                 t.stride[0] = step;
                 t.rank++;
             };
-            prepend(m.C, sC); prepend(m.A, sA); prepend(m.B, sB);
-            rc = contract_dispatch(as_stream(stream), m);
-            for (int64_t k = 0; k < cnt; k++) { descs[i + k].kernel_used = m.kernel_used; descs[i + k].launches = k == 0 ? m.launches : 0; }
+            prepend(m.C, run.sC); prepend(m.A, run.sA); prepend(m.B, run.sB);
+            rc = contract_dispatch(s, m);
+            for (int64_t k = 0; k < run.cnt; k++) { descs[run.first + k].kernel_used = m.kernel_used; descs[run.first + k].launches = k == 0 ? m.launches : 0; }
         }
-        if (rc) return rc;
         groups++;
-        i += cnt;
     }
+    if (naux > 0) { // always join, also after an error, so the caller's stream never runs ahead of forked work
+        for (int a = 0; a < naux; a++) {
+            cudaEventRecord(gs.join[a], gs.aux[a]);
+            cudaStreamWaitEvent(user, gs.join[a], 0);
+        }
+    }
+    if (rc) return rc;
     if (n_launched_groups) *n_launched_groups = groups;
     return EB200_OK;
 }

@@ -93,10 +93,8 @@ def contract(c_idx, Ct, a_idx, At, b_idx, Bt, alpha=1.0, beta=0.0, conj_a=False,
     return d
 
 
-def contract_grouped(c_idx, Cs, a_idx, As, b_idx, Bs, alpha=1.0, beta=0.0, conj_a=False, conj_b=False, stream=None):
-    """The same contraction over lists of tensors (the blocks of block-diagonal / tiled tensors) through
-    eb200_contract_grouped: one stream-ordered group, equal-shape runs with constant pointer steps folded into one launch.
-    Returns (descriptors, number of contractions actually dispatched)."""
+def make_group(c_idx, Cs, a_idx, As, b_idx, Bs, alpha=1.0, beta=0.0, conj_a=False, conj_b=False):
+    """Descriptor array for eb200_contract_grouped (build once, run many times with run_group)."""
     if not (len(Cs) == len(As) == len(Bs)):
         raise ValueError("tensor_compat_error: Block tensors need to have the same number of blocks.")
     n = len(Cs)
@@ -104,9 +102,24 @@ def contract_grouped(c_idx, Cs, a_idx, As, b_idx, Bs, alpha=1.0, beta=0.0, conj_
     for i in range(n):
         _need_cuda(Cs[i], As[i], Bs[i])
         arr[i] = make_desc(c_idx, Cs[i], a_idx, As[i], b_idx, Bs[i], alpha, beta, conj_a, conj_b)
+    return arr, n
+
+
+def run_group(group, stream=None) -> int:
+    """Enqueue a descriptor array from make_group; returns the number of contractions actually dispatched."""
+    arr, n = group
     groups = C.c_int32(0)
     check(lib().eb200_contract_grouped(_stream(stream), n, arr, C.byref(groups)))
-    return [arr[i] for i in range(n)], groups.value
+    return groups.value
+
+
+def contract_grouped(c_idx, Cs, a_idx, As, b_idx, Bs, alpha=1.0, beta=0.0, conj_a=False, conj_b=False, stream=None):
+    """The same contraction over lists of tensors (the blocks of block-diagonal / tiled tensors) through
+    eb200_contract_grouped: one stream-ordered group, equal-shape runs with constant pointer steps folded into one launch.
+    Returns (descriptors, number of contractions actually dispatched)."""
+    group = make_group(c_idx, Cs, a_idx, As, b_idx, Bs, alpha, beta, conj_a, conj_b)
+    groups = run_group(group, stream)
+    return [group[0][i] for i in range(group[1])], groups
 
 
 def plan(c_idx, Ct, a_idx, At, b_idx, Bt, **kw) -> str:
