@@ -5,6 +5,7 @@
 #include <Einsums/LinearAlgebra.hpp>
 #include <Einsums/Tensor/BlockTensor.hpp>
 #include <Einsums/Tensor/DeviceTensor.hpp>
+#include <Einsums/Tensor/TiledTensor.hpp>
 #include <Einsums/TensorAlgebra.hpp>
 
 #include "mini_test.hpp"
@@ -626,6 +627,133 @@ TEST_CASE(gpu_block_tensor_einsum) { // BlockAlgebra.hpp: block x block -> block
     BlockDeviceTensor<double, 2> O("O", 3, 4);
     CHECK_THROWS_AS(einsum(Indices{i, j}, &O, Indices{i, k}, P, Indices{k, j}, Q), dimension_error);
     CHECK_THROWS_AS(einsum(Indices{i, j}, &O, Indices{i, k}, P, Indices{k, j}, Rr), tensor_compat_error);
+}
+
+// ---- tiled tensors ---------------------------------------------------------------------------
+TEST_CASE(gpu_tiled_tensor_known_answers) { // Tensor/tests/unit/DeviceTiledTensor.hip:13-156, 432-504
+    using namespace einsums::index;
+    {
+        TiledDeviceTensor<double, 2> A("A", einsums::detail::DEV_ONLY, std::array{1, 0, 2}), B("B", einsums::detail::DEV_ONLY, std::array{1, 0, 2}),
+            C("C", einsums::detail::DEV_ONLY, std::array{1, 0, 2});
+        CHECK(A.dim(0) == 3 && A.dim(1) == 3);
+        CHECK(A.tile_offset(0)[0] == 0 && A.tile_offset(0)[1] == 1 && A.tile_offset(0)[2] == 1 && A.tile_offset(1)[2] == 1);
+        A.zero();
+        for (int i = 0; i < 3; i++) {
+            A(i, i) = 1.0;
+            B(i, i) = 1.0;
+        }
+        linear_algebra::gemm<false, false>(1.0, A, B, 0.0, &C);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) CHECK((double)C(i, j) == (i == j ? 1.0 : 0.0));
+    }
+    {
+        TiledDeviceTensor<double, 2> A("A", einsums::detail::DEV_ONLY, std::array{1, 0, 2}), B("B", einsums::detail::DEV_ONLY, std::array{1, 0, 2}),
+            C("C", einsums::detail::DEV_ONLY, std::array{1, 0, 2});
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) {
+                A(i, j) = 3 * i + j + 1;
+                B(i, j) = 33 * i + 11 * j + 11;
+            }
+        double nn[9] = {330, 396, 462, 726, 891, 1056, 1122, 1386, 1650}, tn[9] = {726, 858, 990, 858, 1023, 1188, 990, 1188, 1386},
+               nt[9] = {154, 352, 550, 352, 847, 1342, 550, 1342, 2134}, tt[9] = {330, 726, 1122, 396, 891, 1386, 462, 1056, 1650};
+        linear_algebra::gemm<false, false>(1.0, A, B, 0.0, &C);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) CHECK((double)C(i, j) == nn[3 * i + j]);
+        linear_algebra::gemm<true, false>(1.0, A, B, 0.0, &C);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) CHECK((double)C(i, j) == tn[3 * i + j]);
+        linear_algebra::gemm<false, true>(1.0, A, B, 0.0, &C);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) CHECK((double)C(i, j) == nt[3 * i + j]);
+        linear_algebra::gemm<true, true>(1.0, A, B, 0.0, &C);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) CHECK((double)C(i, j) == tt[3 * i + j]);
+
+        DeviceTensor<double, 1> x("x", 3), y("y", 3);
+        for (int i = 0; i < 3; i++) x(i) = 11 * i + 11;
+        linear_algebra::gemv<false>(1.0, A, x, 0.0, &y);
+        CHECK((double)y(0) == 154.0 && (double)y(1) == 352.0 && (double)y(2) == 550.0);
+        linear_algebra::gemv<true>(1.0, A, x, 0.0, &y);
+        CHECK((double)y(0) == 330.0 && (double)y(1) == 396.0 && (double)y(2) == 462.0);
+    }
+    { // ik=ij,jk on 1..9 (:435-467)
+        TiledDeviceTensor<double, 2> A("A", einsums::detail::DEV_ONLY, std::array{1, 0, 2}), B("B", einsums::detail::DEV_ONLY, std::array{1, 0, 2}),
+            C("C", einsums::detail::DEV_ONLY, std::array{1, 0, 2});
+        for (int i = 0, ij = 1; i < 3; i++)
+            for (int j = 0; j < 3; j++, ij++) {
+                A(i, j) = ij;
+                B(i, j) = ij;
+            }
+        einsum(Indices{i, j}, &C, Indices{i, k}, A, Indices{k, j}, B);
+        double want[9] = {30, 36, 42, 66, 81, 96, 102, 126, 150};
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) CHECK((double)C(a, b) == want[3 * a + b]);
+    }
+    { // il=ijk,jkl on 1..27 (:468-503)
+        TiledDeviceTensor<double, 3> A("A", einsums::detail::DEV_ONLY, std::array{1, 0, 2}), B("B", einsums::detail::DEV_ONLY, std::array{1, 0, 2});
+        TiledDeviceTensor<double, 2> C("C", einsums::detail::DEV_ONLY, std::array{1, 0, 2});
+        for (int a = 0, n = 1; a < 3; a++)
+            for (int b = 0; b < 3; b++)
+                for (int c = 0; c < 3; c++, n++) {
+                    A(a, b, c) = n;
+                    B(a, b, c) = n;
+                }
+        einsum(Indices{i, l}, &C, Indices{i, j, k}, A, Indices{j, k, l}, B);
+        double want[9] = {765, 810, 855, 1818, 1944, 2070, 2871, 3078, 3285};
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) CHECK((double)C(a, b) == want[3 * a + b]);
+    }
+}
+
+TEST_CASE(gpu_tiled_tensor_sparse_random) { // absent tiles, ragged grids, prefactors, scalar results: against a dense host loop
+    using namespace einsums::index;
+    std::array<std::vector<int64_t>, 2> ga{std::vector<int64_t>{7, 16, 16, 0, 5}, std::vector<int64_t>{9, 9, 20}},
+        gb{std::vector<int64_t>{9, 9, 20}, std::vector<int64_t>{16, 16, 16, 3}}, gc{std::vector<int64_t>{7, 16, 16, 0, 5}, std::vector<int64_t>{16, 16, 16, 3}};
+    TiledDeviceTensor<double, 2> A("A", einsums::detail::DEV_ONLY, ga), B("B", einsums::detail::DEV_ONLY, gb), C("C", einsums::detail::DEV_ONLY, gc);
+    std::mt19937_64 eng(3);
+    std::uniform_real_distribution<double> dist(-1, 1);
+    auto fill = [&](auto &X, int skip_mod) {
+        int n = 0;
+        X.for_each_grid([&](auto idx) {
+            if (X.has_zero_size(idx) || (n++ % skip_mod) == 1) return; // leave some tiles absent
+            auto &t = X.tile(idx);
+            std::vector<double> h(size_t(t.size()));
+            for (auto &v : h) v = dist(eng);
+            t.read(h);
+        });
+    };
+    fill(A, 3);
+    fill(B, 4);
+    fill(C, 2);
+    auto Ad = (DeviceTensor<double, 2>)A, Bd = (DeviceTensor<double, 2>)B, C0 = (DeviceTensor<double, 2>)C;
+    auto ha = host(Ad), hb = host(Bd), hc0 = host(C0);
+    einsum(0.5, Indices{i, j}, &C, -1.5, Indices{i, k}, A, Indices{k, j}, B);
+    auto Cd = (DeviceTensor<double, 2>)C;
+    auto hc = host(Cd);
+    double worst = 0;
+    for (int64_t x = 0; x < C.dim(0); x++)
+        for (int64_t y = 0; y < C.dim(1); y++) {
+            double ref = 0.5 * hc0(x, y);
+            for (int64_t z = 0; z < A.dim(1); z++) ref += -1.5 * ha(x, z) * hb(z, y);
+            worst = std::max(worst, std::abs(ref - hc(x, y)));
+        }
+    CHECK(worst <= 1e-12);
+
+    // scalar: sum_ij A(i,k) A(i,k) and dot
+    double s = 1.0, ref = 0;
+    for (auto v : ha.v) ref += v * v;
+    einsum(2.0, Indices{}, &s, 1.0, Indices{i, k}, A, Indices{i, k}, A);
+    CHECK_CLOSE(s, 2.0 + ref, 1e-12 * (1 + ref));
+    CHECK_CLOSE(linear_algebra::dot(A, A), ref, 1e-12 * (1 + ref));
+    C *= 2.0;
+    auto hc2 = host((DeviceTensor<double, 2>)C);
+    worst = 0;
+    for (size_t q = 0; q < hc.v.size(); q++) worst = std::max(worst, std::abs(hc2.v[q] - 2.0 * hc.v[q]));
+    CHECK(worst == 0.0);
+
+    // incompatible grids
+    TiledDeviceTensor<double, 2> Bad("Bad", einsums::detail::DEV_ONLY, std::array{4, 4});
+    CHECK_THROWS_AS(einsum(Indices{i, j}, &C, Indices{i, k}, A, Indices{k, j}, Bad), tensor_compat_error);
 }
 
 int main() {
