@@ -601,91 +601,113 @@ static GroupStreams &group_streams() {
 }
 } // namespace eb200
 
-// Grouped contraction (the per-block loops of TA/Backends/BlockAlgebra.hpp:36-47 and TileAlgebra.hpp).
-// Consecutive descriptors that differ only by a constant pointer step are folded into ONE contraction by giving them an
-// extra unique index whose stride is that step (a batch index; or an M/N index when one operand is shared), so a
-// block-diagonal tensor with equal block sizes runs as a single launch. Whatever does not fold is enqueued back to back on
-// the stream with no host synchronisation in between.
+// Grouped contraction (the per-block loops of TA/Backends/BlockAlgebra.hpp:36-47 and TileAlgebra.hpp:57-90).
+// Neighbouring descriptors that differ only by base pointers advancing by a constant element step are folded into ONE
+// contraction by giving them an extra unique index whose stride is that step:
+//   C, A, B all step (or one operand is shared)  -> a batch / M / N index: equal-size blocks become one batched launch;
+//   C is the same, A and B step, beta == 1       -> a contracted index: the accumulation over tile columns becomes K.
+// Folding is repeated on the folded list, so a full grid of equal tiles collapses level by level (k, then j, then i) into
+// a single launch. Whatever does not fold is spread over a few auxiliary streams forked from, and joined back into, the
+// caller's stream; members that write the same C stay on one stream, in order. Members with different C must be
+// independent of each other (distinct outputs, no output aliasing another member's input), as blocks and tiles are.
+namespace eb200 {
+struct GroupItem {
+    eb200_contract_desc d;
+    int64_t             first, count; // range of the caller's descriptors this item covers
+};
+static bool group_same_shape(const eb200_contract_desc &x, const eb200_contract_desc &y) {
+    if (x.n_unique != y.n_unique || x.conj_a != y.conj_a || x.conj_b != y.conj_b || x.force_kernel != y.force_kernel || x.split_k != y.split_k) return false;
+    for (int k = 0; k < 2; k++)
+        if (x.alpha[k] != y.alpha[k] || x.beta[k] != y.beta[k]) return false;
+    for (int u = 0; u < x.n_unique; u++)
+        if (x.extent[u] != y.extent[u]) return false;
+    const eb200_tensor_desc *tx[3] = {&x.C, &x.A, &x.B}, *ty[3] = {&y.C, &y.A, &y.B};
+    for (int t = 0; t < 3; t++) {
+        if (tx[t]->dtype != ty[t]->dtype || tx[t]->rank != ty[t]->rank) return false;
+        for (int i = 0; i < tx[t]->rank; i++)
+            if (tx[t]->index[i] != ty[t]->index[i] || tx[t]->stride[i] != ty[t]->stride[i]) return false;
+    }
+    return true;
+}
+static bool group_steps(const eb200_contract_desc &x, const eb200_contract_desc &y, int64_t st[3]) { // element steps y - x of C, A, B
+    const eb200_tensor_desc *tx[3] = {&x.C, &x.A, &x.B}, *ty[3] = {&y.C, &y.A, &y.B};
+    for (int t = 0; t < 3; t++) {
+        ptrdiff_t d = (const char *)ty[t]->data - (const char *)tx[t]->data, es = (ptrdiff_t)dtype_size(tx[t]->dtype);
+        if (d % es) return false;
+        st[t] = d / es;
+    }
+    return true;
+}
+static bool group_foldable(const eb200_contract_desc &d, const int64_t st[3]) {
+    if (st[0] > 0) return st[1] >= 0 && st[2] >= 0 && (st[1] > 0 || st[2] > 0);
+    if (st[0] == 0) return st[1] > 0 && st[2] > 0 && d.beta[0] == 1.0 && d.beta[1] == 0.0; // accumulation into one C
+    return false;
+}
+/// one folding pass; returns true when the list got shorter
+static bool group_fold_pass(std::vector<GroupItem> &items) {
+    std::vector<GroupItem> out;
+    out.reserve(items.size());
+    for (size_t i = 0; i < items.size();) {
+        const eb200_contract_desc &first = items[i].d;
+        size_t                     cnt = 1;
+        int64_t                    st[3] = {0, 0, 0};
+        const bool room = first.n_unique < EB200_MAX_UNIQUE && first.C.rank < EB200_MAX_RANK && first.A.rank < EB200_MAX_RANK && first.B.rank < EB200_MAX_RANK;
+        if (room && i + 1 < items.size() && group_same_shape(first, items[i + 1].d) && group_steps(first, items[i + 1].d, st) && group_foldable(first, st)) {
+            cnt = 2;
+            int64_t nx[3];
+            while (i + cnt < items.size() && group_same_shape(first, items[i + cnt].d) && group_steps(items[i + cnt - 1].d, items[i + cnt].d, nx) &&
+                   nx[0] == st[0] && nx[1] == st[1] && nx[2] == st[2])
+                cnt++;
+        }
+        GroupItem m = items[i];
+        if (cnt > 1) {
+            const int g = m.d.n_unique++;
+            m.d.extent[g] = (int64_t)cnt;
+            eb200_tensor_desc *t3[3] = {&m.d.C, &m.d.A, &m.d.B};
+            for (int t = 0; t < 3; t++) {
+                if (st[t] == 0) continue; // shared by every member: the new index does not address it
+                eb200_tensor_desc &td = *t3[t];
+                for (int k = td.rank; k > 0; k--) { td.index[k] = td.index[k - 1]; td.stride[k] = td.stride[k - 1]; }
+                td.index[0] = g;
+                td.stride[0] = st[t];
+                td.rank++;
+            }
+            for (size_t k = 1; k < cnt; k++) m.count += items[i + k].count;
+        }
+        out.push_back(m);
+        i += cnt;
+    }
+    const bool shrunk = out.size() < items.size();
+    items.swap(out);
+    return shrunk;
+}
+} // namespace eb200
+
 int eb200_contract_grouped(void *stream, int64_t n, eb200_contract_desc *descs, int32_t *n_launched_groups) {
     using namespace eb200;
     if (n < 0 || (n > 0 && !descs)) return fail(EB200_ERR_INVALID_ARGUMENT, "eb200_contract_grouped: bad arguments");
-    auto same_shape = [](const eb200_contract_desc &x, const eb200_contract_desc &y) {
-        if (x.n_unique != y.n_unique || x.conj_a != y.conj_a || x.conj_b != y.conj_b || x.force_kernel != y.force_kernel || x.split_k != y.split_k) return false;
-        for (int k = 0; k < 2; k++)
-            if (x.alpha[k] != y.alpha[k] || x.beta[k] != y.beta[k]) return false;
-        for (int u = 0; u < x.n_unique; u++)
-            if (x.extent[u] != y.extent[u]) return false;
-        const eb200_tensor_desc *tx[3] = {&x.C, &x.A, &x.B}, *ty[3] = {&y.C, &y.A, &y.B};
-        for (int t = 0; t < 3; t++) {
-            if (tx[t]->dtype != ty[t]->dtype || tx[t]->rank != ty[t]->rank) return false;
-            for (int i = 0; i < tx[t]->rank; i++)
-                if (tx[t]->index[i] != ty[t]->index[i] || tx[t]->stride[i] != ty[t]->stride[i]) return false;
-        }
-        return true;
-    };
-    auto step_of = [](const eb200_tensor_desc &x, const eb200_tensor_desc &y, int64_t &step) { // element step y - x, if whole
-        ptrdiff_t d = (const char *)y.data - (const char *)x.data;
-        ptrdiff_t es = (ptrdiff_t)dtype_size(x.dtype);
-        if (d % es) return false;
-        step = d / es;
-        return true;
-    };
-    // pass 1: cut the list into runs that fold
-    struct Run { int64_t first, cnt, sC, sA, sB; };
-    std::vector<Run> runs;
-    for (int64_t i = 0; i < n;) {
-        eb200_contract_desc &first = descs[i];
-        int64_t              cnt = 1, sC = 0, sA = 0, sB = 0;
-        bool                 room = first.n_unique < EB200_MAX_UNIQUE && first.C.rank < EB200_MAX_RANK && first.A.rank < EB200_MAX_RANK && first.B.rank < EB200_MAX_RANK;
-        if (room && i + 1 < n && same_shape(first, descs[i + 1]) && step_of(first.C, descs[i + 1].C, sC) && step_of(first.A, descs[i + 1].A, sA) &&
-            step_of(first.B, descs[i + 1].B, sB) && sC > 0 && sA >= 0 && sB >= 0 && (sA > 0 || sB > 0)) {
-            cnt = 2;
-            while (i + cnt < n && same_shape(first, descs[i + cnt])) {
-                int64_t c, a, b;
-                if (!step_of(descs[i + cnt - 1].C, descs[i + cnt].C, c) || !step_of(descs[i + cnt - 1].A, descs[i + cnt].A, a) ||
-                    !step_of(descs[i + cnt - 1].B, descs[i + cnt].B, b) || c != sC || a != sA || b != sB)
-                    break;
-                cnt++;
-            }
-        }
-        runs.push_back({i, cnt, sC, sA, sB});
-        i += cnt;
-    }
-    // pass 2: dispatch. Several runs (ragged blocks: each too small to fill 148 SMs) are spread over a few auxiliary
-    // streams forked from, and joined back into, the caller's stream, so their kernels overlap on the device.
-    // The members of a group must be independent (distinct outputs, no output aliasing an input), as blocks are.
+    std::vector<GroupItem> items((size_t)n);
+    for (int64_t i = 0; i < n; i++) items[(size_t)i] = {descs[i], i, 1};
+    for (int pass = 0; pass < 6 && items.size() > 1 && group_fold_pass(items); pass++) {}
+
     cudaStream_t  user = as_stream(stream);
     GroupStreams &gs = group_streams();
-    const int     naux = runs.size() > 1 ? gs.ensure() : 0;
+    const int     naux = items.size() > 1 ? gs.ensure() : 0;
     if (naux > 0) {
         EB_CUDA(cudaEventRecord(gs.fork, user));
         for (int a = 0; a < naux; a++) EB_CUDA(cudaStreamWaitEvent(gs.aux[a], gs.fork, 0));
     }
-    int32_t groups = 0;
-    int     rc = EB200_OK;
-    for (size_t r = 0; r < runs.size() && rc == EB200_OK; r++) {
-        const Run           &run = runs[r];
-        eb200_contract_desc &first = descs[run.first];
-        const int            lane = naux > 0 ? int(r % size_t(naux + 1)) : 0;
-        cudaStream_t         s = lane == 0 ? user : gs.aux[lane - 1];
-        if (run.cnt == 1) {
-            rc = contract_dispatch(s, first);
-        } else {
-            eb200_contract_desc m = first;
-            const int           g = m.n_unique++;
-            m.extent[g] = run.cnt;
-            auto prepend = [&](eb200_tensor_desc &t, int64_t step) {
-                if (step == 0) return; // shared by every member of the group: the new index does not address it
-                for (int k = t.rank; k > 0; k--) { t.index[k] = t.index[k - 1]; t.stride[k] = t.stride[k - 1]; }
-                t.index[0] = g;
-                t.stride[0] = step;
-                t.rank++;
-            };
-            prepend(m.C, run.sC); prepend(m.A, run.sA); prepend(m.B, run.sB);
-            rc = contract_dispatch(s, m);
-            for (int64_t k = 0; k < run.cnt; k++) { descs[run.first + k].kernel_used = m.kernel_used; descs[run.first + k].launches = k == 0 ? m.launches : 0; }
+    int rc = EB200_OK;
+    for (size_t r = 0; r < items.size() && rc == EB200_OK; r++) {
+        GroupItem &it = items[r];
+        // same output -> same stream (accumulations stay ordered); different outputs spread over the lanes
+        const int    lane = naux > 0 ? int((((uintptr_t)it.d.C.data) / 256u * 2654435761u >> 16) % (unsigned)(naux + 1)) : 0;
+        cudaStream_t s = lane == 0 ? user : gs.aux[lane - 1];
+        rc = contract_dispatch(s, it.d);
+        for (int64_t k = 0; k < it.count; k++) {
+            descs[it.first + k].kernel_used = it.d.kernel_used;
+            descs[it.first + k].launches = k == 0 ? it.d.launches : 0;
         }
-        groups++;
     }
     if (naux > 0) { // always join, also after an error, so the caller's stream never runs ahead of forked work
         for (int a = 0; a < naux; a++) {
@@ -694,7 +716,7 @@ int eb200_contract_grouped(void *stream, int64_t n, eb200_contract_desc *descs, 
         }
     }
     if (rc) return rc;
-    if (n_launched_groups) *n_launched_groups = groups;
+    if (n_launched_groups) *n_launched_groups = (int32_t)items.size();
     return EB200_OK;
 }
 

@@ -5,14 +5,16 @@
 //
 // B200-first: tiles are carved out of a growing arena (a few large device allocations) instead of one allocation per
 // tile, so equal-size tiles created one after another sit at a constant distance and eb200_contract_grouped can fold them
-// into batched launches. A tiled contraction is issued in ROUNDS: round r holds the r-th contribution to every output
-// tile, so the members of a round are independent (one grouped call, no host wait, ragged members overlapping on auxiliary
-// streams) and successive rounds accumulate in stream order. The reference runs one einsum + wait per tile triple under a
-// per-tile lock.
+// level by level: the accumulation over tile columns becomes one contraction with a longer K, rows of output tiles become
+// batches, and a full grid of equal tiles collapses into a single launch. A tiled contraction is ONE grouped call: all
+// tile triples in the reference's enumeration order (last unique index fastest, so the contributions to one output tile
+// are neighbours); what does not fold overlaps on auxiliary streams, contributions to the same tile staying in order.
+// The reference runs one einsum + wait per tile triple under a per-tile lock.
 #pragma once
 #include <Einsums/B200/LinearAlgebra.hpp>
 #include <Einsums/B200/TensorAlgebra.hpp>
 
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <numeric>
@@ -29,11 +31,13 @@ class DeviceArena {
     ~DeviceArena() {
         for (auto &c : _chunks) eb200_free(c.base);
     }
+    /// chunk size: what the whole tensor would need if every tile existed, capped — so that a (nearly) full grid is one
+    /// contiguous run of tiles and an almost empty one wastes at most one chunk
+    explicit DeviceArena(size_t dense_bytes) : _chunk(std::clamp<size_t>(dense_bytes, size_t(4) << 10, size_t(512) << 20)) {}
     void *take(size_t bytes) {
         bytes = (bytes + 255) / 256 * 256;
         if (_chunks.empty() || _chunks.back().used + bytes > _chunks.back().cap) {
-            size_t cap = std::max<size_t>(bytes, std::min<size_t>(_next, size_t(256) << 20));
-            _next = std::min<size_t>(_next * 2, size_t(256) << 20);
+            size_t cap = std::max<size_t>(bytes, _chunk);
             void *p = nullptr;
             (void)gpu::get_stream();
             EB200_CHECK(eb200_malloc(&p, cap));
@@ -48,7 +52,7 @@ class DeviceArena {
   private:
     struct Chunk { char *base; size_t cap, used; };
     std::vector<Chunk> _chunks;
-    size_t             _next = size_t(1) << 20;
+    size_t             _chunk = size_t(1) << 20;
 };
 } // namespace detail
 
@@ -126,7 +130,7 @@ template <typename T, size_t R> class TiledDeviceTensor {
             s[size_t(a)] = n;
             n *= d[size_t(a)];
         }
-        if (!_arena) _arena = std::make_unique<detail::DeviceArena>();
+        if (!_arena) _arena = std::make_unique<detail::DeviceArena>(dense_bytes());
         T *p = static_cast<T *>(_arena->take(size_t(std::max<std::int64_t>(n, 1)) * sizeof(T)));
         if (n) EB200_CHECK(eb200_memset_zero(p, size_t(n) * sizeof(T), gpu::get_stream()));
         std::string tname = _name + " - (";
@@ -237,6 +241,12 @@ template <typename T, size_t R> class TiledDeviceTensor {
     }
 
   private:
+    size_t dense_bytes() const {
+        double b = double(sizeof(T));
+        for (size_t a = 0; a < R; a++) b *= double(_dims[a]);
+        b += 256.0 * double(grid_size());
+        return b > 1e18 ? size_t(1e18) : size_t(b);
+    }
     void finish() {
         for (size_t a = 0; a < R; a++) {
             _offsets[a].clear();
@@ -321,7 +331,7 @@ std::vector<std::int64_t> grid_ranges(TileTables<CR, AR, BR> const &tab, CType c
     return g;
 }
 
-/// C = beta*C + alpha * A*B over tiles (reference: TileAlgebra.hpp:17-91). Issued in rounds, see the file header.
+/// C = beta*C + alpha * A*B over tiles (reference: TileAlgebra.hpp:17-91): one grouped call, see the file header.
 template <typename T, size_t CR, size_t AR, size_t BR>
 void tiled_contract(TileTables<CR, AR, BR> const &tab, T beta, TiledDeviceTensor<T, CR> *C, T alpha, TiledDeviceTensor<T, AR> const &A,
                     TiledDeviceTensor<T, BR> const &B, bool conj_a, bool conj_b) {
@@ -329,9 +339,8 @@ void tiled_contract(TileTables<CR, AR, BR> const &tab, T beta, TiledDeviceTensor
     if (beta == T(0)) C->zero_no_clear();
     else if (beta != T(1)) *C *= beta;
 
-    std::map<std::array<int, CR>, size_t>         seen; // contributions so far per output tile
-    std::vector<std::vector<eb200_contract_desc>> rounds;
-    std::int64_t                                  total = 1;
+    std::vector<eb200_contract_desc> descs;
+    std::int64_t                     total = 1;
     for (auto g : grid) total *= g;
     std::vector<int> u(size_t(tab.n_unique), 0);
     for (std::int64_t s = 0; s < total; s++) {
@@ -348,11 +357,9 @@ void tiled_contract(TileTables<CR, AR, BR> const &tab, T beta, TiledDeviceTensor
         auto       &ct = C->tile(ci);
         auto const &at = A.tile(ai);
         auto const &bt = B.tile(bi);
-        size_t      r = seen[ci]++;
-        if (rounds.size() <= r) rounds.emplace_back();
-        rounds[r].push_back(tile_desc<T>(tab, T(1), ct.gpu_data(), ct.dims(), ct.strides(), alpha, at, bt, conj_a, conj_b));
+        descs.push_back(tile_desc<T>(tab, T(1), ct.gpu_data(), ct.dims(), ct.strides(), alpha, at, bt, conj_a, conj_b));
     }
-    for (auto &round : rounds) EB200_CHECK(eb200_contract_grouped(gpu::get_stream(), std::int64_t(round.size()), round.data(), nullptr));
+    if (!descs.empty()) EB200_CHECK(eb200_contract_grouped(gpu::get_stream(), std::int64_t(descs.size()), descs.data(), nullptr));
     gpu::op_wait();
 }
 
@@ -468,7 +475,7 @@ void gemm(U alpha, TiledDeviceTensor<T, 2> const &A, TiledDeviceTensor<T, 2> con
     gemm(TransA ? 't' : 'n', TransB ? 't' : 'n', alpha, A, B, beta, C);
 }
 
-/// y = beta*y + alpha*op(A)*x with a tiled A and ordinary vectors (reference :231-355): rounds over the tile columns
+/// y = beta*y + alpha*op(A)*x with a tiled A and ordinary vectors (reference :231-355)
 template <typename T, DeviceTensorLike XType, DeviceTensorLike YType, typename U>
     requires(XType::Rank == 1 && YType::Rank == 1)
 void gemv(char transA, U alpha, TiledDeviceTensor<T, 2> const &A, XType const &x, U beta, YType *y) {
@@ -482,19 +489,16 @@ void gemv(char transA, U alpha, TiledDeviceTensor<T, 2> const &A, XType const &x
     tab.c = {0};
     tab.a = tA ? std::array<int, 2>{1, 0} : std::array<int, 2>{0, 1};
     tab.b = {1};
-    std::vector<std::vector<eb200_contract_desc>> rounds;
-    std::map<int, size_t>                         seen;
+    std::vector<eb200_contract_desc> descs;
     for (auto const &[idx, t] : A.tiles()) {
         if (!t.size()) continue;
         int          to = idx[out_axis], ti = idx[in_axis];
         std::int64_t o0 = A.tile_offset(out_axis)[size_t(to)], i0 = A.tile_offset(in_axis)[size_t(ti)];
         DeviceTensorView<T, 1> xs(const_cast<T *>(x.gpu_data()) + i0 * x.stride(0), Dim<1>{A.tile_size(in_axis)[size_t(ti)]}, Stride<1>{x.stride(0)});
         std::array<std::int64_t, 1> cd{A.tile_size(out_axis)[size_t(to)]}, cs{y->stride(0)};
-        size_t r = seen[to]++;
-        if (rounds.size() <= r) rounds.emplace_back();
-        rounds[r].push_back(tensor_algebra::detail::tile_desc<T>(tab, T(1), y->gpu_data() + o0 * y->stride(0), cd, cs, T(alpha), t, xs, cA, false));
+        descs.push_back(tensor_algebra::detail::tile_desc<T>(tab, T(1), y->gpu_data() + o0 * y->stride(0), cd, cs, T(alpha), t, xs, cA, false));
     }
-    for (auto &round : rounds) EB200_CHECK(eb200_contract_grouped(gpu::get_stream(), std::int64_t(round.size()), round.data(), nullptr));
+    if (!descs.empty()) EB200_CHECK(eb200_contract_grouped(gpu::get_stream(), std::int64_t(descs.size()), descs.data(), nullptr));
     gpu::op_wait();
 }
 template <bool TransA, typename T, DeviceTensorLike XType, DeviceTensorLike YType, typename U>
