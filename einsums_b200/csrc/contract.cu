@@ -560,6 +560,8 @@ int eb200_contract(void *stream, eb200_contract_desc *desc) {
     return eb200::contract_dispatch(eb200::as_stream(stream), *desc);
 }
 
+} // extern "C" (helpers below need C++ linkage)
+
 namespace eb200 {
 // Auxiliary streams of eb200_contract_grouped: per host thread, created on first use for the current device.
 struct GroupStreams {
@@ -643,23 +645,27 @@ static bool group_foldable(const eb200_contract_desc &d, const int64_t st[3]) {
     if (st[0] == 0) return st[1] > 0 && st[2] > 0 && d.beta[0] == 1.0 && d.beta[1] == 0.0; // accumulation into one C
     return false;
 }
-/// one folding pass; returns true when the list got shorter
-static bool group_fold_pass(std::vector<GroupItem> &items) {
-    std::vector<GroupItem> out;
-    out.reserve(items.size());
-    for (size_t i = 0; i < items.size();) {
-        const eb200_contract_desc &first = items[i].d;
+/// one folding pass over `n` descriptors reached through `at(i)`; emits one item per run
+template <typename At, typename Range> static void group_fold_pass(size_t n, At &&at, Range &&range_of, std::vector<GroupItem> &out) {
+    out.clear();
+    for (size_t i = 0; i < n;) {
+        const eb200_contract_desc &first = at(i);
         size_t                     cnt = 1;
         int64_t                    st[3] = {0, 0, 0};
         const bool room = first.n_unique < EB200_MAX_UNIQUE && first.C.rank < EB200_MAX_RANK && first.A.rank < EB200_MAX_RANK && first.B.rank < EB200_MAX_RANK;
-        if (room && i + 1 < items.size() && group_same_shape(first, items[i + 1].d) && group_steps(first, items[i + 1].d, st) && group_foldable(first, st)) {
+        if (room && i + 1 < n && group_same_shape(first, at(i + 1)) && group_steps(first, at(i + 1), st) && group_foldable(first, st)) {
             cnt = 2;
             int64_t nx[3];
-            while (i + cnt < items.size() && group_same_shape(first, items[i + cnt].d) && group_steps(items[i + cnt - 1].d, items[i + cnt].d, nx) &&
-                   nx[0] == st[0] && nx[1] == st[1] && nx[2] == st[2])
+            while (i + cnt < n && group_same_shape(first, at(i + cnt)) && group_steps(at(i + cnt - 1), at(i + cnt), nx) && nx[0] == st[0] &&
+                   nx[1] == st[1] && nx[2] == st[2])
                 cnt++;
         }
-        GroupItem m = items[i];
+        out.emplace_back();
+        GroupItem &m = out.back();
+        m.d = first;
+        m.first = range_of(i).first;
+        m.count = 0;
+        for (size_t k = 0; k < cnt; k++) m.count += range_of(i + k).second;
         if (cnt > 1) {
             const int g = m.d.n_unique++;
             m.d.extent[g] = (int64_t)cnt;
@@ -672,23 +678,28 @@ static bool group_fold_pass(std::vector<GroupItem> &items) {
                 td.stride[0] = st[t];
                 td.rank++;
             }
-            for (size_t k = 1; k < cnt; k++) m.count += items[i + k].count;
         }
-        out.push_back(m);
         i += cnt;
     }
-    const bool shrunk = out.size() < items.size();
-    items.swap(out);
-    return shrunk;
 }
 } // namespace eb200
+
+extern "C" {
 
 int eb200_contract_grouped(void *stream, int64_t n, eb200_contract_desc *descs, int32_t *n_launched_groups) {
     using namespace eb200;
     if (n < 0 || (n > 0 && !descs)) return fail(EB200_ERR_INVALID_ARGUMENT, "eb200_contract_grouped: bad arguments");
-    std::vector<GroupItem> items((size_t)n);
-    for (int64_t i = 0; i < n; i++) items[(size_t)i] = {descs[i], i, 1};
-    for (int pass = 0; pass < 6 && items.size() > 1 && group_fold_pass(items); pass++) {}
+    std::vector<GroupItem> items, next;
+    // level 1 reads the caller's array in place; further levels fold the folded list until nothing changes
+    group_fold_pass((size_t)n, [&](size_t i) -> const eb200_contract_desc & { return descs[i]; },
+                    [&](size_t i) { return std::pair<int64_t, int64_t>((int64_t)i, 1); }, items);
+    for (int pass = 0; pass < 6 && items.size() > 1; pass++) {
+        group_fold_pass(items.size(), [&](size_t i) -> const eb200_contract_desc & { return items[i].d; },
+                        [&](size_t i) { return std::pair<int64_t, int64_t>(items[i].first, items[i].count); }, next);
+        const bool shrunk = next.size() < items.size();
+        items.swap(next);
+        if (!shrunk) break;
+    }
 
     cudaStream_t  user = as_stream(stream);
     GroupStreams &gs = group_streams();

@@ -146,6 +146,11 @@ template <typename T, size_t R> class TiledDeviceTensor {
         requires(sizeof...(I) == R && (std::is_integral_v<std::remove_cvref_t<I>> && ...))
     Tile &tile(I... i) { return tile(TileIndex{int(i)...}); }
     std::map<TileIndex, Tile> const &tiles() const { return _tiles; }
+    /// the tile if it exists, else nullptr (one lookup; idx must already be in range)
+    Tile const *find_tile(TileIndex const &idx) const {
+        auto it = _tiles.find(idx);
+        return it == _tiles.end() ? nullptr : &it->second;
+    }
 
     /// grid position that holds element index idx, and the index inside that tile (reference: tile_of)
     TileIndex tile_of(std::array<std::int64_t, R> idx, std::array<std::int64_t, R> *inside = nullptr) const {
@@ -292,9 +297,9 @@ template <size_t CR, size_t AR, size_t BR> struct TileTables {
 };
 
 template <typename T, typename CT, typename AT, typename BT, size_t CR, size_t AR, size_t BR>
-eb200_contract_desc tile_desc(TileTables<CR, AR, BR> const &tab, T beta, CT *c_data, std::array<std::int64_t, CR> const &cdim,
-                              std::array<std::int64_t, CR> const &cstr, T alpha, AT const &A, BT const &B, bool conj_a, bool conj_b) {
-    eb200_contract_desc d{};
+void tile_desc_into(eb200_contract_desc &d, TileTables<CR, AR, BR> const &tab, T beta, CT *c_data, std::array<std::int64_t, CR> const &cdim,
+                    std::array<std::int64_t, CR> const &cstr, T alpha, AT const &A, BT const &B, bool conj_a, bool conj_b) {
+    d.conj_a = d.conj_b = d.force_kernel = d.split_k = d.kernel_used = d.launches = 0;
     d.n_unique = tab.n_unique;
     for (int u = 0; u < tab.n_unique; u++) d.extent[u] = -1;
     auto put = [&](int u, std::int64_t e) {
@@ -313,6 +318,12 @@ eb200_contract_desc tile_desc(TileTables<CR, AR, BR> const &tab, T beta, CT *c_d
     d.alpha[0] = a.real(); d.alpha[1] = a.imag(); d.beta[0] = b.real(); d.beta[1] = b.imag();
     d.conj_a = conj_a && IsComplexV<T>;
     d.conj_b = conj_b && IsComplexV<T>;
+}
+template <typename T, typename CT, typename AT, typename BT, size_t CR, size_t AR, size_t BR>
+eb200_contract_desc tile_desc(TileTables<CR, AR, BR> const &tab, T beta, CT *c_data, std::array<std::int64_t, CR> const &cdim,
+                              std::array<std::int64_t, CR> const &cstr, T alpha, AT const &A, BT const &B, bool conj_a, bool conj_b) {
+    eb200_contract_desc d{};
+    tile_desc_into<T>(d, tab, beta, c_data, cdim, cstr, alpha, A, B, conj_a, conj_b);
     return d;
 }
 
@@ -353,11 +364,14 @@ void tiled_contract(TileTables<CR, AR, BR> const &tab, T beta, TiledDeviceTensor
         for (size_t p = 0; p < AR; p++) ai[p] = u[size_t(tab.a[p])];
         for (size_t p = 0; p < BR; p++) bi[p] = u[size_t(tab.b[p])];
         for (size_t p = 0; p < CR; p++) ci[p] = u[size_t(tab.c[p])];
-        if (!A.has_tile(ai) || !B.has_tile(bi) || A.has_zero_size(ai) || B.has_zero_size(bi) || C->has_zero_size(ci)) continue;
-        auto       &ct = C->tile(ci);
-        auto const &at = A.tile(ai);
-        auto const &bt = B.tile(bi);
-        descs.push_back(tile_desc<T>(tab, T(1), ct.gpu_data(), ct.dims(), ct.strides(), alpha, at, bt, conj_a, conj_b));
+        auto const *at = A.find_tile(ai);
+        if (!at || !at->size()) continue;
+        auto const *bt = B.find_tile(bi);
+        if (!bt || !bt->size() || C->has_zero_size(ci)) continue;
+        auto &ct = C->tile(ci);
+        if (descs.empty()) descs.reserve(size_t(std::min<std::int64_t>(total - s, std::int64_t(1) << 20)));
+        descs.emplace_back(); // filled in place: only the fields the library reads are written
+        tile_desc_into<T>(descs.back(), tab, T(1), ct.gpu_data(), ct.dims(), ct.strides(), alpha, *at, *bt, conj_a, conj_b);
     }
     if (!descs.empty()) EB200_CHECK(eb200_contract_grouped(gpu::get_stream(), std::int64_t(descs.size()), descs.data(), nullptr));
     gpu::op_wait();
