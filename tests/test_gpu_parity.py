@@ -237,6 +237,41 @@ def test_grouped_shared_operand_and_rank3(gpu, oracle):
         gpu.contract_grouped("ij", Cs, "ikl", [Ad[0]], "lkj", [Md] * nb)
 
 
+@pytest.mark.parametrize("present", ["all", "checkerboard", "random"])
+def test_grouped_tile_grid_folds_to_k_and_batches(gpu, oracle, present):
+    """A tiled product C(i,j) += A(i,k) B(k,j) handed over as one descriptor per tile triple (TileAlgebra.hpp:57-90), tiles packed
+    grid-major in one buffer: contributions to one C tile fold into a longer K, then the grid folds into batches."""
+    g, t = 4, 24
+    rng = np.random.default_rng(21)
+    Ah, Bh = rand(rng, (g, g, t, t), np.float64), rand(rng, (g, g, t, t), np.float64)
+    Ch = rand(rng, (g, g, t, t), np.float64)
+    keep = {"all": lambda i, j: True, "checkerboard": lambda i, j: (i + j) % 2 == 0, "random": lambda i, j: (i * 7 + j * 3) % 5 != 0}[present]
+    Ad, Bd, Cd = dev(Ah), dev(Bh), dev(Ch)
+    Cs, As, Bs = [], [], []
+    ref = Ch.copy()
+    for i in range(g):
+        for j in range(g):
+            for k in range(g):
+                if keep(i, k) and keep(k, j):
+                    Cs.append(Cd[i, j]); As.append(Ad[i, k]); Bs.append(Bd[k, j])
+                    blk = np.ascontiguousarray(ref[i, j])
+                    oracle.einsum_generic("ij", blk, "ik", np.ascontiguousarray(Ah[i, k]), "kj", np.ascontiguousarray(Bh[k, j]), 1.0, 1.0)
+                    ref[i, j] = blk
+    descs, groups = gpu.contract_grouped("ij", Cs, "ik", As, "kj", Bs, 1.0, 1.0)
+    torch.cuda.synchronize()
+    assert_close(Cd.cpu().numpy(), ref, np.float64, f"tile grid {present}")
+    if present == "all":
+        assert groups == 1 and sum(d.launches for d in descs) == 1
+    else:
+        assert groups < len(Cs)
+    # beta != 1 with a repeated output must not fold into K (it would apply beta once instead of per member)
+    C2 = dev(Ch)
+    descs, groups = gpu.contract_grouped("ij", [C2[0, 0]] * 2, "ik", [Ad[0, 0], Ad[0, 1]], "kj", [Bd[0, 0], Bd[1, 0]], 1.0, 0.5)
+    torch.cuda.synchronize()
+    want = 0.5 * (0.5 * Ch[0, 0] + Ah[0, 0] @ Bh[0, 0]) + Ah[0, 1] @ Bh[1, 0]
+    assert groups == 2 and rel_err(C2[0, 0].cpu().numpy(), want) <= 1e-12
+
+
 def test_beta_zero_never_reads_c(gpu):
     A = torch.rand(70, 50, dtype=torch.float64, device="cuda")
     B = torch.rand(50, 90, dtype=torch.float64, device="cuda")
