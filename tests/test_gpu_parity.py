@@ -70,6 +70,100 @@ def test_contract_small_all_patterns(gpu, oracle, case, dtype):
         run_case(gpu, oracle, c_idx, a_idx, b_idx, ext, dtype, alpha, beta)
 
 
+def _random_spec(rng):
+    """A random legal contraction: 2-6 unique indices, each placed in a random non-empty subset of {C, A, B} (indices only
+    in C broadcast, indices in A and/or B but not C are summed, indices everywhere are batch/Hadamard), random axis orders,
+    sometimes a repeated index inside one operand, extents 1-7 (1 and primes on purpose)."""
+    letters = "abcdefgh"
+    nu = int(rng.integers(2, 7))
+    ext, c, a, b = {}, [], [], []
+    for u in range(nu):
+        ch = letters[u]
+        ext[ch] = int(rng.choice([1, 2, 3, 4, 5, 7]))
+        where = int(rng.integers(1, 8))  # bit 0: C, bit 1: A, bit 2: B
+        if where & 1: c.append(ch)
+        if where & 2: a.append(ch)
+        if where & 4: b.append(ch)
+    if not a: a.append(letters[0]); ext.setdefault(letters[0], 2)
+    if not b: b.append(letters[min(1, nu - 1)])
+    if rng.random() < 0.2 and len(a) < 4: a.append(a[int(rng.integers(0, len(a)))])  # Hadamard inside A
+    for lst in (c, a, b):
+        rng.shuffle(lst)
+    return "".join(c), "".join(a), "".join(b), ext
+
+
+@pytest.mark.parametrize("chunk", range(8))
+def test_contract_fuzz(gpu, oracle, chunk):
+    """Seeded random contractions (25 per chunk, 200 in total) against the oracle's generic loops, all four value types, random
+    prefactors and conjugations. The device semantics (sum over the full unique space) are the oracle's `full_space` mode."""
+    rng = np.random.default_rng(1000 + chunk)
+    for n in range(25):
+        c_idx, a_idx, b_idx, ext = _random_spec(rng)
+        dtype = [np.float64, np.float32, np.complex128, np.complex64][int(rng.integers(0, 4))]
+        alpha, beta = [(1.0, 0.0), (0.5, 2.0), (-1.0, 1.0), (2.0, 0.0)][int(rng.integers(0, 4))]
+        conj_a, conj_b = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        try:
+            run_case(gpu, oracle, c_idx, a_idx, b_idx, ext, dtype, alpha, beta, conj_a, conj_b, seed=chunk * 100 + n)
+        except AssertionError as e:
+            raise AssertionError(f"fuzz case {chunk}/{n}: {c_idx}<-{a_idx},{b_idx} ext={ext} {np.dtype(dtype)} a={alpha} b={beta} conj={conj_a},{conj_b}: {e}") from e
+
+
+@pytest.mark.parametrize("chunk", range(4))
+def test_contract_fuzz_mid_strided(gpu, oracle, chunk):
+    """Random contractions at tile-kernel sizes (ragged extents 1...40, index space up to 2e7 points) on padded, strided
+    views of larger buffers: bytes outside the views must stay untouched and every family / split-K choice must agree
+    with the oracle."""
+    rng = np.random.default_rng(2000 + chunk)
+    done = 0
+    while done < 10:
+        letters = "abcde"
+        nu = int(rng.integers(3, 6))
+        ext = {letters[u]: int(rng.choice([1, 3, 8, 17, 33, 40])) for u in range(nu)}
+        if np.prod([float(v) for v in ext.values()]) > 2e7:
+            continue
+        c, a, b = [], [], []
+        for u in range(nu):
+            where = int(rng.choice([3, 5, 6, 6, 6, 7, 3, 5]))  # every index touches at least two tensors; 6 = contracted
+            ch = letters[u]
+            if where & 1: c.append(ch)
+            if where & 2: a.append(ch)
+            if where & 4: b.append(ch)
+        if not a or not b:
+            continue
+        for lst in (c, a, b):
+            rng.shuffle(lst)
+        c_idx, a_idx, b_idx = "".join(c), "".join(a), "".join(b)
+        dtype = [np.float64, np.float64, np.float32, np.complex128][int(rng.integers(0, 4))]
+        alpha, beta = [(1.0, 0.0), (0.5, 2.0), (-1.0, 1.0)][int(rng.integers(0, 3))]
+
+        def padded(idx):
+            shape = tuple(ext[x] for x in idx)
+            pad = tuple(int(rng.integers(0, 3)) for _ in idx)
+            big = rand(rng, tuple(s + p for s, p in zip(shape, pad)), dtype)
+            return big, big[tuple(slice(0, s) for s in shape)] if idx else big
+
+        Abig, Av = padded(a_idx); Bbig, Bv = padded(b_idx); Cbig, Cv = padded(c_idx)
+        ref_big = Cbig.copy()
+        ref_view = ref_big[tuple(slice(0, ext[x]) for x in c_idx)] if c_idx else ref_big
+        tmp = np.ascontiguousarray(ref_view)
+        oracle.einsum_generic(c_idx, tmp, a_idx, np.ascontiguousarray(Av), b_idx, np.ascontiguousarray(Bv), alpha, beta)
+        ref_view[...] = tmp
+        Cd_big = dev(Cbig)
+        Cd = Cd_big[tuple(slice(0, ext[x]) for x in c_idx)] if c_idx else Cd_big
+        Ad = dev(Abig)[tuple(slice(0, ext[x]) for x in a_idx)]
+        Bd = dev(Bbig)[tuple(slice(0, ext[x]) for x in b_idx)]
+        d = gpu.contract(c_idx, Cd, a_idx, Ad, b_idx, Bd, alpha, beta)
+        torch.cuda.synchronize()
+        got = Cd_big.cpu().numpy()
+        what = f"fuzz-mid {chunk}/{done}: {c_idx}<-{a_idx},{b_idx} ext={ext} {np.dtype(dtype)} a={alpha} b={beta} kernel={d.kernel_used}"
+        assert_close(got, ref_big, dtype, what)
+        mask = np.ones(Cbig.shape, bool)
+        if c_idx:
+            mask[tuple(slice(0, ext[x]) for x in c_idx)] = False
+            assert np.array_equal(got[mask], Cbig[mask]), what + " wrote outside the view"
+        done += 1
+
+
 @pytest.mark.parametrize("conj", [(True, False), (False, True), (True, True)])
 @pytest.mark.parametrize("case", [CASES[0], CASES[1], CASES[4], CASES[6], CASES[7], CASES[8], CASES[10]], ids=lambda c: f"{c[0]}<-{c[1]},{c[2]}")
 def test_contract_conj(gpu, oracle, case, conj):
