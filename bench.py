@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-v", type=int, default=0, help="v for the CPU sample (0 = full config)")
+    ap.add_argument("--e2e-slab-mb", type=int, default=256, help="slab size of the host-path pipeline (MiB)")
     ap.add_argument("--cpu-configs", action="store_true",
                     help="with --impl reference: also time the CPU port on the other BASELINE configs at host-sized samples (one JSON line each)")
     return ap.parse_args()
@@ -277,7 +278,7 @@ def run_ours(args):
         ref_rows = hWa[:2].clone()
         del Wa
         torch.cuda.empty_cache()
-        hc = HostContraction("abef", (v, v, v, v), "mnef", (o, o, v, v), "mnab", (o, o, v, v), slab_bytes=1 << 30)
+        hc = HostContraction("abef", (v, v, v, v), "mnef", (o, o, v, v), "mnab", (o, o, v, v), slab_bytes=args.e2e_slab_mb << 20)
         counts = {}
 
         def e2e_step():
@@ -307,7 +308,7 @@ def run_ours(args):
         e2e = {"value": world * FLOPS_STEP / (te.item() / ke * 1e-3) / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": counts["h2d"],
                "d2h_bytes_per_step": counts["d2h"], "ms_per_step": te.item() / ke, "steps": ke, "max_abs_diff_vs_resident_path": e2e_err,
                "note": "pinned host -> device of g, t, Wmnij, Wabef; both einsums; device -> pinned host of both results; "
-                       "Wabef in 1 GiB slabs with H2D|compute|D2H overlapped (einsums_b200.host_path)"}
+                       f"Wabef in {args.e2e_slab_mb} MiB slabs with H2D|compute|D2H overlapped (einsums_b200.host_path)"}
         Wa = None
 
     if rank != 0:
