@@ -73,6 +73,10 @@ def build(verbose: bool = False) -> str:
     return LIB_PATH
 
 
+class HostStats(C.Structure):
+    _fields_ = [("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("slabs", C.c_int64)]
+
+
 _lib = None
 
 _REAL = {"s": C.c_float, "d": C.c_double, "c": C.c_float, "z": C.c_double}
@@ -86,6 +90,7 @@ def _declare(lib):
     lib.eb200_contract.argtypes = [vp, C.POINTER(ContractDesc)]
     lib.eb200_contract_plan.argtypes = [C.POINTER(ContractDesc)]
     lib.eb200_contract_grouped.argtypes = [vp, C.c_int64, C.POINTER(ContractDesc), C.POINTER(C.c_int32)]
+    lib.eb200_contract_host.argtypes = [vp, C.POINTER(ContractDesc), C.c_size_t, C.POINTER(HostStats)]
     lib.eb200_malloc.argtypes = [C.POINTER(vp), C.c_size_t]
     lib.eb200_free.argtypes = [vp]
     lib.eb200_malloc_host.argtypes = [C.POINTER(vp), C.c_size_t]

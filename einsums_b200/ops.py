@@ -93,6 +93,15 @@ def contract(c_idx, Ct, a_idx, At, b_idx, Bt, alpha=1.0, beta=0.0, conj_a=False,
     return d
 
 
+def contract_host(c_idx, Ct, a_idx, At, b_idx, Bt, alpha=1.0, beta=0.0, conj_a=False, conj_b=False, slab_bytes=0, stream=None):
+    """eb200_contract_host: any of C, A, B may be a HOST tensor (pinned for overlap); C is updated in place, the call returns
+    when the result is in host memory. Returns the transfer statistics (h2d_bytes, d2h_bytes, slabs)."""
+    d = make_desc(c_idx, Ct, a_idx, At, b_idx, Bt, alpha, beta, conj_a, conj_b)
+    st = _lib.HostStats()
+    check(lib().eb200_contract_host(_stream(stream), C.byref(d), int(slab_bytes), C.byref(st)))
+    return st
+
+
 def make_group(c_idx, Cs, a_idx, As, b_idx, Bs, alpha=1.0, beta=0.0, conj_a=False, conj_b=False):
     """Descriptor array for eb200_contract_grouped (build once, run many times with run_group)."""
     if not (len(Cs) == len(As) == len(Bs)):

@@ -262,6 +262,20 @@ int eb200_contract(void *stream, eb200_contract_desc *desc);
  * *n_launched_groups (optional) receives the number of contractions actually dispatched (<= n). */
 int eb200_contract_grouped(void *stream, int64_t n, eb200_contract_desc *descs, int32_t *n_launched_groups);
 
+/* Contraction with tensors in HOST memory (pinned memory recommended; pageable works but copies do not overlap).
+ * Replaces the reference's host-tensor offload (LinearAlgebra/Bases/gemm.hpp:248-486 impl_gemm_gpu,
+ * TensorImpl/TensorImpl.hpp:1676-1776 gpu_cache_tensor). Every data pointer of the descriptor is inspected: device
+ * pointers are used in place, host operands are uploaded once, and a host C is processed in slabs of about `slab_bytes`
+ * (0 = 256 MiB) along its slowest axis with H2D | contract | D2H overlapped on three streams; C is updated in place.
+ * Host-resident tensors must be dense row-major; the slowest index of a host C must be an uncontracted index carried by
+ * exactly one operand. Returns after the result is in host memory. Device scratch is cached per host thread
+ * (eb200_contract_host_release frees it). */
+typedef struct eb200_host_stats {
+    int64_t h2d_bytes, d2h_bytes, slabs;
+} eb200_host_stats;
+int eb200_contract_host(void *stream, const eb200_contract_desc *desc, size_t slab_bytes, eb200_host_stats *stats);
+int eb200_contract_host_release(void);
+
 /* Host-side only (no device needed): classification the engine would pick for this
  * descriptor, written to desc->kernel_used. Lets CPU tests pin the planner. */
 int eb200_contract_plan(eb200_contract_desc *desc);

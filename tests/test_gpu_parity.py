@@ -366,6 +366,57 @@ def test_grouped_tile_grid_folds_to_k_and_batches(gpu, oracle, present):
     assert groups == 2 and rel_err(C2[0, 0].cpu().numpy(), want) <= 1e-12
 
 
+# ---------------------------------------------------------------------------------------------
+# host-resident tensors through eb200_contract_host (slab pipeline)
+@pytest.mark.parametrize("beta", [0.0, 1.0])
+@pytest.mark.parametrize("pinned", [True, False])
+def test_contract_host_slabs(gpu, oracle, beta, pinned):
+    o, v = 5, 24
+    rng = np.random.default_rng(31)
+    g, t, W0 = rand(rng, (o, o, v, v)), rand(rng, (o, o, v, v)), rand(rng, (v, v, v, v))
+    ref = W0.copy()
+    oracle.einsum_generic("abef", ref, "mnef", g, "mnab", t, 0.25, beta)
+    mk = (lambda x: torch.from_numpy(x.copy()).pin_memory()) if pinned else (lambda x: torch.from_numpy(x.copy()))
+    Wh, gh, th = mk(W0), mk(g), mk(t)
+    st = gpu.contract_host("abef", Wh, "mnef", gh, "mnab", th, 0.25, beta, slab_bytes=3 * v**3 * 8)   # 3 rows of `a` per slab
+    assert st.slabs == v // 3
+    assert st.d2h_bytes == W0.nbytes and st.h2d_bytes == g.nbytes + t.nbytes + (W0.nbytes if beta else 0)
+    assert_close(Wh.numpy(), ref, np.float64, f"contract_host beta={beta} pinned={pinned}")
+    # bit-identical to the resident path
+    Wd = dev(W0)
+    gpu.contract("abef", Wd, "mnef", dev(g), "mnab", dev(t), 0.25, beta)
+    assert np.array_equal(Wd.cpu().numpy(), Wh.numpy())
+
+
+def test_contract_host_mixed_residency_scalar_and_errors(gpu, oracle):
+    rng = np.random.default_rng(32)
+    A, B, C0 = rand(rng, (40, 30)), rand(rng, (30, 50)), rand(rng, (40, 50))
+    want = 2.0 * C0 + A @ B
+    # operands on the device, C on the host; the slab index lives in A
+    Ch = torch.from_numpy(C0.copy()).pin_memory()
+    st = gpu.contract_host("ij", Ch, "ik", dev(A), "kj", dev(B), 1.0, 2.0, slab_bytes=7 * 50 * 8)
+    assert st.slabs == 6 and st.h2d_bytes == C0.nbytes
+    assert rel_err(Ch.numpy(), want) <= 1e-12
+    # the slab index lives in B (C = B^T-like order), A on the host
+    Ch = torch.from_numpy(np.ascontiguousarray(C0.T)).pin_memory()
+    gpu.contract_host("ji", Ch, "ik", torch.from_numpy(A.copy()).pin_memory(), "kj", dev(B), 1.0, 2.0, slab_bytes=4096)
+    assert rel_err(Ch.numpy(), want.T) <= 1e-12
+    # host operands, device C
+    Cd = dev(C0)
+    gpu.contract_host("ij", Cd, "ik", torch.from_numpy(A.copy()).pin_memory(), "kj", torch.from_numpy(B.copy()), 1.0, 2.0)
+    assert rel_err(Cd.cpu().numpy(), want) <= 1e-12
+    # scalar on the host
+    s = torch.tensor(3.0, dtype=torch.float64).pin_memory()
+    gpu.contract_host("", s, "ik", torch.from_numpy(A.copy()), "ik", torch.from_numpy(A.copy()), 1.0, 0.5)
+    assert abs(float(s) - (1.5 + float((A * A).sum()))) <= 1e-10
+    # not supported: strided host C; slowest C index contracted away / carried by both operands
+    big = torch.zeros(40, 60, dtype=torch.float64).pin_memory()
+    with pytest.raises(Exception, match="dense row-major"):
+        gpu.contract_host("ij", big[:, :50], "ik", dev(A), "kj", dev(B))
+    with pytest.raises(Exception, match="slowest index"):
+        gpu.contract_host("ij", torch.zeros(40, 50, dtype=torch.float64), "ij", dev(C0), "ij", dev(C0))
+
+
 def test_beta_zero_never_reads_c(gpu):
     A = torch.rand(70, 50, dtype=torch.float64, device="cuda")
     B = torch.rand(50, 90, dtype=torch.float64, device="cuda")
