@@ -84,18 +84,19 @@ template <typename T, bool CONJ, int TILE, int ROWS> __global__ void __launch_bo
 // axis c, 8 independent stores. Needs even extents/strides and 2-element-aligned bases (checked on the host).
 template <typename T> struct alignas(2 * sizeof(T)) Pair { T x, y; };
 
-template <typename T, bool HAS_BETA> __global__ void __launch_bounds__(256, HAS_BETA ? 2 : 3) permute_tile_vec(const __grid_constant__ PermArgs a) {
-    constexpr int TILE = 64;
+// TILE = 64: 8 pairs per thread; TILE = 32 (extents that fill 64-tiles badly, e.g. 96 or 160): 2 pairs per thread, more CTAs per SM.
+template <typename T, bool HAS_BETA, int TILE> __global__ void __launch_bounds__(256, TILE == 64 ? (HAS_BETA ? 2 : 3) : 6) permute_tile_vec(const __grid_constant__ PermArgs a) {
+    constexpr int LX = TILE / 2, ROWS = 256 / LX, NI = TILE / ROWS; // lanes along the pair direction, rows per pass, passes
     __shared__ __align__(16) T tile[TILE * TILE];
     const T      *A = reinterpret_cast<const T *>(a.A);
     T            *C = reinterpret_cast<T *>(a.C);
     const T       alpha = make_scalar<T>(a.alpha[0], a.alpha[1]), beta = make_scalar<T>(a.beta[0], a.beta[1]);
     constexpr bool has_beta = HAS_BETA;
     const bool    plain = is_one(alpha) && !has_beta;
-    const int     tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
+    const int     tid = threadIdx.x, lx = tid % LX, ly = tid / LX;
     const int64_t per_rest = a.tiles_a * a.tiles_c;
     const int64_t ntiles = per_rest * a.rest.tot;
-    // swizzle: element (ia, ic) lives at tile[ia*64 + (ic ^ sw(ia))], sw(ia) = 2*((ia>>1)&7) keeps (even,odd) pairs together
+    // swizzle: element (ia, ic) lives at tile[ia*TILE + (ic ^ sw(ia))], sw(ia) = 2*((ia>>1)&7) keeps (even,odd) pairs together
     auto sw = [](int ia) { return ((ia >> 1) & 7) << 1; };
 
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -112,25 +113,25 @@ template <typename T, bool HAS_BETA> __global__ void __launch_bounds__(256, HAS_
         int64_t offA, offC;
         grp_offset2(a.rest, rest, ROLE_A, ROLE_C, offA, offC);
         const int64_t a0 = ta * TILE, c0 = tc * TILE;
-        Pair<T> v[8], old[HAS_BETA ? 8 : 1];
+        Pair<T> v[NI], old[HAS_BETA ? NI : 1];
         if constexpr (HAS_BETA) { // the old C values of this thread's phase-2 pairs are fetched together with the A tile
             const int64_t ic = c0 + 2 * lx;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int64_t ia = a0 + ly + 8 * i;
+            for (int i = 0; i < NI; i++) {
+                const int64_t ia = a0 + ly + ROWS * i;
                 if (ia < a.ea && ic < a.ec) old[i] = *reinterpret_cast<const Pair<T> *>(C + offC + ia * a.sc_a + ic);
             }
         }
         {
             const int64_t ia = a0 + 2 * lx;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int64_t ic = c0 + ly + 8 * i;
+            for (int i = 0; i < NI; i++) {
+                const int64_t ic = c0 + ly + ROWS * i;
                 if (ia < a.ea && ic < a.ec) v[i] = *reinterpret_cast<const Pair<T> *>(A + offA + ia + ic * a.sa_c);
             }
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int icl = ly + 8 * i, ial = 2 * lx;
+            for (int i = 0; i < NI; i++) {
+                const int icl = ly + ROWS * i, ial = 2 * lx;
                 tile[ial * TILE + (icl ^ sw(ial))] = v[i].x;
                 tile[(ial + 1) * TILE + (icl ^ sw(ial + 1))] = v[i].y;
             }
@@ -139,8 +140,8 @@ template <typename T, bool HAS_BETA> __global__ void __launch_bounds__(256, HAS_
         {
             const int64_t ic = c0 + 2 * lx;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int     ial = ly + 8 * i;
+            for (int i = 0; i < NI; i++) {
+                const int     ial = ly + ROWS * i;
                 const int64_t ia = a0 + ial;
                 if (ia < a.ea && ic < a.ec) {
                     Pair<T>  w = *reinterpret_cast<const Pair<T> *>(&tile[ial * TILE + ((2 * lx) ^ sw(ial))]);
@@ -379,10 +380,23 @@ int permute_impl(void *stream, int rank, const int64_t *dimsA, const int64_t *st
             if (vec_ok) {
                 pa.tiles_a = (pa.ea + 63) / 64;
                 pa.tiles_c = (pa.ec + 63) / 64;
+                // how full are 64-tiles / 32-tiles? (96 -> 56 % vs 100 %, 160 -> 69 % vs 100 %)
+                const int64_t ta32 = (pa.ea + 31) / 32, tc32 = (pa.ec + 31) / 32;
+                const double  fill64 = double(pa.ea) * double(pa.ec) / (double(pa.tiles_a * 64) * double(pa.tiles_c * 64));
+                const double  fill32 = double(pa.ea) * double(pa.ec) / (double(ta32 * 32) * double(tc32 * 32));
+                // measured (n = 96, 160): with beta the old-C prefetch doubles the loads in flight and 32-tiles reach 99 % of the copy
+                // rate; without it they only pay off when 64-tiles are less than 60 % full
+                const bool    small = is_zero(beta) ? (fill32 > fill64 + 0.1 && fill64 < 0.6) : fill32 >= fill64;
+                if (small) { pa.tiles_a = ta32; pa.tiles_c = tc32; }
                 int64_t ntiles = pa.tiles_a * pa.tiles_c * pa.rest.tot;
                 int     grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, 0x3fffffffLL)); // one tile per CTA: the hardware scheduler balances the tail
-                if (!is_zero(beta)) permute_tile_vec<T, true><<<grid, 256, 0, s>>>(pa);
-                else permute_tile_vec<T, false><<<grid, 256, 0, s>>>(pa);
+                if (small) {
+                    if (!is_zero(beta)) permute_tile_vec<T, true, 32><<<grid, 256, 0, s>>>(pa);
+                    else permute_tile_vec<T, false, 32><<<grid, 256, 0, s>>>(pa);
+                } else {
+                    if (!is_zero(beta)) permute_tile_vec<T, true, 64><<<grid, 256, 0, s>>>(pa);
+                    else permute_tile_vec<T, false, 64><<<grid, 256, 0, s>>>(pa);
+                }
                 EB_POST_LAUNCH("permute_tile_vec");
                 return EB200_OK;
             }
