@@ -158,6 +158,76 @@ template <typename T, bool HAS_BETA, int TILE> __global__ void __launch_bounds__
     }
 }
 
+// beta == 0 and extents that fill 64-tiles badly (96, 160 ...): U consecutive 32 x 32 tiles per CTA. All U*2 loads of a thread are
+// issued before the first shared-memory store, so a CTA keeps as many bytes in flight as the 64-tile kernel while every tile is full.
+template <typename T, int U> __global__ void __launch_bounds__(256, 3) permute_tile32_multi(const __grid_constant__ PermArgs a) {
+    constexpr int TILE = 32, LX = 16, ROWS = 16, NI = 2;
+    __shared__ __align__(16) T tile[U][TILE * TILE];
+    const T      *A = reinterpret_cast<const T *>(a.A);
+    T            *C = reinterpret_cast<T *>(a.C);
+    const T       alpha = make_scalar<T>(a.alpha[0], a.alpha[1]);
+    const bool    plain = is_one(alpha);
+    const int     tid = threadIdx.x, lx = tid % LX, ly = tid / LX;
+    const int64_t per_rest = a.tiles_a * a.tiles_c;
+    const int64_t ntiles = per_rest * a.rest.tot;
+    auto sw = [](int ia) { return ((ia >> 1) & 7) << 1; };
+
+    const int64_t t0 = (int64_t)blockIdx.x * U;
+    int64_t       offA[U], offC[U], a0[U], c0[U];
+    Pair<T>       v[U][NI];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int64_t t = t0 + u;
+        a0[u] = c0[u] = a.ea; // out of range => nothing is loaded or stored
+        offA[u] = offC[u] = 0;
+        if (t >= ntiles) continue;
+        int64_t rest, ta, tc;
+        if (ntiles <= 0x7fffffffLL) {
+            uint32_t tt = (uint32_t)t, pr = (uint32_t)per_rest, r_ = tt / pr, in = tt - r_ * pr;
+            uint32_t c_ = in / (uint32_t)a.tiles_a;
+            rest = r_; tc = c_; ta = in - c_ * (uint32_t)a.tiles_a;
+        } else {
+            rest = t / per_rest;
+            int64_t in = t - rest * per_rest;
+            tc = in / a.tiles_a; ta = in - tc * a.tiles_a;
+        }
+        grp_offset2(a.rest, rest, ROLE_A, ROLE_C, offA[u], offC[u]);
+        a0[u] = ta * TILE; c0[u] = tc * TILE;
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int64_t ia = a0[u] + 2 * lx;
+#pragma unroll
+        for (int i = 0; i < NI; i++) {
+            const int64_t ic = c0[u] + ly + ROWS * i;
+            if (ia < a.ea && ic < a.ec) v[u][i] = *reinterpret_cast<const Pair<T> *>(A + offA[u] + ia + ic * a.sa_c);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int i = 0; i < NI; i++) {
+            const int icl = ly + ROWS * i, ial = 2 * lx;
+            tile[u][ial * TILE + (icl ^ sw(ial))] = v[u][i].x;
+            tile[u][(ial + 1) * TILE + (icl ^ sw(ial + 1))] = v[u][i].y;
+        }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const int64_t ic = c0[u] + 2 * lx;
+#pragma unroll
+        for (int i = 0; i < NI; i++) {
+            const int     ial = ly + ROWS * i;
+            const int64_t ia = a0[u] + ial;
+            if (ia < a.ea && ic < a.ec) {
+                Pair<T> w = *reinterpret_cast<const Pair<T> *>(&tile[u][ial * TILE + ((2 * lx) ^ sw(ial))]);
+                if (!plain) { w.x = mul_(alpha, w.x); w.y = mul_(alpha, w.y); }
+                *reinterpret_cast<Pair<T> *>(C + offC[u] + ia * a.sc_a + ic) = w;
+            }
+        }
+    }
+}
+
 // Row-type permutations (the same axis is fastest in A and in C) with at least one more axis: a CTA copies a 64 x 64 patch of the
 // plane (fastest axis, one other axis). Every thread issues 8 independent 2-element loads, then 8 stores; the only index decode
 // is one per CTA for the remaining axes. No shared memory: nothing is transposed inside a row.
@@ -386,13 +456,15 @@ int permute_impl(void *stream, int rank, const int64_t *dimsA, const int64_t *st
                 const double  fill32 = double(pa.ea) * double(pa.ec) / (double(ta32 * 32) * double(tc32 * 32));
                 // measured (n = 96, 160): with beta the old-C prefetch doubles the loads in flight and 32-tiles reach 99 % of the copy
                 // rate; without it they only pay off when 64-tiles are less than 60 % full
-                const bool    small = is_zero(beta) ? (fill32 > fill64 + 0.1 && fill64 < 0.6) : fill32 >= fill64;
+                const bool    small = is_zero(beta) ? (fill32 > fill64 + 0.1 && fill64 < 0.8) : fill32 >= fill64;
                 if (small) { pa.tiles_a = ta32; pa.tiles_c = tc32; }
                 int64_t ntiles = pa.tiles_a * pa.tiles_c * pa.rest.tot;
                 int     grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, 0x3fffffffLL)); // one tile per CTA: the hardware scheduler balances the tail
-                if (small) {
-                    if (!is_zero(beta)) permute_tile_vec<T, true, 32><<<grid, 256, 0, s>>>(pa);
-                    else permute_tile_vec<T, false, 32><<<grid, 256, 0, s>>>(pa);
+                if (small && is_zero(beta)) {
+                    constexpr int U = 4;
+                    permute_tile32_multi<T, U><<<(unsigned)std::min<int64_t>((ntiles + U - 1) / U, 0x3fffffffLL), 256, 0, s>>>(pa);
+                } else if (small) {
+                    permute_tile_vec<T, true, 32><<<grid, 256, 0, s>>>(pa);
                 } else {
                     if (!is_zero(beta)) permute_tile_vec<T, true, 64><<<grid, 256, 0, s>>>(pa);
                     else permute_tile_vec<T, false, 64><<<grid, 256, 0, s>>>(pa);
