@@ -208,7 +208,19 @@ def run_ours(args):
     torch.cuda.set_device(local)
     ops.init(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # stdout carries exactly one JSON line: while the communicator comes up, NCCL's banner (NCCL_DEBUG=VERSION prints
+        # "NCCL version ..." with printf) is sent to stderr by pointing fd 1 at fd 2
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     def barrier():
         if world > 1:
