@@ -343,7 +343,7 @@ template <typename T> int run_reduce(cudaStream_t s, const Plan &p, eb200_contra
 
     const bool    row = (p.family != EB200_KF_COLREDUCE);
     const int64_t R = p.rows.tot, K = p.k.tot;
-    const int64_t rows_per_block = row ? 4 : 256 * 2;
+    const int64_t rows_per_block = row ? reduce_rows_per_block(p.n.tot, p.k.tot) : 256 * 2;
     const int64_t row_blocks = (R + rows_per_block - 1) / rows_per_block;
     if (row_blocks > 0x7fffffffLL) return fail(EB200_ERR_UNSUPPORTED, "contract: too many rows for the reduction grid");
     int splits = 1;

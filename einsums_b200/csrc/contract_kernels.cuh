@@ -634,7 +634,7 @@ __global__ void __launch_bounds__(256) row_reduce(const __grid_constant__ Reduce
 // time and reuse each B value RB times. Units are split over blockIdx.y; partial sums are combined
 // in a fixed order (deterministic).
 template <typename T, int NN, int RB, int VEC>
-__global__ void __launch_bounds__(256, (NN * RB * sizeof(T) <= 64 ? 3 : 1)) row_reduce_seg(const __grid_constant__ ReduceArgs a) {
+__global__ void __launch_bounds__(256, (RB >= 8 ? 2 : (NN * RB * sizeof(T) <= 64 ? 3 : 1))) row_reduce_seg(const __grid_constant__ ReduceArgs a) {
     constexpr int NT = 256, NW = NT / 32;
     __shared__ T  red[NW][RB * NN];
     const int     tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

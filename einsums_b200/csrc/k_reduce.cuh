@@ -1,6 +1,7 @@
 // k_reduce.cuh — launch dispatch of the streaming reductions, shared by the real and complex translation units.
 #pragma once
 #include "launch_api.cuh"
+#include <type_traits>
 namespace eb200 {
 namespace {
 // 0: flat kernel; 1: segmented, scalar loads; 2: segmented, 16-byte pairs
@@ -32,12 +33,22 @@ template <typename T, int NN> int launch_reduce_nn(cudaStream_t s, bool row, Red
                 fastdiv_init(ppr, a.ppr_mul, a.ppr_shift);
             }
         }
-        if (mode == 2) {
-            if constexpr (sizeof(T) <= 8) row_reduce_seg<T, NN, 4, 2><<<grid, 256, 0, s>>>(a);
-        } else if (mode == 1) {
-            row_reduce_seg<T, NN, 4, 1><<<grid, 256, 0, s>>>(a);
+        auto go = [&](auto rb_tag) {
+            constexpr int RB = decltype(rb_tag)::value;
+            if (mode == 2) {
+                if constexpr (sizeof(T) <= 8) row_reduce_seg<T, NN, RB, 2><<<grid, 256, 0, s>>>(a);
+            } else if (mode == 1) {
+                row_reduce_seg<T, NN, RB, 1><<<grid, 256, 0, s>>>(a);
+            } else {
+                row_reduce<T, NN, RB><<<grid, 256, 0, s>>>(a);
+            }
+        };
+        // must agree with run_reduce's grid (contract.cu): both call reduce_rows_per_block
+        if constexpr (NN == 1) {
+            if (reduce_rows_per_block(a.n.tot, a.k.tot) == 8) go(std::integral_constant<int, 8>{});
+            else go(std::integral_constant<int, 4>{});
         } else {
-            row_reduce<T, NN, 4><<<grid, 256, 0, s>>>(a);
+            go(std::integral_constant<int, 4>{});
         }
         EB_POST_LAUNCH("row_reduce");
     } else {
