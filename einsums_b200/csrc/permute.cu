@@ -456,7 +456,7 @@ int permute_impl(void *stream, int rank, const int64_t *dimsA, const int64_t *st
                 const double  fill32 = double(pa.ea) * double(pa.ec) / (double(ta32 * 32) * double(tc32 * 32));
                 // measured (n = 96, 160): with beta the old-C prefetch doubles the loads in flight and 32-tiles reach 99 % of the copy
                 // rate; without it they only pay off when 64-tiles are less than 60 % full
-                const bool    small = is_zero(beta) ? (fill32 > fill64 + 0.1 && fill64 < 0.8) : fill32 >= fill64;
+                const bool    small = is_zero(beta) ? (fill32 > fill64 + 0.1 && fill64 < 0.6) : fill32 >= fill64;
                 if (small) { pa.tiles_a = ta32; pa.tiles_c = tc32; }
                 int64_t ntiles = pa.tiles_a * pa.tiles_c * pa.rest.tot;
                 int     grid = (int)std::max<int64_t>(1, std::min<int64_t>(ntiles, 0x3fffffffLL)); // one tile per CTA: the hardware scheduler balances the tail
