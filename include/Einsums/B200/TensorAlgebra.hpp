@@ -11,6 +11,7 @@
 // which fuses the index permutation into its loads (no transposed copies, no atomics).
 #pragma once
 #include <Einsums/B200/Analysis.hpp>
+#include <Einsums/B200/IndexUtilities.hpp>
 #include <Einsums/B200/Index.hpp>
 #include <Einsums/B200/LinearAlgebra.hpp>
 

@@ -3,6 +3,7 @@
 // extracted list with file:line; the two are kept in sync by tests/test_cpp_shim.py).
 #include <Einsums/B200/Analysis.hpp>
 #include <Einsums/B200/Index.hpp>
+#include <Einsums/B200/IndexUtilities.hpp>
 
 #include <cstdio>
 
@@ -68,7 +69,43 @@ static_assert(choose<true, false>(Indices{i, j}, Indices{k, i}, Indices{k, j}) =
 static_assert(choose<false, false, false>(Indices{i, j}, Indices{i, k}, Indices{k, j}) == GENERIC);
 static_assert(choose(Indices{i}, Indices{i, i}, Indices{i}) == GENERIC);
 
+// index utilities (TensorBase/IndexUtilities.hpp): strides <-> running index, index tables, extents resolved C -> A -> B
+namespace index_utils_checks {
+constexpr bool strides_ok() {
+    std::array<int64_t, 3> d{4, 5, 6}, s{}, sc{};
+    size_t n = einsums::dims_to_strides(d, s), nc = einsums::dims_to_strides(d, sc, false);
+    std::array<int64_t, 3> ix{};
+    einsums::sentinel_to_indices(size_t(2 * 30 + 3 * 6 + 4), s, ix);
+    bool ok = n == 120 && nc == 120 && s[0] == 30 && s[1] == 6 && s[2] == 1 && sc[0] == 1 && sc[1] == 4 && sc[2] == 20;
+    ok = ok && ix[0] == 2 && ix[1] == 3 && ix[2] == 4 && einsums::indices_to_sentinel(s, ix) == 82;
+    einsums::sentinel_to_indices(size_t(2 + 3 * 4 + 4 * 20), sc, ix);
+    return ok && ix[0] == 2 && ix[1] == 3 && ix[2] == 4;
+}
+static_assert(strides_ok());
+constexpr bool table_ok() {
+    using namespace einsums::index;
+    std::array<int, 3> t{};
+    einsums::compile_index_table(std::tuple{i, j, k, l}, std::tuple{k, i, l}, t);
+    return t[0] == 2 && t[1] == 0 && t[2] == 3;
+}
+static_assert(table_ok());
+struct FakeTensor {
+    std::array<int64_t, 2> d;
+    int64_t dim(std::ptrdiff_t a) const { return d[size_t(a)]; }
+};
+inline bool ranges_ok() {
+    using namespace einsums::index;
+    FakeTensor C{{3, 4}}, A{{3, 7}}, B{{7, 4}};
+    auto r = einsums::get_dim_ranges_for_many(C, std::tuple{i, j}, A, std::tuple{i, k}, B, std::tuple{k, j}, std::tuple{i, j, k});
+    return r[0] == 3 && r[1] == 4 && r[2] == 7;
+}
+} // namespace index_utils_checks
+
 int main() {
+    if (!index_utils_checks::ranges_ok()) {
+        std::printf("index utilities: get_dim_ranges_for_many FAILED\n");
+        return 1;
+    }
     // print the decisions so that the Python side can diff them against tests/golden/algorithm_choice.json
     const char *names[] = {"GENERIC", "DOT", "DIRECT", "GER", "GEMV", "GEMM", "INDETERMINATE"};
 #define SHOW(C_, A_, B_) std::printf("%s <- %s , %s : %s\n", #C_, #A_, #B_, names[choose(C_, A_, B_)])
