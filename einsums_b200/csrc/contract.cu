@@ -343,6 +343,26 @@ template <typename T> int run_reduce(cudaStream_t s, const Plan &p, eb200_contra
 
     const bool    row = (p.family != EB200_KF_COLREDUCE);
     const int64_t R = p.rows.tot, K = p.k.tot;
+    // whole-tensor inner product of two unit-stride operands: dedicated streaming kernel (8 pairs per thread in flight)
+    if (row && R == 1 && p.n.tot == 1 && p.k.n == 1 && p.k.s[ROLE_A][0] == 1 && p.k.s[ROLE_B][0] == 1 && K >= 65536 && d.split_k <= 0) {
+        const int splits = (int)std::min<int64_t>((int64_t)sm_count() * 8, K / 16384);
+        a.splits = splits;
+        d.split_k = splits;
+        void *ws = nullptr;
+        int   rc = ws_alloc(&ws, (size_t)splits * sizeof(T), s);
+        if (rc) return rc;
+        a.ws = ws;
+        rc = k_launch_dot(Scalar<T>::dtype, s, a, splits);
+        if (rc) return rc;
+        d.launches++;
+        Grp none;
+        memset(&none, 0, sizeof(none));
+        none.tot = 1;
+        rc = launch_finalize<T>(s, none, p.rows, p.n, ws, d.C.data, d.alpha, beta_eff, splits, d);
+        if (rc) return rc;
+        EB_CUDA(cudaFreeAsync(ws, s));
+        return EB200_OK;
+    }
     const int64_t rows_per_block = row ? reduce_rows_per_block(p.n.tot, p.k.tot) : 256 * 2;
     const int64_t row_blocks = (R + rows_per_block - 1) / rows_per_block;
     if (row_blocks > 0x7fffffffLL) return fail(EB200_ERR_UNSUPPORTED, "contract: too many rows for the reduction grid");

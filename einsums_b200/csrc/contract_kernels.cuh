@@ -794,6 +794,42 @@ __global__ void __launch_bounds__(256, (RB >= 8 ? 2 : (NN * RB * sizeof(T) <= 64
     }
 }
 
+// dot_contig: the whole-tensor inner product of two unit-stride operands (dot / true_dot / energy-style contractions to a scalar).
+// One CTA per K segment, 8 independent element pairs per thread in flight, fixed-order reduction; partials go to a.ws[split].
+template <typename T> __global__ void __launch_bounds__(256) dot_contig(const __grid_constant__ ReduceArgs a) {
+    constexpr int NT = 256, NW = NT / 32, UNR = 8;
+    __shared__ T  red[NW];
+    const T      *A = reinterpret_cast<const T *>(a.A);
+    const T      *B = reinterpret_cast<const T *>(a.B);
+    const int64_t K = a.k.tot;
+    const int64_t k0 = K * blockIdx.x / a.splits, k1 = K * ((int64_t)blockIdx.x + 1) / a.splits;
+    const bool    ca = a.conj_a != 0, cb = a.conj_b != 0;
+    T             acc[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; u++) acc[u] = zero_of<T>();
+    int64_t k = k0 + threadIdx.x;
+    for (; k + (int64_t)(UNR - 1) * NT < k1; k += (int64_t)UNR * NT) {
+        T x[UNR], y[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; u++) { x[u] = A[k + (int64_t)u * NT]; y[u] = B[k + (int64_t)u * NT]; }
+#pragma unroll
+        for (int u = 0; u < UNR; u++) acc[u] = fma_(conj_if(x[u], ca), conj_if(y[u], cb), acc[u]);
+    }
+    for (; k < k1; k += NT) acc[0] = fma_(conj_if(A[k], ca), conj_if(B[k], cb), acc[0]);
+    T sum = acc[0];
+#pragma unroll
+    for (int u = 1; u < UNR; u++) sum = add_(sum, acc[u]);
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T t = red[0];
+#pragma unroll
+        for (int w = 1; w < NW; w++) t = add_(t, red[w]);
+        reinterpret_cast<T *>(a.ws)[blockIdx.x] = t;
+    }
+}
+
 // col_reduce: threads run along rows (contiguous in A); each thread owns RT rows and walks a K segment.
 template <typename T, int NN, int RT>
 __global__ void __launch_bounds__(256) col_reduce(const __grid_constant__ ReduceArgs a) {
@@ -913,6 +949,48 @@ template <typename T, bool CONJ_A, bool CONJ_B> __global__ void __launch_bounds_
         grp_offset3(a.t, x, oa, ob, oc);
         T v = mul_(maybe_conj<CONJ_A>(A[oa]), maybe_conj<CONJ_B>(B[ob]));
         C[oc] = axpby_(alpha, v, beta, has_beta ? C[oc] : zero_of<T>(), has_beta);
+    }
+}
+
+// elementwise_pairs: the same operation when the innermost target index is unit-stride in C with an even extent and every other C
+// stride is even (outer products, direct products on contiguous tensors): a thread owns two neighbouring elements (one 16-byte C
+// access for 8-byte types), decodes the index once per pair and keeps two pairs in flight. A and B inner strides may be 0 or anything.
+template <typename T, bool CONJ_A, bool CONJ_B> __global__ void __launch_bounds__(256) elementwise_pairs(const __grid_constant__ ElemArgs a) {
+    struct alignas(2 * sizeof(T)) P2 { T x, y; };
+    const T      *A = reinterpret_cast<const T *>(a.A);
+    const T      *B = reinterpret_cast<const T *>(a.B);
+    T            *C = reinterpret_cast<T *>(a.C);
+    const T       alpha = make_scalar<T>(a.alpha[0], a.alpha[1]), beta = make_scalar<T>(a.beta[0], a.beta[1]);
+    const bool    has_beta = !is_zero(beta);
+    const int64_t pairs = a.t.tot / 2, stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t sa0 = a.t.s[0][0], sb0 = a.t.s[1][0];
+    constexpr int UNR = 2;
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < pairs; x += stride * UNR) {
+        int64_t oa[UNR], ob[UNR], oc[UNR];
+        T       a0[UNR], a1[UNR], b0[UNR], b1[UNR];
+        P2      c[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            const int64_t xx = x + u * stride;
+            oc[u] = -1;
+            if (xx < pairs) grp_offset3(a.t, 2 * xx, oa[u], ob[u], oc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; u++)
+            if (oc[u] >= 0) {
+                a0[u] = A[oa[u]]; a1[u] = A[oa[u] + sa0];
+                b0[u] = B[ob[u]]; b1[u] = B[ob[u] + sb0];
+                if (has_beta) c[u] = *reinterpret_cast<const P2 *>(C + oc[u]);
+                else c[u].x = c[u].y = zero_of<T>();
+            }
+#pragma unroll
+        for (int u = 0; u < UNR; u++)
+            if (oc[u] >= 0) {
+                P2 r;
+                r.x = axpby_(alpha, mul_(maybe_conj<CONJ_A>(a0[u]), maybe_conj<CONJ_B>(b0[u])), beta, c[u].x, has_beta);
+                r.y = axpby_(alpha, mul_(maybe_conj<CONJ_A>(a1[u]), maybe_conj<CONJ_B>(b1[u])), beta, c[u].y, has_beta);
+                *reinterpret_cast<P2 *>(C + oc[u]) = r;
+            }
     }
 }
 

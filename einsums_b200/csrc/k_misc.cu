@@ -3,6 +3,15 @@
 namespace eb200 {
 namespace {
 template <typename T, bool CA, bool CB> int launch_elem(cudaStream_t s, ElemArgs &a, int grid) {
+    // pair path: innermost target index unit-stride in C, even extent, every other C stride even, C base aligned to two elements
+    bool pairs = sizeof(T) <= 8 && a.t.n >= 1 && a.t.s[2][0] == 1 && (a.t.ext[0] % 2) == 0 && ((uintptr_t)a.C % (2 * sizeof(T))) == 0;
+    for (int i = 1; i < a.t.n && pairs; i++)
+        if (a.t.s[2][i] % 2) pairs = false;
+    if (pairs) {
+        elementwise_pairs<T, CA, CB><<<grid, 256, 0, s>>>(a);
+        EB_POST_LAUNCH("elementwise_pairs");
+        return EB200_OK;
+    }
     elementwise<T, CA, CB><<<grid, 256, 0, s>>>(a);
     EB_POST_LAUNCH("elementwise");
     return EB200_OK;
@@ -71,6 +80,7 @@ int k_launch_elem(int dtype, cudaStream_t s, ElemArgs &a, int ca, int cb, int gr
     return EB200_OK;
 int k_launch_scale(int dtype, cudaStream_t s, ScaleArgs &a, int grid) { EB_BY_DTYPE(scale_tensor, "scale_tensor") }
 int k_launch_finalize(int dtype, cudaStream_t s, FinalizeArgs &a, int grid) { EB_BY_DTYPE(splitk_finalize, "splitk_finalize") }
+int k_launch_dot(int dtype, cudaStream_t s, ReduceArgs &a, int grid) { EB_BY_DTYPE(dot_contig, "dot_contig") }
 #undef EB_BY_DTYPE
 int k_launch_convert(cudaStream_t s, int src_dtype, int dst_dtype, const ConvArgs &a, int grid) { return launch_convert_any(s, src_dtype, dst_dtype, a, grid); }
 } // namespace eb200

@@ -23,6 +23,7 @@ int k_launch_tf32x3(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &t
 int k_launch_reduce(int dtype, cudaStream_t s, bool row, ReduceArgs &a, dim3 grid);              // k_reduce_{real,cplx}.cu
 int k_launch_reduce_real(int dtype, cudaStream_t s, bool row, ReduceArgs &a, dim3 grid);
 int k_launch_reduce_cplx(int dtype, cudaStream_t s, bool row, ReduceArgs &a, dim3 grid);
+int k_launch_dot(int dtype, cudaStream_t s, ReduceArgs &a, int grid);                          // k_misc.cu
 int k_launch_elem(int dtype, cudaStream_t s, ElemArgs &a, int conj_a, int conj_b, int grid);     // k_misc.cu
 int k_launch_scale(int dtype, cudaStream_t s, ScaleArgs &a, int grid);
 int k_launch_finalize(int dtype, cudaStream_t s, FinalizeArgs &a, int grid);
