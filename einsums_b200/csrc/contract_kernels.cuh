@@ -875,7 +875,32 @@ __global__ void __launch_bounds__(256) col_reduce(const __grid_constant__ Reduce
             }
         }
     }
-    for (int64_t k = k_begin; k < k_end; k++) {
+    int64_t k = k_begin;
+    if (a.k.n == 1) { // a single contracted index (plain gemv): four k positions per iteration, all loads issued before the FMAs
+        constexpr int UK = 4;
+        const int64_t sA = a.k.s[ROLE_A][0], sB = a.k.s[ROLE_B][0];
+        for (; k + UK <= k_end; k += UK) {
+            T av[UK][RT], bv[UK][RT][NN];
+#pragma unroll
+            for (int u = 0; u < UK; u++)
+#pragma unroll
+                for (int j = 0; j < RT; j++) {
+                    av[u][j] = (rowA[j] != OFF_INVALID) ? A[rowA[j] + offA + u * sA] : zero_of<T>();
+#pragma unroll
+                    for (int c = 0; c < NN; c++) bv[u][j][c] = (c < ncols) ? B[rowB[j] + offB + u * sB + colB[c]] : zero_of<T>();
+                }
+#pragma unroll
+            for (int u = 0; u < UK; u++)
+#pragma unroll
+                for (int j = 0; j < RT; j++)
+#pragma unroll
+                    for (int c = 0; c < NN; c++) acc[j][c] = fma_(conj_if(av[u][j], a.conj_a != 0), conj_if(bv[u][j][c], a.conj_b != 0), acc[j][c]);
+            offA += UK * sA;
+            offB += UK * sB;
+        }
+        idx[0] = k; // k.n == 1: the running index is the position itself (the generic loop below finishes the tail)
+    }
+    for (; k < k_end; k++) {
         T av[RT];
 #pragma unroll
         for (int j = 0; j < RT; j++) av[j] = (rowA[j] != OFF_INVALID) ? conj_if(A[rowA[j] + offA], a.conj_a != 0) : zero_of<T>();
