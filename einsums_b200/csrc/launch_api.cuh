@@ -7,8 +7,8 @@
 
 namespace eb200 {
 /// rows a CTA of the row-direction reductions owns. One output column and long rows: 8 rows = 8 independent 16-byte loads per
-/// lane in flight (Fock J/K at n=300: 6.5 -> 7.1 TB/s); short rows keep 4 (more CTAs per SM hide the per-CTA prologue better).
-inline int reduce_rows_per_block(int64_t nn, int64_t k_tot) { return (nn <= 1 && k_tot >= 32768) ? 8 : 4; }
+/// lane in flight (Fock J/K at n=300: 6.5 -> 7.1 TB/s); short rows (K < 16384) keep 4 (more CTAs per SM hide the per-CTA prologue better).
+inline int reduce_rows_per_block(int64_t nn, int64_t k_tot) { return (nn <= 1 && k_tot >= 16384) ? 8 : 4; }
 struct ConvArgs {
     Grp         g; // ROLE_A = source strides, ROLE_C = destination strides
     const void *src;
