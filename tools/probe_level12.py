@@ -22,3 +22,6 @@ t = timeit(lambda: ops.dot(N, u, 1, v, 1)); print(json.dumps({"op": "ddot 2^28 (
 t = timeit(lambda: ops.axpy(N, 0.5, u, 1, v, 1)); print(json.dumps({"op": "daxpy 2^28", "ms": round(t * 1e3, 3), "gbs": round(24.0 * N / t / 1e9, 1)}), flush=True)
 m = 16384
 t = timeit(lambda: ops.ger(m, m, 0.5, x, 1, x, 1, A, m)); print(json.dumps({"op": f"dger {m}x{m}", "ms": round(t * 1e3, 3), "gbs": round(16.0 * m * m / t / 1e9, 1)}), flush=True)
+Bm = torch.rand(m, m, dtype=torch.float64, device="cuda"); Cm = torch.zeros(m, m, dtype=torch.float64, device="cuda")
+t = timeit(lambda: ops.contract("ij", Cm, "ij", A, "ij", Bm, 1.0, 0.0)); print(json.dumps({"op": f"direct product {m}x{m} (beta=0)", "ms": round(t * 1e3, 3), "gbs": round(24.0 * m * m / t / 1e9, 1)}), flush=True)
+t = timeit(lambda: ops.contract("ij", Cm, "ij", A, "ij", Bm, 0.5, 2.0)); print(json.dumps({"op": f"direct product {m}x{m} (beta=2)", "ms": round(t * 1e3, 3), "gbs": round(32.0 * m * m / t / 1e9, 1)}), flush=True)
