@@ -979,7 +979,7 @@ template <typename T, bool CONJ_A, bool CONJ_B> __global__ void __launch_bounds_
 
 // elementwise_pairs: the same operation when the innermost target index is unit-stride in C with an even extent and every other C
 // stride is even (outer products, direct products on contiguous tensors): a thread owns two neighbouring elements (one 16-byte C
-// access for 8-byte types), decodes the index once per pair and keeps two pairs in flight. A and B inner strides may be 0 or anything.
+// access for 8-byte types), decodes the index once per pair and keeps four pairs in flight. A and B inner strides may be 0 or anything.
 template <typename T, bool CONJ_A, bool CONJ_B> __global__ void __launch_bounds__(256) elementwise_pairs(const __grid_constant__ ElemArgs a) {
     struct alignas(2 * sizeof(T)) P2 { T x, y; };
     const T      *A = reinterpret_cast<const T *>(a.A);
@@ -989,7 +989,7 @@ template <typename T, bool CONJ_A, bool CONJ_B> __global__ void __launch_bounds_
     const bool    has_beta = !is_zero(beta);
     const int64_t pairs = a.t.tot / 2, stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t sa0 = a.t.s[0][0], sb0 = a.t.s[1][0];
-    constexpr int UNR = 2;
+    constexpr int UNR = 4;
     for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < pairs; x += stride * UNR) {
         int64_t oa[UNR], ob[UNR], oc[UNR];
         T       a0[UNR], a1[UNR], b0[UNR], b1[UNR];
