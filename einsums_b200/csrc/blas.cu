@@ -204,8 +204,9 @@ template <typename T> int dot_dev_impl(void *stream, bool conj_x, int64_t n, con
 template <typename T> int dot_host_impl(void *stream, bool conj_x, int64_t n, const T *x, int64_t incx, const T *y, int64_t incy, T *result_host) {
     if (!result_host) return fail(EB200_ERR_INVALID_ARGUMENT, "dot: result pointer is NULL");
     T  *tmp = nullptr;
-    EB_CUDA(cudaMallocAsync((void **)&tmp, sizeof(T), as_stream(stream)));
-    int rc = dot_dev_impl<T>(stream, conj_x, n, x, incx, y, incy, tmp);
+    int rc = scratch_alloc((void **)&tmp, sizeof(T), as_stream(stream));
+    if (rc) return rc;
+    rc = dot_dev_impl<T>(stream, conj_x, n, x, incx, y, incy, tmp);
     if (rc == EB200_OK) {
         cudaError_t e = cudaMemcpyAsync(result_host, tmp, sizeof(T), cudaMemcpyDeviceToHost, as_stream(stream));
         if (e == cudaSuccess) e = cudaStreamSynchronize(as_stream(stream));

@@ -38,6 +38,8 @@ int64_t     &launch_counter();
 
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 int                 sm_count();
+/// stream-ordered scratch from the library's private memory pool (runtime.cu); release with cudaFreeAsync on the same stream
+int scratch_alloc(void **p, size_t bytes, cudaStream_t s);
 
 // ---------------------------------------------------------------- scalar algebra
 // real types are float/double; complex are float2/double2 (interleaved re,im = the C ABI layout)

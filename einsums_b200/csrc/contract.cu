@@ -7,6 +7,7 @@
 #include "launch_api.cuh"
 
 #include <algorithm>
+#include <map>
 #include <mutex>
 #include <vector>
 #include <cstdlib>
@@ -25,23 +26,9 @@ template <typename K> int set_smem(K kernel, size_t bytes) {
     return EB200_OK;
 }
 
-// stream-ordered scratch for split partials: no synchronisation, freed after the finalize kernel
-int ws_alloc(void **p, size_t bytes, cudaStream_t s) {
-    // keep freed scratch in the pool across synchronisations (the default threshold of 0 hands it back to the
-    // driver at every sync, which costs ~1 ms per split-K call)
-    static thread_local int pool_dev = -1;
-    int                     dev = 0;
-    EB_CUDA(cudaGetDevice(&dev));
-    if (pool_dev != dev) {
-        cudaMemPool_t pool;
-        EB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-        uint64_t keep = UINT64_MAX;
-        EB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        pool_dev = dev;
-    }
-    EB_CUDA(cudaMallocAsync(p, bytes, s));
-    return EB200_OK;
-}
+// stream-ordered scratch for split partials: no synchronisation, freed after the finalize kernel (scratch_alloc, runtime.cu:
+// a PRIVATE memory pool with a bounded release threshold; the device's default pool is left alone)
+int ws_alloc(void **p, size_t bytes, cudaStream_t s) { return scratch_alloc(p, bytes, s); }
 
 template <typename T> int launch_scale(cudaStream_t s, const Grp &t, void *C, const double beta[2], eb200_contract_desc &d) {
     ScaleArgs a;
@@ -521,9 +508,14 @@ int contract_mixed(cudaStream_t s, eb200_contract_desc &d) {
         int64_t dense[EB200_MAX_RANK];
         Grp     g;
         if ((rc = axes_group(d, *os[i], dense, g, true))) break;
-        if (g.tot == 0) continue;
-        cudaError_t e = cudaMallocAsync(&tmp[i], (size_t)g.tot * dtype_size(W), s);
-        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMallocAsync(mixed)"); break; }
+        if (g.tot == 0) {
+            // an empty tensor has nothing to widen, but it must still take the promoted type: leaving its dtype alone sent the
+            // descriptor straight back into contract_mixed (endless recursion, stack overflow)
+            ts[i]->dtype = W;
+            for (int a = 0; a < os[i]->rank; a++) ts[i]->stride[a] = dense[a];
+            continue;
+        }
+        if ((rc = scratch_alloc(&tmp[i], (size_t)g.tot * dtype_size(W), s))) break;
         const bool need_values = (i != 0) || !(d.beta[0] == 0.0 && d.beta[1] == 0.0);
         if (need_values) {
             ConvArgs ca{g, os[i]->data, tmp[i]};
@@ -537,7 +529,8 @@ int contract_mixed(cudaStream_t s, eb200_contract_desc &d) {
     }
     if (rc == EB200_OK) {
         int l0 = d.launches;
-        rc = contract_dispatch(s, w);
+        if (w.A.dtype != w.C.dtype || w.B.dtype != w.C.dtype) rc = fail(EB200_ERR_UNSUPPORTED, "contract: mixed-type promotion did not converge");
+        else rc = contract_dispatch(s, w);
         d.kernel_used = w.kernel_used;
         d.split_k = w.split_k;
         d.launches = l0 + w.launches;
@@ -728,11 +721,59 @@ int eb200_contract_grouped(void *stream, int64_t n, eb200_contract_desc *descs, 
         EB_CUDA(cudaEventRecord(gs.fork, user));
         for (int a = 0; a < naux; a++) EB_CUDA(cudaStreamWaitEvent(gs.aux[a], gs.fork, 0));
     }
+    // Lane assignment by the byte range of C each (possibly folded) item touches: items whose ranges overlap share a lane
+    // and therefore stay ordered, also when a folded item covers C0..Cn and a later one accumulates into Ck (k > 0).
+    // Ranges are kept as disjoint intervals (lo -> hi, lane); an item overlapping intervals of different lanes forces a
+    // join + re-fork of all lanes first (rare).
+    struct Span { uintptr_t hi; int lane; };
+    std::map<uintptr_t, Span> spans;
+    auto c_range = [](const eb200_contract_desc &d, uintptr_t &lo, uintptr_t &hi) {
+        const int64_t es = (int64_t)dtype_size(d.C.dtype);
+        int64_t       mn = 0, mx = 0;
+        for (int a = 0; a < d.C.rank; a++) {
+            const int64_t e = d.extent[d.C.index[a]];
+            if (e <= 0) { lo = hi = (uintptr_t)d.C.data; return; }
+            const int64_t reach = (e - 1) * d.C.stride[a];
+            if (reach < 0) mn += reach; else mx += reach;
+        }
+        lo = (uintptr_t)((const char *)d.C.data + mn * es);
+        hi = (uintptr_t)((const char *)d.C.data + (mx + 1) * es);
+    };
     int rc = EB200_OK;
     for (size_t r = 0; r < items.size() && rc == EB200_OK; r++) {
         GroupItem &it = items[r];
-        // same output -> same stream (accumulations stay ordered); different outputs spread over the lanes
-        const int    lane = naux > 0 ? int((((uintptr_t)it.d.C.data) / 256u * 2654435761u >> 16) % (unsigned)(naux + 1)) : 0;
+        int        lane = 0;
+        if (naux > 0) {
+            uintptr_t lo, hi;
+            c_range(it.d, lo, hi);
+            lane = int(((lo / 256u) * 2654435761u >> 16) % (unsigned)(naux + 1));
+            if (hi > lo) {
+                auto first = spans.upper_bound(lo);
+                if (first != spans.begin() && std::prev(first)->second.hi > lo) --first;
+                auto last = first;
+                int  seen = -1;
+                bool conflict = false;
+                for (; last != spans.end() && last->first < hi; ++last) {
+                    if (seen >= 0 && last->second.lane != seen) conflict = true;
+                    seen = last->second.lane;
+                    lo = std::min(lo, last->first);
+                    hi = std::max(hi, last->second.hi);
+                }
+                if (conflict) { // order this item after everything enqueued so far, then carry on in parallel
+                    for (int a = 0; a < naux; a++) {
+                        cudaEventRecord(gs.join[a], gs.aux[a]);
+                        cudaStreamWaitEvent(user, gs.join[a], 0);
+                    }
+                    cudaEventRecord(gs.fork, user);
+                    for (int a = 0; a < naux; a++) cudaStreamWaitEvent(gs.aux[a], gs.fork, 0);
+                    spans.clear();
+                    first = last = spans.end();
+                    lane = 0;
+                } else if (seen >= 0) lane = seen;
+                spans.erase(first, last);
+                spans[lo] = Span{hi, lane};
+            }
+        }
         cudaStream_t s = lane == 0 ? user : gs.aux[lane - 1];
         rc = contract_dispatch(s, it.d);
         for (int64_t k = 0; k < it.count; k++) {

@@ -151,7 +151,7 @@ int eb200_contract_host(void *stream, const eb200_contract_desc *desc, size_t sl
     // ---- C on the host: slabs along its slowest axis -------------------------------------------------------------
     if (d.C.rank < 1) { // a scalar result: one element through a stream-ordered temporary
         void *host_c = d.C.data, *tmp = nullptr;
-        EB_CUDA(cudaMallocAsync(&tmp, 16, s_cmp));
+        if ((rc = scratch_alloc(&tmp, 16, s_cmp))) return rc;
         if (!beta_zero) EB_CUDA(cudaMemcpyAsync(tmp, host_c, esC, cudaMemcpyHostToDevice, s_cmp));
         d.C.data = tmp;
         rc = contract_dispatch(s_cmp, d);

@@ -3,6 +3,9 @@
 // libs/Einsums/Tensor/include/Einsums/Tensor/Backends/DeviceTensor.hpp:33-116 (reference paths).
 #include "common.cuh"
 
+#include <mutex>
+#include <unordered_map>
+
 namespace eb200 {
 
 ErrorState &err_state() {
@@ -48,6 +51,65 @@ int        sm_count() {
     }
     return g_sm_count[dev];
 }
+
+// ---------------------------------------------------------------- stream-ordered scratch
+// Split-K partials, mixed-type widened copies and device-side scalars come from a PRIVATE memory pool per device. The
+// device's default pool (shared with the embedding application, e.g. torch) is never touched. Freed scratch up to
+// `keep` bytes stays cached across synchronisations (a release threshold of 0 would hand it back at every sync, ~1 ms
+// per split-K call); anything above is returned to the driver at the next synchronisation point.
+namespace {
+struct ScratchPools {
+    std::mutex    mu;
+    cudaMemPool_t pool[64] = {};
+};
+ScratchPools &scratch_pools() {
+    static ScratchPools *p = new ScratchPools; // leaked on purpose: the context may be gone at static destruction
+    return *p;
+}
+} // namespace
+
+int scratch_alloc(void **p, size_t bytes, cudaStream_t s) {
+    int dev = 0;
+    EB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(EB200_ERR_UNSUPPORTED, "scratch_alloc: device index %d not supported", dev);
+    ScratchPools &sp = scratch_pools();
+    cudaMemPool_t pool;
+    {
+        std::lock_guard<std::mutex> lock(sp.mu);
+        if (!sp.pool[dev]) {
+            cudaMemPoolProps props;
+            memset(&props, 0, sizeof(props));
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            EB_CUDA(cudaMemPoolCreate(&sp.pool[dev], &props));
+            uint64_t keep = 256ull << 20;
+            EB_CUDA(cudaMemPoolSetAttribute(sp.pool[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+        }
+        pool = sp.pool[dev];
+    }
+    EB_CUDA(cudaMallocFromPoolAsync(p, bytes ? bytes : 1, pool, s));
+    return EB200_OK;
+}
+
+// ---------------------------------------------------------------- budgeted device allocator
+// Replaces gpu::GPUAllocator + Einsums_GPUMemory_vars (reference: libs/Einsums/GPUMemory/include/Einsums/GPUMemory/
+// GPUAllocator.hpp:157-191 allocate/deallocate, src/ModuleVars.cpp:43-63 try_allocate/deallocate, src/InitModule.cpp:39-55
+// --einsums:gpu-buffer-size): every eb200_malloc is charged against a byte budget and refused (no CUDA call) when it
+// would exceed it. Budget 0 = unlimited (B200-first default: 180 GB of HBM belong to the tensors). The size of each live
+// allocation is remembered so eb200_free needs no size argument.
+namespace {
+struct Budget {
+    std::mutex                         mu;
+    size_t                             budget = 0, in_use = 0, peak = 0;
+    std::unordered_map<void *, size_t> live;
+};
+Budget &budget_state() {
+    static Budget *b = new Budget;
+    return *b;
+}
+} // namespace
 
 } // namespace eb200
 
@@ -152,12 +214,52 @@ int eb200_malloc(void **ptr, size_t bytes) {
     if (!ptr) return fail(EB200_ERR_INVALID_ARGUMENT, "eb200_malloc: NULL");
     *ptr = nullptr;
     if (bytes == 0) return EB200_OK;
-    EB_CUDA(cudaMalloc(ptr, bytes));
+    Budget &b = budget_state();
+    {
+        std::lock_guard<std::mutex> lock(b.mu);
+        if (b.budget && (bytes > b.budget || b.in_use > b.budget - bytes))
+            return fail(EB200_ERR_OUT_OF_MEMORY, "Could not allocate enough memory on the GPU device. Requested %zu bytes (budget %zu, in use %zu).",
+                        bytes, b.budget, b.in_use);
+        b.in_use += bytes; // reserved before the CUDA call so that concurrent callers cannot overshoot the budget
+    }
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    std::lock_guard<std::mutex> lock(b.mu);
+    if (e != cudaSuccess) {
+        b.in_use -= bytes;
+        *ptr = nullptr;
+        return cuda_fail(e, "cudaMalloc");
+    }
+    b.live[*ptr] = bytes;
+    if (b.in_use > b.peak) b.peak = b.in_use;
     return EB200_OK;
 }
 int eb200_free(void *ptr) {
     if (!ptr) return EB200_OK;
+    Budget &b = budget_state();
+    {
+        std::lock_guard<std::mutex> lock(b.mu);
+        auto it = b.live.find(ptr);
+        if (it != b.live.end()) {
+            b.in_use = b.in_use < it->second ? 0 : b.in_use - it->second;
+            b.live.erase(it);
+        }
+    }
     EB_CUDA(cudaFree(ptr));
+    return EB200_OK;
+}
+int eb200_set_memory_budget(size_t bytes) {
+    Budget                     &b = budget_state();
+    std::lock_guard<std::mutex> lock(b.mu);
+    b.budget = bytes;
+    return EB200_OK;
+}
+int eb200_memory_stats(size_t *budget_bytes, size_t *in_use_bytes, size_t *peak_bytes, size_t *live_allocations) {
+    Budget                     &b = budget_state();
+    std::lock_guard<std::mutex> lock(b.mu);
+    if (budget_bytes) *budget_bytes = b.budget;
+    if (in_use_bytes) *in_use_bytes = b.in_use;
+    if (peak_bytes) *peak_bytes = b.peak;
+    if (live_allocations) *live_allocations = b.live.size();
     return EB200_OK;
 }
 int eb200_malloc_host(void **ptr, size_t bytes) {

@@ -59,16 +59,21 @@ def make_desc(c_idx, Ct, a_idx, At, b_idx, Bt, alpha=1.0, beta=0.0, conj_a=False
         raise ValueError("too many distinct indices")
     d = ContractDesc()
     d.n_unique = len(unique)
-    for u, lab in enumerate(unique):
-        ext = None
-        for pack, t in ((c_idx, Ct), (a_idx, At), (b_idx, Bt)):
-            if lab in pack:
-                ext = t.shape[list(pack).index(lab)]
-                break
-        d.extent[u] = int(ext)
-    for td, pack, t in ((d.C, c_idx, Ct), (d.A, a_idx, At), (d.B, b_idx, Bt)):
+    for name, pack, t in (("C", c_idx, Ct), ("A", a_idx, At), ("B", b_idx, Bt)):
         if len(pack) != t.dim():
             raise ValueError(f"index pack {pack} does not match tensor rank {t.dim()}")
+    # extents resolve C -> A -> B (get_dim_ranges_for_many); every other occurrence of the label, in any tensor and also
+    # repeated inside one tensor, must agree -- the C ABI carries no per-tensor shapes, so a mismatch would read or write
+    # out of bounds. Same error class as the shim's check_dims (reference: TA/Backends/Dispatch.hpp:125-127).
+    extent = {}
+    for name, pack, t in (("C", c_idx, Ct), ("A", a_idx, At), ("B", b_idx, Bt)):
+        for ax, lab in enumerate(pack):
+            n = int(t.shape[ax])
+            if extent.setdefault(lab, n) != n:
+                raise ValueError(f"dimension_error: index {lab!r} has extent {extent[lab]} but axis {ax} of {name} has {n}")
+    for u, lab in enumerate(unique):
+        d.extent[u] = extent[lab]
+    for td, pack, t in ((d.C, c_idx, Ct), (d.A, a_idx, At), (d.B, b_idx, Bt)):
         td.data = t.data_ptr()
         td.dtype = _DTYPES[t.dtype]
         td.rank = t.dim()

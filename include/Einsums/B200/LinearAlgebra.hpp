@@ -100,6 +100,8 @@ void gemv(char transA, T alpha, AType const &A, XType const &x, T beta, YType *y
     using V = typename AType::ValueType;
     char t = (char)std::tolower(transA);
     if (t != 'n' && t != 't' && t != 'c') throw std::invalid_argument("Invalid transpose parameter! Expected c, n, or t case insensitive.");
+    if (A.stride(1) != 1 && !(t == 'c' && IsComplexV<V>)) // the BLAS route takes A.stride(0) as lda (the conj route passes both strides)
+        throw tensor_compat_error("gemv: the device matrix must have unit stride along its last axis");
     std::int64_t m = A.dim(1), n = A.dim(0);
     char         blas_t = (t == 'n') ? 't' : (t == 't' ? 'n' : 'n');
     if (t == 'c' && IsComplexV<V>) {

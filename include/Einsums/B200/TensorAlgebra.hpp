@@ -160,14 +160,16 @@ bool do_matrix_product(Analysis const &z, CV beta, CType *C, CV alpha, AType con
     if (sA[1] != 1 || sB[1] != 1 || sC[1] != 1) return false; // reference Dispatch.hpp:818-821
 
     using AV = typename AType::ValueType;
-    constexpr bool cA = ConjA && IsComplexV<AV>, cB = ConjB && IsComplexV<AV>;
+    using BV = typename BType::ValueType;
+    constexpr bool cA = ConjA && IsComplexV<AV>, cB = ConjB && IsComplexV<BV>;
     // The reference's flag choice drops a conjugation on a non-transposed operand (it passes 'n'); we keep the result
     // mathematically right by sending exactly those cases through the contraction engine with its conj flags.
     if ((cA && ((!tC && !tA) || (tC && tA))) || (cB && ((!tC && !tB) || (tC && tB)))) {
         run_contract<ConjA, ConjB>(z, beta, C, alpha, A, B, C->gpu_data());
         return true;
     }
-    DeviceTensorView<AV, 2> vA(const_cast<AV *>(A.gpu_data()), dA, sA), vB(const_cast<AV *>(B.gpu_data()), dB, sB);
+    DeviceTensorView<AV, 2> vA(const_cast<AV *>(A.gpu_data()), dA, sA);
+    DeviceTensorView<BV, 2> vB(const_cast<BV *>(B.gpu_data()), dB, sB);
     DeviceTensorView<CV, 2> vC(C->gpu_data(), dC, sC);
     if (!tC) {
         char ta = tA ? (cA ? 'c' : 't') : 'n', tb = tB ? (cB ? 'c' : 't') : 'n';

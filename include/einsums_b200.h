@@ -114,6 +114,13 @@ int eb200_event_elapsed_ms(void *start, void *stop, float *ms);
 /* T/Backends/DeviceTensor.hpp:62-116 (ctor: hipMalloc) and :33-60 (dtor) */
 int eb200_malloc(void **ptr, size_t bytes);
 int eb200_free(void *ptr);
+/* Byte budget of eb200_malloc: replaces gpu::GPUAllocator / Einsums_GPUMemory_vars and the --einsums:gpu-buffer-size
+ * option (libs/Einsums/GPUMemory/include/Einsums/GPUMemory/GPUAllocator.hpp:157-191, src/ModuleVars.cpp:43-63,
+ * src/InitModule.cpp:39-55). An allocation that would push the live total past the budget fails with
+ * EB200_ERR_OUT_OF_MEMORY before any CUDA call ("Could not allocate enough memory on the GPU device. Requested N bytes.").
+ * 0 = unlimited (default). Process-wide, thread-safe. */
+int eb200_set_memory_budget(size_t bytes);
+int eb200_memory_stats(size_t *budget_bytes, size_t *in_use_bytes, size_t *peak_bytes, size_t *live_allocations);
 int eb200_malloc_host(void **ptr, size_t bytes); /* pinned host memory (PINNED mode)           */
 int eb200_free_host(void *ptr);
 int eb200_mem_get_info(size_t *free_bytes, size_t *total_bytes);

@@ -86,3 +86,51 @@ def test_no_cpu_fallback(eb):
     one, zero = (C.c_double * 1)(1.0), (C.c_double * 1)(0.0)
     rc = lib.eb200_dgemm(None, b"n", b"n", 64, 64, 64, one, a.ctypes.data, 64, a.ctypes.data, 64, zero, c.ctypes.data, 64)
     assert rc != 0 and not c.any()
+
+
+def test_mixed_dtype_zero_extent_terminates(eb):
+    """A mixed-type contraction whose narrower tensor is empty must not recurse (it used to overflow the stack: the empty
+    tensor kept its dtype, so the widened descriptor went back into the mixed-type path for ever). Run in a child
+    process so that a regression shows up as a failed assertion, not as a dead pytest."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import ctypes as C, torch
+        from einsums_b200 import _lib, ops
+        for (cs, as_, bs) in (((4, 4), (4, 0), (0, 4)), ((0, 4), (0, 3), (3, 4))):
+            d = ops.make_desc("ij", torch.empty(cs, dtype=torch.float64), "ik", torch.empty(as_, dtype=torch.float32), "kj", torch.empty(bs, dtype=torch.float64))
+            d.C.data = d.A.data = d.B.data = 0
+            rc = _lib.lib().eb200_contract(None, C.byref(d))
+            print("rc", rc)
+        print("done")
+    """)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, cwd=_lib.ROOT)
+    assert out.returncode == 0 and "done" in out.stdout, (out.returncode, out.stdout[-500:], out.stderr[-500:])
+
+
+def test_make_desc_rejects_inconsistent_extents(eb):
+    """The C ABI has no per-tensor shapes: the Python door must refuse a label whose extent differs between tensors (or
+    between two axes of one tensor) with the reference's dimension_error class, as the C++ shim's check_dims does."""
+    z = lambda *s: torch.empty(s, dtype=torch.float64)
+    with pytest.raises(ValueError, match="dimension_error"):
+        ops.make_desc("ij", z(5, 3), "ik", z(3, 4), "kj", z(4, 3))
+    with pytest.raises(ValueError, match="dimension_error"):
+        ops.make_desc("i", z(3), "ii", z(3, 4), "i", z(3))
+    with pytest.raises(ValueError, match="dimension_error"):
+        ops.make_desc("ij", z(3, 3), "ik", z(3, 4), "kj", z(5, 3))
+    ops.make_desc("ij", z(3, 5), "ik", z(3, 4), "kj", z(4, 5))
+
+
+def test_memory_budget_accounting(eb):
+    """Budgeted allocator (reference: GPUMemory/src/ModuleVars.cpp:43-63 try_allocate): a request over the budget is refused
+    before any CUDA call, so this part of the contract is testable without a device."""
+    lib = _lib.lib()
+    lib.eb200_set_memory_budget.argtypes = [C.c_size_t]
+    lib.eb200_memory_stats.argtypes = [C.POINTER(C.c_size_t)] * 4
+    assert lib.eb200_set_memory_budget(1 << 20) == 0
+    p = C.c_void_p()
+    assert lib.eb200_malloc(C.byref(p), 2 << 20) == 6  # OUT_OF_MEMORY
+    assert b"Could not allocate enough memory on the GPU device" in lib.eb200_last_error_string()
+    b, u, pk, n = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+    assert lib.eb200_memory_stats(C.byref(b), C.byref(u), C.byref(pk), C.byref(n)) == 0
+    assert b.value == 1 << 20 and u.value == 0 and n.value == 0
+    assert lib.eb200_set_memory_budget(0) == 0
