@@ -7,7 +7,14 @@ Workload (BASELINE.json configs[1]): CCD W intermediates, o=20, v=200, FP64, one
 both through the C ABI (eb200_contract -> gemm_tma_f64: TMA + mbarrier + DMMA). flops/step = 2*o^4*v^2 + 2*v^4*o^2 = 1.2928e12.
 
 N > 1 (torchrun, one rank per GPU): the `a` index of Wabef is sharded — rank r owns the slab a in [r*v,(r+1)*v) of a
-W with N*v values of `a` (per-GPU work fixed => weak scaling); no collective on the data path.
+W with N*v values of `a` (per-GPU work fixed => weak scaling): g_oovv is the same on every rank, t[:,:,a_r,:] and the W
+slab are the rank's own; no collective on the data path.
+
+Besides the headline the same JSON line carries
+  "sharded": BASELINE configs[4] — Wabef o=40 v=400 (W = 204.8 GB, 8.192e13 flop) sharded over `a` across the N ranks with
+             both operands replicated (identical seeds): STRONG scaling, total work fixed, at every N including 1;
+  "configs": (N = 1 only) the other BASELINE configs at full size — Fock J/K n=100, Wmnij, Wmbej o=60 v=240, Fock J/K and
+             permuted-K at n=300, the 24-order rank-4 permute sweep — each with its roofline fraction (tools/run_configs.py).
 
 --impl reference : the reference's CPU path (oracle port: analyser + OpenBLAS dgemm, all host threads) on the same config.
 """
@@ -41,6 +48,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-v", type=int, default=0, help="v for the CPU sample (0 = full config)")
     ap.add_argument("--e2e-slab-mb", type=int, default=128, help="slab size of the host-path pipeline (MiB)")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the strong-scaling record (Wabef o=40 v=400 sharded over a)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the records of the other BASELINE configs (N = 1 only)")
+    ap.add_argument("--sharded-budget-gb", type=float, default=60.0, help="largest C sub-slab kept on one GPU")
     ap.add_argument("--cpu-configs", action="store_true",
                     help="with --impl reference: also time the CPU port on the other BASELINE configs at host-sized samples (one JSON line each)")
     return ap.parse_args()
@@ -189,6 +199,8 @@ def run_reference(args):
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": f"CPU arm: one step takes about a second on the host, so it runs at most 3 timed steps after 1 warm-up whatever --steps/--warmup "
+                f"say (asked: {args.steps}/{args.warmup}; ran: {steps}/{warm}); value is per step, independent of the count",
     }
     print(json.dumps(line), flush=True)
     if args.cpu_configs:
@@ -196,6 +208,65 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def run_sharded(args, world, rank, barrier):
+    """BASELINE configs[4]: Wabef[a,b,e,f] = W + 0.25 sum_mn g[m,n,e,f] t[m,n,a,b], o=40, v=400 (W = 204.8 GB, 8.192e13 flop), the
+    a-index block-distributed over the ranks (einsums_b200.sharding), g and t REPLICATED (same seed on every rank; 2 x 2.05 GB),
+    each rank walking its slab in sub-slabs of at most --sharded-budget-gb through one reused C buffer. Strong scaling: total
+    work is fixed. No collective in the timed region; max over ranks of the CUDA-event time."""
+    import torch
+    import torch.distributed as dist
+    from einsums_b200 import ops
+    from einsums_b200.sharding import plan_slabs
+    o, v = 40, 400
+    plan = plan_slabs(v, v**3, o * o, world, rank, int(args.sharded_budget_gb * 2**30))
+    gen = torch.Generator(device="cuda").manual_seed(20251017 + 5)   # identical on every rank: the operands are replicated
+    g = torch.rand(o, o, v, v, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+    t = torch.rand(o, o, v, v, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+    check = torch.stack([g.sum(), t.sum()])
+    if world > 1:   # prove the replication: the operand checksums of all ranks must coincide
+        lo, hi = check.clone(), check.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert torch.equal(lo, hi), "g/t differ between ranks"
+    rows = max(e - s for s, e in plan.sub)
+    W = torch.zeros(rows, v, v, v, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def run():
+        for s, e in plan.sub:
+            ops.contract("abef", W[: e - s], "mnef", g, "mnab", t[:, :, s:e, :], 0.25, 1.0)
+
+    run()   # warm-up (also the first-touch of W)
+    # parity: the first row of this rank's slab against a float64 torch.einsum on the same device (different summation order)
+    s0 = plan.a0
+    Wrow = torch.zeros(1, v, v, v, dtype=torch.float64, device="cuda")
+    ops.contract("abef", Wrow, "mnef", g, "mnab", t[:, :, s0:s0 + 1, :], 0.25, 1.0)
+    ref = 0.25 * torch.einsum("mnef,mnb->bef", g, t[:, :, s0, :])
+    err = torch.tensor([((Wrow[0] - ref).abs().max() / ref.abs().max()).item()], dtype=torch.float64, device="cuda")
+    del Wrow, ref
+    W.zero_()
+    l0 = ops.launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    run()
+    e1.record(stream)
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    flops = 2.0 * v**4 * o**2
+    out = {"workload": f"Wabef o={o} v={v} FP64 a-sharded (BASELINE configs[4]); W = {8 * v**4 / 1e9:.1f} GB produced in sub-slabs of <= {args.sharded_budget_gb:g} GB",
+           "scaling": "strong", "n_gpus": world, "ms": ms.item(), "tflops_total": flops / ms.item() / 1e9, "tflops_per_gpu": flops / ms.item() / 1e9 / world,
+           "rows_per_rank": plan.a1 - plan.a0, "sub_slabs_per_rank": len(plan.sub), "parity_rel_err": err.item(), "parity_tol": 1e-12,
+           "operands": "g, t replicated: same generator seed on every rank, checksums compared across ranks", "collectives_in_timed_region": 0,
+           "gpu_launches": int(ops.launch_count() - l0), "kernel": ops.last_kernel()}
+    assert out["parity_rel_err"] < 1e-12, out
+    del W, g, t
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -228,19 +299,23 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     o, v = O, V
-    gen = torch.Generator(device="cuda").manual_seed(20251017 + 2 + rank)
-    rnd = lambda *s: torch.rand(*s, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
-    g, t = rnd(o, o, v, v), rnd(o, o, v, v)        # g_oovv replicated; t = this rank's a-slab t[m,n,a_r,b]
-    Wm, Wa = rnd(o, o, o, o), rnd(v, v, v, v)      # Wabef slab of this rank: a in [rank*v, (rank+1)*v)
+    gen_all = torch.Generator(device="cuda").manual_seed(20251017 + 2)          # same stream on every rank: replicated tensors
+    gen = torch.Generator(device="cuda").manual_seed(20251017 + 2 + 1000 * (rank + 1))  # this rank's own slabs
+    rnd = lambda *s, gen=gen: torch.rand(*s, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+    g = rnd(o, o, v, v, gen=gen_all)               # g_oovv: replicated (identical on every rank)
+    t = rnd(o, o, v, v)                            # t[m,n,a_r,b]: this rank's a-slab of the N*v-wide t
+    Wm, Wa = rnd(o, o, o, o), rnd(v, v, v, v)      # Wmnij (per rank) and the Wabef slab a in [rank*v, (rank+1)*v)
     stream = torch.cuda.current_stream()
 
-    kinds = {}
+    kinds, knames = {}, {}
 
     def step(ev=None):
         d1 = ops.contract("mnij", Wm, "mnef", g, "ijef", t, 0.25, 1.0)
+        knames["wmnij"] = ops.last_kernel()
         if ev is not None:
             ev[0].record(stream)
         d2 = ops.contract("abef", Wa, "mnef", g, "mnab", t, 0.25, 1.0)
+        knames["wabef"] = ops.last_kernel()
         if ev is not None:
             ev[1].record(stream)
         kinds["wmnij"], kinds["wabef"] = d1, d2
@@ -323,13 +398,22 @@ def run_ours(args):
                "d2h_bytes_per_step": counts["d2h"], "ms_per_step": te.item() / ke, "steps": ke, "max_abs_diff_vs_resident_path": e2e_err,
                "note": "pinned host -> device of g, t, Wmnij, Wabef; both einsums; device -> pinned host of both results; "
                        f"Wabef through eb200_contract_host in {args.e2e_slab_mb} MiB slabs with H2D|compute|D2H overlapped"}
-        Wa = None
+        del e2e_step, hWa, oWa, hg, ht, hWm, oWm, ge, te_, chk   # 12.8 GB of pinned host memory per rank goes back before the next section
 
+    # ---- BASELINE configs[4]: Wabef o=40 v=400 sharded over `a` (strong scaling), at every N
+    del g, t, Wm
+    Wa = None
+    torch.cuda.empty_cache()
+    sharded = None
+    if not args.no_sharded:
+        sharded = run_sharded(args, world, rank, barrier)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     peak, peak_src, peak_json = fp64_peak()
+    if sharded:
+        sharded["frac_of_dmma"] = sharded["tflops_total"] / world / peak
     achieved = FLOPS_WABEF / (ms_wabef * 1e-3) / 1e12
     traffic = None
     prof = os.path.join(ROOT, "profiles", "traffic.json")
@@ -350,9 +434,23 @@ def run_ours(args):
                      "algorithmic_flops_per_launch": FLOPS_WABEF},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "kernels": {k: {"family": int(d.kernel_used), "split_k": int(d.split_k), "launches": int(d.launches)} for k, d in kinds.items()},
+        "kernel_names": knames,
     }
     if peak_json:
         line["fp64_peaks"] = peak_json
+    if sharded:
+        line["sharded"] = sharded
+    if not args.no_configs and world == 1:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import run_configs
+        torch.cuda.empty_cache()
+        csampler = ClockSampler(local)
+        csampler.start()
+        l0 = ops.launch_count()
+        records, pk = run_configs.run_all(("1", "2", "3", "4"), wabef=False)   # Wabef is the headline above
+        line["configs"] = {"records": records, "peaks": pk, "clocks": csampler.stop(), "gpu_launches": int(ops.launch_count() - l0),
+                           "timing": "median of CUDA-event timings after warm-up; ops under 1 ms are timed as 20 back-to-back launches; inputs exceed L2 "
+                                     "(except cfg1's D and Wmnij's 1.3 MB output)"}
     if not args.no_cpu_baseline and world == 1:
         torch.cuda.empty_cache()
         cb = cpu_reference(2, 1, args.cpu_sample_v)

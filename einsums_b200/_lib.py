@@ -87,6 +87,11 @@ def _declare(lib):
     lib.eb200_last_error_string.restype = C.c_char_p
     lib.eb200_launch_count.restype = C.c_int64
     lib.eb200_launch_count_reset.restype = None
+    lib.eb200_last_kernel_name.restype = C.c_char_p
+    lib.eb200_set_option.argtypes = [C.c_char_p, ci]
+    lib.eb200_get_option.argtypes = [C.c_char_p, C.POINTER(ci)]
+    lib.eb200_set_memory_budget.argtypes = [C.c_size_t]
+    lib.eb200_memory_stats.argtypes = [C.POINTER(C.c_size_t)] * 4
     lib.eb200_contract.argtypes = [vp, C.POINTER(ContractDesc)]
     lib.eb200_contract_plan.argtypes = [C.POINTER(ContractDesc)]
     lib.eb200_contract_grouped.argtypes = [vp, C.c_int64, C.POINTER(ContractDesc), C.POINTER(C.c_int32)]

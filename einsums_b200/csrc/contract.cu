@@ -4,6 +4,7 @@
 #include "contract.cuh"
 #include "contract_kernels.cuh"
 #include "gemm_tma.cuh"
+#include "contract_tma.cuh"
 #include "launch_api.cuh"
 
 #include <algorithm>
@@ -89,7 +90,8 @@ EncodeTiledFn encode_tiled_fn() {
     }();
     return fn;
 }
-int g_use_tma = -1; // EB200_USE_TMA=0 disables the TMA path (A/B comparisons)
+// tuning / testing knobs (eb200_set_option, defaults from the environment): tma = 0 disables both TMA kernels; tma_generic = 0
+// disables the multi-index one, 2 takes it whenever it is legal (ignores the padding-waste rule); tma_tile = 0 / 1 forces 128x64 / 80x80
 
 // 2-D map over an operand: dim0 = the unit-stride direction, dim1 = the other one (ld elements apart)
 bool make_operand_map(CUtensorMap *map, const double *base, int64_t inner, int64_t outer, int64_t ld, uint32_t box_inner, uint32_t box_outer) {
@@ -103,13 +105,32 @@ bool make_operand_map(CUtensorMap *map, const double *base, int64_t inner, int64
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// ---- tile shape / split-K choice shared by both TMA kernels. mb, nb: 16-row block counts of the (padded) composite M and N.
+struct TmaChoice { int cfg; int64_t tm, tn; int splits; };
+TmaChoice choose_tma_tile(int64_t mb, int64_t nb, int64_t batches, int64_t KT, int forced_split) {
+    const int forced_cfg = option(OPT_TMA_TILE);
+    const int64_t tm0 = (mb + 7) / 8, tn0 = (nb + 3) / 4, tm1 = (mb + 4) / 5, tn1 = (nb + 4) / 5;
+    const double  real = (double)mb * nb, area0 = (double)tm0 * 8 * tn0 * 4, area1 = (double)tm1 * 5 * tn1 * 5;
+    TmaChoice     c;
+    // 128x64 unless it pads the output by more than 15 % and 80x80 tiles cover it clearly better (Wmnij: 400x400 -> 512x448 vs 400x400)
+    c.cfg = (area0 > 1.15 * real && area1 * 1.08 < area0) ? 1 : 0;
+    if (forced_cfg == 0 || forced_cfg == 1) c.cfg = forced_cfg;
+    c.tm = c.cfg ? tm1 : tm0;
+    c.tn = c.cfg ? tn1 : tn0;
+    const int64_t tiles = c.tm * c.tn * std::max<int64_t>(1, batches);
+    int64_t       splits = 1;
+    if (forced_split > 0) splits = forced_split;
+    else {
+        const int64_t target = (int64_t)sm_count() * (c.cfg ? 3 : 2);
+        if (tiles * 2 <= target) splits = std::min<int64_t>(target / tiles, std::max<int64_t>(1, KT / 8));
+    }
+    c.splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(splits, KT), 65535));
+    return c;
+}
+
 // returns 1 when the TMA kernel ran, 0 when the shape does not qualify, <0 on error
 int try_run_tma(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const double beta_eff[2]) {
-    if (g_use_tma < 0) {
-        const char *e = getenv("EB200_USE_TMA");
-        g_use_tma = e ? atoi(e) : 1;
-    }
-    if (!g_use_tma || d.force_kernel != 0 && d.force_kernel != EB200_KF_TILE_MMA) return 0;
+    if (!option(OPT_TMA) || (d.force_kernel != 0 && d.force_kernel != EB200_KF_TILE_MMA)) return 0;
     if (p.b.n != 0 || p.m.n != 1 || p.n.n != 1 || p.k.n != 1) return 0;
     const double *A = (const double *)d.A.data, *B = (const double *)d.B.data;
     const int64_t M = p.m.tot, N = p.n.tot, K = p.k.tot;
@@ -123,6 +144,9 @@ int try_run_tma(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const dou
     // an extent-1 "other" direction makes ld meaningless but harmless; TMA needs ld*8 to be a multiple of 16 (checked) and >= inner*8
     if ((ak ? K : M) > lda && (ak ? M : K) > 1) return 0;
     if ((bk ? K : N) > ldb && (bk ? N : K) > 1) return 0;
+    // split-K and the 80x80 tile live in the generic TMA kernel (fused reduction, no finalize pass)
+    const TmaChoice ch = choose_tma_tile((M + 15) / 16, (N + 15) / 16, 1, (K + 15) / 16, d.split_k);
+    if (ch.cfg != 0 || ch.splits != 1) return 0;
 
     CUtensorMap tmA, tmB;
     if (!(ak ? make_operand_map(&tmA, A, K, M, lda, 16, 128) : make_operand_map(&tmA, A, M, K, lda, 16, 16))) return 0;
@@ -132,42 +156,138 @@ int try_run_tma(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const dou
     a.M = M; a.N = N; a.K = K;
     a.sCm = p.m.s[ROLE_C][0]; a.sCn = p.n.s[ROLE_C][0];
     a.C = (double *)d.C.data;
-    a.ws = nullptr;
     a.alpha = d.alpha[0]; a.beta = beta_eff[0];
     const int64_t tm = (M + 127) / 128, tn = (N + 63) / 64;
     if (tm * tn > 0x7fffffffLL) return 0;
     a.tiles_m = (int)tm; a.tiles_n = (int)tn;
     a.vec_c = (a.sCn == 1 && !(N & 1) && !(a.sCm & 1) && ((uintptr_t)a.C % 16) == 0) ? 1 : 0;
-    const int64_t KT = (K + 15) / 16, tiles = tm * tn;
-    int           splits = 1;
-    if (d.split_k > 0) splits = d.split_k;
-    else {
-        const int64_t target = (int64_t)sm_count() * 2;
-        if (tiles * 2 <= target) splits = (int)std::min<int64_t>(target / tiles, std::max<int64_t>(1, KT / 8));
-    }
-    splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(splits, KT), 65535));
-    a.splits = splits;
-    d.split_k = splits;
-    void *ws = nullptr;
-    if (splits > 1) {
-        int rc = ws_alloc(&ws, (size_t)splits * M * N * sizeof(double), s);
-        if (rc) return -rc;
-        a.ws = (double *)ws;
-    }
+    d.split_k = 1;
     static const size_t smem_pad = getenv("EB200_TMA_SMEM_PAD") ? (size_t)atoi(getenv("EB200_TMA_SMEM_PAD")) : 0; // debugging: forces 1 CTA/SM
     const size_t        SMEM = 4 * (128 * 16 * 8 + 64 * 16 * 8) + 1024 + 64 + smem_pad;
-    dim3             grid((unsigned)tiles, (unsigned)splits, 1);
     {
-        int rc_ = k_launch_tma(s, tmA, tmB, a, grid, SMEM, ak, bk);
+        int rc_ = k_launch_tma(s, tmA, tmB, a, dim3((unsigned)(tm * tn), 1, 1), SMEM, ak, bk);
         if (rc_) return -rc_;
     }
     d.launches++;
-    if (splits > 1) {
-        int rc = launch_finalize<double>(s, p.b, p.m, p.n, ws, d.C.data, d.alpha, beta_eff, splits, d);
-        if (rc) return -rc;
-        cudaError_t fe = cudaFreeAsync(ws, s);
-        if (fe != cudaSuccess) return -cuda_fail(fe, "cudaFreeAsync");
+    set_last_kernel("gemm_tma_f64");
+    return 1;
+}
+
+// ---------------------------------------------------------------- generic TMA path (multi-index groups, batches, split-K, 80x80 tiles)
+// One <= 5-dimensional tensor map per operand: dimension 0 is the operand's unit-stride index, the others follow by stride.
+// Boxes are 16 x 16 over (inner target index, inner contracted index); see contract_tma.cuh.
+struct GenMapDim { int64_t ext, stride; int grp, idx; }; // grp: 0 target (M or N), 1 contracted, 2 batch
+bool make_generic_map(CUtensorMap *map, const double *base, const Grp &tgt, const Grp &k, const Grp &b, int role, bool kmajor, int32_t *d_t,
+                      int32_t *d_k, int32_t *d_b) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || ((uintptr_t)base % 16)) return false;
+    if (tgt.n < 1 || k.n < 1 || tgt.n > TG_MAXI || k.n > TG_MAXI || b.n > TG_MAXI || tgt.n + k.n + b.n > 5) return false;
+    std::vector<GenMapDim> dims;
+    for (int i = 0; i < tgt.n; i++) dims.push_back({tgt.ext[i], tgt.s[role][i], 0, i});
+    for (int i = 0; i < k.n; i++) dims.push_back({k.ext[i], k.s[role][i], 1, i});
+    for (int i = 0; i < b.n; i++) dims.push_back({b.ext[i], b.s[role][i], 2, i});
+    for (auto &x : dims)
+        if (x.stride <= 0 || x.ext < 1 || x.ext >= (1LL << 31) || x.stride >= (1LL << 36)) return false; // broadcast (stride 0) and reversed axes: gather kernel
+    const int unit_grp = kmajor ? 1 : 0;
+    std::stable_sort(dims.begin(), dims.end(), [&](const GenMapDim &x, const GenMapDim &y) {
+        const bool ux = x.grp == unit_grp && x.idx == 0, uy = y.grp == unit_grp && y.idx == 0;
+        if (ux != uy) return ux;
+        return x.stride < y.stride;
+    });
+    if (dims[0].stride != 1) return false;
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t box[5], es[5] = {1, 1, 1, 1, 1};
+    int64_t    span = 2;
+    for (int i = 0; i < TG_MAXI; i++) d_t[i] = d_k[i] = d_b[i] = -1;
+    for (int dd = 0; dd < 5; dd++) {
+        if (dd < (int)dims.size()) {
+            const GenMapDim &x = dims[dd];
+            if (dd > 0 && (x.stride & 1)) return false; // byte strides must be multiples of 16
+            gdim[dd] = (cuuint64_t)x.ext;
+            if (dd > 0) gstr[dd - 1] = (cuuint64_t)x.stride * 8;
+            box[dd] = (x.idx == 0 && x.grp != 2) ? 16 : 1;
+            (x.grp == 0 ? d_t : x.grp == 1 ? d_k : d_b)[x.idx] = dd;
+            span = std::max(span, x.stride * x.ext);
+        } else { // unused dimension: extent 1, coordinate always 0
+            gdim[dd] = 1;
+            gstr[dd - 1] = (cuuint64_t)((span + 1) & ~1LL) * 8;
+            box[dd] = 1;
+        }
     }
+    for (int dd = 0; dd < 4; dd++)
+        if (gstr[dd] >= (1ULL << 40)) return false;
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void *)base, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int try_run_tma_generic(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const double beta_eff[2]) {
+    const int use_generic = option(OPT_TMA_GENERIC);
+    if (!option(OPT_TMA) || !use_generic || (d.force_kernel != 0 && d.force_kernel != EB200_KF_TILE_MMA)) return 0;
+    if (p.swapped) return 0;
+    const double *A = (const double *)d.A.data, *B = (const double *)d.B.data;
+    const bool    ak = p.a_kmajor != 0, bk = p.b_kmajor != 0;
+    TmaGenArgs    a;
+    memset(&a, 0, sizeof(a));
+    CUtensorMap tmA, tmB;
+    if (!make_generic_map(&tmA, A, p.m, p.k, p.b, ROLE_A, ak, a.dAm, a.dAk, a.dAb)) return 0;
+    if (!make_generic_map(&tmB, B, p.n, p.k, p.b, ROLE_B, bk, a.dBn, a.dBk, a.dBb)) return 0;
+    for (int i = 0; i < TG_MAXI; i++) {
+        a.em[i] = i < p.m.n ? (int32_t)p.m.ext[i] : 1;
+        a.en[i] = i < p.n.n ? (int32_t)p.n.ext[i] : 1;
+        a.ek[i] = i < p.k.n ? (int32_t)p.k.ext[i] : 1;
+        a.eb[i] = i < p.b.n ? (int32_t)p.b.ext[i] : 1;
+        a.sCm[i] = i < p.m.n ? p.m.s[ROLE_C][i] : 0;
+        a.sCn[i] = i < p.n.n ? p.n.s[ROLE_C][i] : 0;
+        a.sCb[i] = i < p.b.n ? p.b.s[ROLE_C][i] : 0;
+    }
+    a.mblk0 = (a.em[0] + 15) / 16; a.nblk0 = (a.en[0] + 15) / 16; a.kstep0 = (a.ek[0] + 15) / 16;
+    a.MB = (int64_t)a.mblk0 * a.em[1] * a.em[2];
+    a.NB = (int64_t)a.nblk0 * a.en[1] * a.en[2];
+    const int64_t KT = (int64_t)a.kstep0 * a.ek[1] * a.ek[2];
+    if (KT > 0x7fffffffLL) return 0;
+    a.KT = (int32_t)KT;
+    // padding the inner indices to multiples of 16 must stay cheap, otherwise the gather kernel (no padding) is the better choice
+    const double waste = (double)a.MB * 16 / (double)p.m.tot * ((double)a.NB * 16 / (double)p.n.tot) * ((double)KT * 16 / (double)p.k.tot);
+    if (waste > 1.12 && use_generic != 2) {
+        // a plain product with ragged edges pads only the last block of each direction: always fine
+        if (!(p.m.n == 1 && p.n.n == 1 && p.k.n == 1)) return 0;
+    }
+    const TmaChoice ch = choose_tma_tile(a.MB, a.NB, p.b.tot, KT, d.split_k);
+    if (ch.tm * ch.tn > 0x7fffffffLL) return 0;
+    a.tiles_m = (int)ch.tm; a.tiles_n = (int)ch.tn;
+    a.splits = ch.splits;
+    d.split_k = ch.splits;
+    a.C = (double *)d.C.data;
+    a.alpha = d.alpha[0]; a.beta = beta_eff[0];
+    a.vec_c = operand_pairs_ok(p, ROLE_C, p.n, p.m, a.C) ? 1 : 0;
+    const int64_t tiles = ch.tm * ch.tn, per_launch = std::min<int64_t>(65535, p.b.tot);
+    const size_t  tile_elems = ch.cfg ? 80 * 80 : 128 * 64;
+    void         *ws = nullptr;
+    size_t        counter_bytes = 0;
+    if (ch.splits > 1) {
+        counter_bytes = ((size_t)(tiles * per_launch) * sizeof(unsigned) + 255) & ~(size_t)255;
+        int rc = ws_alloc(&ws, counter_bytes + (size_t)(tiles * per_launch) * ch.splits * tile_elems * sizeof(double), s);
+        if (rc) return -rc;
+        a.counters = (unsigned *)ws;
+        a.ws = (double *)((char *)ws + counter_bytes);
+    }
+    int rc = EB200_OK;
+    for (int64_t b0 = 0; b0 < p.b.tot && rc == EB200_OK; b0 += 65535) {
+        a.batch0 = b0;
+        if (ws) {
+            cudaError_t e = cudaMemsetAsync(ws, 0, counter_bytes, s);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "cudaMemsetAsync(split counters)"); break; }
+        }
+        dim3 grid((unsigned)tiles, (unsigned)ch.splits, (unsigned)std::min<int64_t>(65535, p.b.tot - b0));
+        rc = k_launch_tma_generic(s, tmA, tmB, a, grid, ch.cfg, ak, bk);
+        if (rc == EB200_OK) d.launches++;
+    }
+    if (ws) {
+        cudaError_t fe = cudaFreeAsync(ws, s);
+        if (rc == EB200_OK && fe != cudaSuccess) rc = cuda_fail(fe, "cudaFreeAsync");
+    }
+    if (rc) return -rc;
+    set_last_kernel(ch.cfg ? "contract_tma_f64<80x80>" : "contract_tma_f64<128x64>");
     return 1;
 }
 
@@ -224,6 +344,7 @@ int try_run_tf32x3(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const 
     d.launches++;
     d.split_k = 1;
     d.kernel_used = EB200_KF_TILE_TCGEN05;
+    set_last_kernel("gemm_tf32x3_tcgen05");
     return 1;
 }
 
@@ -243,6 +364,9 @@ template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract
     if constexpr (std::is_same_v<T, double>) {
         if (mma) {
             int r = try_run_tma(s, p, d, beta_eff);
+            if (r == 1) return EB200_OK;
+            if (r < 0) return -r;
+            r = try_run_tma_generic(s, p, d, beta_eff);
             if (r == 1) return EB200_OK;
             if (r < 0) return -r;
         }
@@ -307,6 +431,7 @@ template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract
         if (rc == EB200_OK) d.launches++;
     }
     if (rc) return rc;
+    set_last_kernel(mma ? "tile_mma_f64" : "tile_simt");
     if (splits > 1) {
         rc = launch_finalize<T>(s, p.b, p.m, p.n, ws, d.C.data, d.alpha, beta_eff, splits, d);
         if (rc) return rc;

@@ -12,7 +12,8 @@
 //     (a sum over k does not care about the order, and A and B use the same permutation); this works for both
 //     K-major tiles (row = m, 16 k per row) and M-major tiles (row = k, 16 m per row), see DESIGN.md §2.1;
 //   * FP64 has no tcgen05 kind: the math is mma.sync.m8n8k4.f64 (DMMA), accumulators in registers;
-//   * tile 128x64x16, 4 stages (96 KB), 256 threads, 2 CTAs per SM; split-K partials to scratch as tile_mma_f64.
+//   * tile 128x64x16, 4 stages (96 KB), 256 threads, 2 CTAs per SM; split-K, batches, multi-index groups and the 80x80 tile
+//     are served by contract_tma_f64 (contract_tma.cuh).
 #pragma once
 #include <cuda.h>
 
@@ -24,9 +25,8 @@ struct TmaGemmArgs {
     int64_t M, N, K;
     int64_t sCm, sCn;      // element strides of C
     double *C;
-    double *ws;            // split partials [split][M][N]
     double  alpha, beta;
-    int32_t splits, tiles_m, tiles_n, vec_c;
+    int32_t tiles_m, tiles_n, vec_c;
 };
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
@@ -84,10 +84,8 @@ __global__ void __launch_bounds__(256, 2) gemm_tma_f64(const __grid_constant__ C
         tile_m = first + in_g % gsize;
         tile_n = in_g / gsize;
     }
-    const int split = blockIdx.y;
-    const int KT = (int)((args.K + BK - 1) / BK);
-    const int ks0 = (int)((int64_t)KT * split / args.splits), ks1 = (int)((int64_t)KT * (split + 1) / args.splits);
-    const int nsteps = ks1 - ks0;
+    // split-K and other tile shapes are served by contract_tma_f64 (contract_tma.cuh); this kernel always owns the whole K range
+    const int ks0 = 0, nsteps = (int)((args.K + BK - 1) / BK);
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) {
@@ -184,63 +182,48 @@ __global__ void __launch_bounds__(256, 2) gemm_tma_f64(const __grid_constant__ C
 
     // ---- epilogue from registers (C fragment: row = lane/4, cols = 2*(lane%4) + {0,1})
     const int64_t m_base = (int64_t)tile_m * BM + wm0 + r, n_base = (int64_t)tile_n * BN + wn0 + 2 * j;
-    if (args.splits == 1) {
-        const double alpha = args.alpha, beta = args.beta;
-        const bool   has_beta = beta != 0.0;
+    const double alpha = args.alpha, beta = args.beta;
+    const bool   has_beta = beta != 0.0;
 #pragma unroll
-        for (int h = 0; h < FM; h += 2) {
-            double cold[2][FN][2];
+    for (int h = 0; h < FM; h += 2) {
+        double cold[2][FN][2];
 #pragma unroll
-            for (int ii = 0; ii < 2; ii++) {
-                const int64_t m = m_base + 8 * (h + ii);
+        for (int ii = 0; ii < 2; ii++) {
+            const int64_t m = m_base + 8 * (h + ii);
 #pragma unroll
-                for (int jj = 0; jj < FN; jj++) {
-                    const int64_t n = n_base + 8 * jj;
-                    cold[ii][jj][0] = cold[ii][jj][1] = 0.0;
-                    if (has_beta && m < args.M) {
-                        const double *src = args.C + m * args.sCm + n * args.sCn;
-                        if (args.vec_c) {
-                            if (n < args.N) {
-                                double2 v = *reinterpret_cast<const double2 *>(src);
-                                cold[ii][jj][0] = v.x; cold[ii][jj][1] = v.y;
-                            }
-                        } else {
-                            if (n < args.N) cold[ii][jj][0] = src[0];
-                            if (n + 1 < args.N) cold[ii][jj][1] = src[args.sCn];
+            for (int jj = 0; jj < FN; jj++) {
+                const int64_t n = n_base + 8 * jj;
+                cold[ii][jj][0] = cold[ii][jj][1] = 0.0;
+                if (has_beta && m < args.M) {
+                    const double *src = args.C + m * args.sCm + n * args.sCn;
+                    if (args.vec_c) {
+                        if (n < args.N) {
+                            double2 v = *reinterpret_cast<const double2 *>(src);
+                            cold[ii][jj][0] = v.x; cold[ii][jj][1] = v.y;
                         }
-                    }
-                }
-            }
-#pragma unroll
-            for (int ii = 0; ii < 2; ii++) {
-                const int64_t m = m_base + 8 * (h + ii);
-                if (m >= args.M) continue;
-#pragma unroll
-                for (int jj = 0; jj < FN; jj++) {
-                    const int64_t n = n_base + 8 * jj;
-                    if (n >= args.N) continue;
-                    double v0 = alpha * acc[h + ii][jj][0], v1 = alpha * acc[h + ii][jj][1];
-                    if (has_beta) { v0 = fma(beta, cold[ii][jj][0], v0); v1 = fma(beta, cold[ii][jj][1], v1); }
-                    double *dst = args.C + m * args.sCm + n * args.sCn;
-                    if (args.vec_c) *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
-                    else {
-                        dst[0] = v0;
-                        if (n + 1 < args.N) dst[args.sCn] = v1;
+                    } else {
+                        if (n < args.N) cold[ii][jj][0] = src[0];
+                        if (n + 1 < args.N) cold[ii][jj][1] = src[args.sCn];
                     }
                 }
             }
         }
-    } else {
-        double *ws = args.ws + (int64_t)split * args.M * args.N;
 #pragma unroll
-        for (int i = 0; i < FM; i++) {
-            const int64_t m = m_base + 8 * i;
+        for (int ii = 0; ii < 2; ii++) {
+            const int64_t m = m_base + 8 * (h + ii);
             if (m >= args.M) continue;
 #pragma unroll
             for (int jj = 0; jj < FN; jj++) {
                 const int64_t n = n_base + 8 * jj;
-                if (n < args.N) ws[m * args.N + n] = acc[i][jj][0];
-                if (n + 1 < args.N) ws[m * args.N + n + 1] = acc[i][jj][1];
+                if (n >= args.N) continue;
+                double v0 = alpha * acc[h + ii][jj][0], v1 = alpha * acc[h + ii][jj][1];
+                if (has_beta) { v0 = fma(beta, cold[ii][jj][0], v0); v1 = fma(beta, cold[ii][jj][1], v1); }
+                double *dst = args.C + m * args.sCm + n * args.sCn;
+                if (args.vec_c) *reinterpret_cast<double2 *>(dst) = make_double2(v0, v1);
+                else {
+                    dst[0] = v0;
+                    if (n + 1 < args.N) dst[args.sCn] = v1;
+                }
             }
         }
     }

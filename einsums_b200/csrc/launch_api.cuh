@@ -3,6 +3,7 @@
 #pragma once
 #include "contract_kernels.cuh"
 #include "gemm_tma.cuh"
+#include "contract_tma.cuh"
 #include "gemm_tf32x3.cuh"
 
 namespace eb200 {
@@ -18,6 +19,8 @@ int k_launch_mma(cudaStream_t s, TileArgs &args, dim3 grid);                    
 int k_launch_simt(int dtype, cudaStream_t s, TileArgs &args, dim3 grid);                         // k_tile_simt.cu
 int k_launch_tma(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB, const TmaGemmArgs &a, dim3 grid, size_t smem, bool ak,
                  bool bk);                                                                       // k_tile_tma.cu
+int k_launch_tma_generic(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB, const TmaGenArgs &a, dim3 grid, int cfg, bool ak,
+                         bool bk);                                                               // k_tile_tma.cu
 int k_launch_tf32x3(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB, const Tf32GemmArgs &a, dim3 grid, size_t smem, bool a_mn,
                     bool b_mn); // k_tile_tf32.cu
 int k_launch_reduce(int dtype, cudaStream_t s, bool row, ReduceArgs &a, dim3 grid);              // k_reduce_{real,cplx}.cu

@@ -3,6 +3,8 @@
 // libs/Einsums/Tensor/include/Einsums/Tensor/Backends/DeviceTensor.hpp:33-116 (reference paths).
 #include "common.cuh"
 
+#include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -51,6 +53,27 @@ int        sm_count() {
     }
     return g_sm_count[dev];
 }
+
+// ---------------------------------------------------------------- knobs and introspection
+namespace {
+struct Options {
+    std::atomic<int> v[OPT_COUNT];
+    Options() {
+        auto env = [](const char *n, int dflt) { const char *e = getenv(n); return e ? atoi(e) : dflt; };
+        v[OPT_TMA] = env("EB200_USE_TMA", 1);
+        v[OPT_TMA_GENERIC] = env("EB200_USE_TMA_GENERIC", 1);
+        v[OPT_TMA_TILE] = env("EB200_TMA_TILE", -1);
+    }
+};
+Options &options() {
+    static Options o;
+    return o;
+}
+const char *const kOptionNames[OPT_COUNT] = {"tma", "tma_generic", "tma_tile"};
+thread_local const char *t_last_kernel = "";
+} // namespace
+int  option(int which) { return options().v[which].load(std::memory_order_relaxed); }
+void set_last_kernel(const char *name) { t_last_kernel = name; }
 
 // ---------------------------------------------------------------- stream-ordered scratch
 // Split-K partials, mixed-type widened copies and device-side scalars come from a PRIVATE memory pool per device. The
@@ -314,6 +337,26 @@ int eb200_memset_zero(void *dst, size_t bytes, void *stream) {
     EB_CUDA(cudaMemsetAsync(dst, 0, bytes, as_stream(stream)));
     return EB200_OK;
 }
+
+int eb200_set_option(const char *name, int value) {
+    if (!name) return fail(EB200_ERR_INVALID_ARGUMENT, "eb200_set_option: name is NULL");
+    for (int i = 0; i < OPT_COUNT; i++)
+        if (!strcmp(name, kOptionNames[i])) {
+            options().v[i].store(value, std::memory_order_relaxed);
+            return EB200_OK;
+        }
+    return fail(EB200_ERR_INVALID_ARGUMENT, "eb200_set_option: unknown option '%s'", name);
+}
+int eb200_get_option(const char *name, int *value) {
+    if (!name || !value) return fail(EB200_ERR_INVALID_ARGUMENT, "eb200_get_option: NULL argument");
+    for (int i = 0; i < OPT_COUNT; i++)
+        if (!strcmp(name, kOptionNames[i])) {
+            *value = option(i);
+            return EB200_OK;
+        }
+    return fail(EB200_ERR_INVALID_ARGUMENT, "eb200_get_option: unknown option '%s'", name);
+}
+const char *eb200_last_kernel_name(void) { return t_last_kernel; }
 
 int64_t eb200_launch_count(void) { return launch_counter(); }
 void    eb200_launch_count_reset(void) { launch_counter() = 0; }

@@ -231,3 +231,19 @@ def launch_count() -> int:
 
 def launch_count_reset():
     lib().eb200_launch_count_reset()
+
+
+def set_option(name: str, value: int):
+    """Process-wide tuning / testing knob (eb200_set_option): "tma", "tma_generic", "tma_tile"."""
+    check(lib().eb200_set_option(name.encode(), int(value)))
+
+
+def get_option(name: str) -> int:
+    v = C.c_int(0)
+    check(lib().eb200_get_option(name.encode(), C.byref(v)))
+    return v.value
+
+
+def last_kernel() -> str:
+    """Name of the tile kernel this thread's last contraction launched (eb200_last_kernel_name)."""
+    return lib().eb200_last_kernel_name().decode()

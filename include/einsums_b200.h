@@ -287,6 +287,17 @@ int eb200_contract_host_release(void);
  * descriptor, written to desc->kernel_used. Lets CPU tests pin the planner. */
 int eb200_contract_plan(eb200_contract_desc *desc);
 
+/* Name of the tile kernel the calling thread's last contraction launched ("gemm_tma_f64", "contract_tma_f64<128x64>",
+ * "contract_tma_f64<80x80>", "tile_mma_f64", "gemm_tf32x3_tcgen05", "tile_simt"; "" before the first one). The
+ * descriptor's kernel_used names the family; this names the kernel inside the family. */
+const char *eb200_last_kernel_name(void);
+/* Tuning / testing knobs, process-wide (defaults from EB200_USE_TMA, EB200_USE_TMA_GENERIC, EB200_TMA_TILE):
+ *   "tma"          1 | 0: use / avoid both TMA kernels (0 = cp.async gather kernel everywhere)
+ *   "tma_generic"  1 | 0 | 2: multi-index TMA kernel by the padding rule / never / whenever it is legal
+ *   "tma_tile"     -1 | 0 | 1: automatic / 128x64 / 80x80 tiles in the multi-index TMA kernel */
+int eb200_set_option(const char *name, int value);
+int eb200_get_option(const char *name, int *value);
+
 /* Number of kernel launches enqueued by this thread through this library since the last
  * eb200_launch_count_reset(); bench.py reports it as "gpu_launches". */
 int64_t eb200_launch_count(void);

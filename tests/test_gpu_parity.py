@@ -753,3 +753,117 @@ def test_launch_counter_and_errors(gpu):
     assert gpu.launch_count() >= 1
     with pytest.raises(Eb200Error):
         gpu.gemm("x", "n", 2, 2, 2, 1.0, A, 2, A, 2, 0.0, C, 2)
+
+
+# ---------------------------------------------------------------------------------------------
+# contract_tma_f64: the multi-index TMA kernel (<= 5-D tensor maps, rotating producer, fused split-K, 128x64 and 80x80 tiles)
+@pytest.fixture
+def tma_generic_always(gpu):
+    """Route every contraction the multi-index TMA kernel can legally take through it (ignores the padding-waste rule)."""
+    gpu.set_option("tma_generic", 2)
+    yield gpu
+    gpu.set_option("tma_generic", 1)
+    gpu.set_option("tma_tile", -1)
+
+
+TMA_GENERIC = [
+    # Wmbej: A = t[j,n,f,b] is M-major (b), B = g[m,n,e,f] is K-major (f); two K indices that do not merge; ragged and exact extents
+    ("mbej", "jnfb", "mnef", dict(m=6, b=32, e=48, j=7, n=5, f=32)),
+    ("mbej", "jnfb", "mnef", dict(m=6, b=22, e=18, j=7, n=5, f=24)),
+    # both operands M/N-major with a split M group (a outer, b inner) and an unmergeable K
+    ("abef", "nmef", "mnab", dict(a=9, b=36, e=10, f=34, m=5, n=6)),
+    # both K-major, K = (f inner, e outer) not mergeable because of a padded view is covered by the fuzz test; here a 3-index K
+    ("ij", "ikln", "jnkl", dict(i=70, j=50, k=4, l=18, n=3)),
+    # A K-major / B N-major and the reverse
+    ("ij", "ik", "kj", dict(i=150, j=132, k=100)),
+    ("ij", "ki", "jk", dict(i=150, j=132, k=100)),
+    ("ji", "ik", "kj", dict(i=129, j=70, k=300)),
+    # batch index outermost / innermost in C, carried by both operands (3-D and 4-D maps with a batch coordinate)
+    ("bij", "bik", "bkj", dict(i=65, j=34, k=40, b=5)),
+    ("ijb", "bik", "kbj", dict(i=66, j=33, k=48, b=3)),
+    # two batch indices, target groups of two indices each
+    ("xyabcd", "xyakb", "ykxcd", dict(x=2, y=3, a=5, b=16, c=4, d=20, k=40)),
+]
+
+
+@pytest.mark.parametrize("case", TMA_GENERIC, ids=lambda c: f"{c[0]}<-{c[1]},{c[2]}")
+@pytest.mark.parametrize("tile", [0, 1])
+def test_tma_generic_patterns(tma_generic_always, oracle, case, tile):
+    from einsums_b200 import KF
+    gpu = tma_generic_always
+    gpu.set_option("tma_tile", tile)
+    c_idx, a_idx, b_idx, ext = case
+    for (alpha, beta, sk) in ((0.25, 1.0, 0), (1.0, 0.0, 1), (-0.5, 2.0, 3)):
+        d = run_case(gpu, oracle, c_idx, a_idx, b_idx, ext, np.float64, alpha, beta, force=KF["TILE_MMA"], seed=41, split_k=sk)
+        assert gpu.last_kernel() == ("contract_tma_f64<80x80>" if tile else "contract_tma_f64<128x64>"), (gpu.last_kernel(), case)
+        if sk:
+            assert d.split_k == sk
+
+
+def test_tma_generic_split_k_is_reproducible(tma_generic_always):
+    """Fused split-K: whichever CTA arrives last, the partials are added in split order, so repeated runs are bit-identical."""
+    gpu = tma_generic_always
+    torch.manual_seed(5)
+    A = torch.rand(400, 20000, dtype=torch.float64, device="cuda") - 0.5
+    B = torch.rand(400, 20000, dtype=torch.float64, device="cuda") - 0.5
+    outs = []
+    for rep in range(4):
+        C = torch.zeros(400, 400, dtype=torch.float64, device="cuda")
+        d = gpu.contract("ij", C, "ik", A, "jk", B)
+        assert d.split_k > 1 and gpu.last_kernel().startswith("contract_tma_f64")
+        outs.append(C)
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    ref = A @ B.T
+    assert rel_err(outs[0].cpu().numpy(), ref.cpu().numpy()) <= 1e-12
+
+
+def test_tma_generic_default_routing(gpu, oracle):
+    """Without any knob: Wmbej-like shapes with 16-aligned inner extents and the batched product take the multi-index TMA kernel;
+    the same pattern with tiny inner extents (padding would waste > 12 %) stays on the gather kernel; a plain product without
+    split-K stays on gemm_tma_f64."""
+    run_case(gpu, oracle, "mbej", "jnfb", "mnef", dict(m=6, b=32, e=48, j=7, n=5, f=32), np.float64, -0.5, 1.0)
+    assert gpu.last_kernel() == "contract_tma_f64<128x64>"
+    run_case(gpu, oracle, "mbej", "jnfb", "mnef", dict(m=6, b=21, e=19, j=7, n=5, f=23), np.float64, -0.5, 1.0)
+    assert gpu.last_kernel() == "tile_mma_f64"
+    run_case(gpu, oracle, "bij", "bik", "bkj", dict(i=64, j=64, k=64, b=12), np.float64, 1.0, 0.0)
+    assert gpu.last_kernel() == "contract_tma_f64<128x64>"
+    run_case(gpu, oracle, "ij", "ik", "kj", dict(i=300, j=260, k=64), np.float64, 1.0, 0.0)
+    assert gpu.last_kernel() == "gemm_tma_f64"
+    run_case(gpu, oracle, "ij", "ik", "jk", dict(i=80, j=80, k=4000), np.float64, 1.0, 1.0)   # split-K: fused reduction in the generic kernel
+    assert gpu.last_kernel().startswith("contract_tma_f64")
+
+
+@pytest.mark.parametrize("chunk", range(3))
+def test_tma_generic_fuzz(tma_generic_always, oracle, chunk):
+    """Random contractions (3-6 indices, extents 16-aligned or ragged, random axis orders) through the multi-index TMA kernel
+    whenever it is legal, both tile shapes, against the oracle."""
+    from einsums_b200 import KF
+    gpu = tma_generic_always
+    rng = np.random.default_rng(3000 + chunk)
+    took = 0
+    for n in range(14):
+        letters = "abcdef"
+        nu = int(rng.integers(3, 7))
+        ext = {letters[u]: int(rng.choice([2, 3, 16, 20, 32, 35, 48])) for u in range(nu)}
+        if np.prod([float(v) for v in ext.values()]) > 3e7:
+            continue
+        c, a, b = [], [], []
+        for u in range(nu):
+            where = int(rng.choice([3, 5, 6, 6, 7, 3, 5]))
+            ch = letters[u]
+            if where & 1: c.append(ch)
+            if where & 2: a.append(ch)
+            if where & 4: b.append(ch)
+        if not a or not b or not c:
+            continue
+        for lst in (c, a, b):
+            rng.shuffle(lst)
+        gpu.set_option("tma_tile", int(rng.integers(0, 2)))
+        alpha, beta = [(1.0, 0.0), (0.5, 2.0), (-1.0, 1.0)][int(rng.integers(0, 3))]
+        d = run_case(gpu, oracle, "".join(c), "".join(a), "".join(b), ext, np.float64, alpha, beta, seed=chunk * 50 + n,
+                     split_k=int(rng.choice([0, 0, 2])))
+        if d.kernel_used == KF["TILE_MMA"] and gpu.last_kernel().startswith("contract_tma_f64"):
+            took += 1
+    assert took >= 3, f"only {took} cases reached the multi-index TMA kernel"

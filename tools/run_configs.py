@@ -1,27 +1,41 @@
 #!/usr/bin/env python
-"""Runs the five BASELINE.json configs at their full single-GPU sizes and prints one JSON line per einsum/permute with the
-achieved TFLOP/s or GB/s and the fraction of the measured roofline (FP64 DMMA peak from tools/fp64_peaks, HBM copy peak from
-MEASURED_PEAKS.json). Every timed call is preceded by a parity spot check against torch (float64) on a slice."""
+"""The five BASELINE.json configs at their full single-GPU sizes: one record per einsum / permute with the achieved TFLOP/s
+or GB/s and the fraction of the measured roofline (FP64 DMMA peak from tools/fp64_peaks, HBM copy peak from
+MEASURED_PEAKS.json). Every timed call is preceded by a parity spot check against torch (float64) on a slice.
+
+Importable (bench.py puts these records into its JSON line as "configs") and runnable:
+    python tools/run_configs.py [1 2 3 4]      -> one JSON line per record, then the peaks and the clocks seen during the run
+"""
 import itertools, json, os, subprocess, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import torch
 from einsums_b200 import ops, KF_NAMES
 
-ops.init(0); torch.cuda.set_device(0)
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-try:
-    HBM = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-except Exception:
-    HBM = 6650.0
-try:
-    FP64 = json.loads(subprocess.run([os.path.join(ROOT, "tools", "fp64_peaks")], capture_output=True, text=True).stdout.strip().splitlines()[-1])["dmma_tflops"]
-except Exception:
-    FP64 = 37.1
 
-def rnd(*s): return torch.rand(*s, dtype=torch.float64, device="cuda") * 2 - 1
+def peaks():
+    """(HBM copy GB/s, its source), (FP64 DMMA TFLOP/s, its source)"""
+    try:
+        hbm, hsrc = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    except Exception:
+        hbm, hsrc = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    try:
+        out = subprocess.run([os.path.join(ROOT, "tools", "fp64_peaks")], capture_output=True, text=True, timeout=120).stdout
+        fp64, fsrc = json.loads(out.strip().splitlines()[-1])["dmma_tflops"], "tools/fp64_peaks measured in this run (DMMA issue loop)"
+    except Exception:
+        fp64, fsrc = 148 * 64 * 2 * 1.965e9 / 1e12, "nominal 148 SM x 64 FMA/clk x 1.965 GHz"
+    return hbm, hsrc, fp64, fsrc
+
+
+def rnd(*s):
+    return torch.rand(*s, dtype=torch.float64, device="cuda") * 2 - 1
+
 
 def timeit(fn, warm=2, reps=5):
-    for _ in range(warm): fn()
+    """median of `reps` CUDA-event timings on the current stream; sub-millisecond ops are timed as 20 (or 4) back-to-back launches"""
+    for _ in range(warm):
+        fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); fn(); e1.record(); torch.cuda.synchronize()
@@ -29,19 +43,33 @@ def timeit(fn, warm=2, reps=5):
     ts = []
     for _ in range(reps):
         e0.record()
-        for _ in range(inner): fn()
+        for _ in range(inner):
+            fn()
         e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) / inner)
     return sorted(ts)[len(ts) // 2]
 
-def report(cfg, op, ms, flops=None, nbytes=None, **kw):
-    d = {"config": cfg, "op": op, "ms": round(ms, 4)}
-    if flops: d.update(tflops=round(flops / ms / 1e9, 2), frac_of_fp64_peak=round(flops / ms / 1e9 / FP64, 3))
-    if nbytes: d.update(gbs=round(nbytes / ms / 1e6, 1), frac_of_hbm_copy=round(nbytes / ms / 1e6 / HBM, 3))
-    d.update(kw); print(json.dumps(d), flush=True)
 
-which = sys.argv[1:] or ["1", "2", "3", "4"]
-if "1" in which:
+class Recorder:
+    def __init__(self, hbm, fp64, emit=None):
+        self.hbm, self.fp64, self.records, self.emit = hbm, fp64, [], emit
+
+    def __call__(self, cfg, op, ms, flops=None, nbytes=None, **kw):
+        d = {"config": cfg, "op": op, "ms": round(ms, 4)}
+        if flops:
+            d.update(tflops=round(flops / ms / 1e9, 2), frac_of_fp64_peak=round(flops / ms / 1e9 / self.fp64, 3))
+        if nbytes:
+            d.update(gbs=round(nbytes / ms / 1e6, 1), frac_of_hbm_copy=round(nbytes / ms / 1e6 / self.hbm, 3))
+        d.update(kw)
+        self.add(d)
+
+    def add(self, d):
+        self.records.append(d)
+        if self.emit:
+            self.emit(d)
+
+
+def cfg1(report):
     n = 100
     g, D, J, K = rnd(n, n, n, n), rnd(n, n), rnd(n, n), rnd(n, n)
     ops.contract("pq", J, "pqrs", g, "rs", D, 2.0, 0.0); ops.contract("pq", K, "prqs", g, "rs", D, -1.0, 0.0)
@@ -49,22 +77,33 @@ if "1" in which:
     errK = ((K + torch.einsum("prqs,rs->pq", g, D)).abs().max() / K.abs().max()).item()
     report("cfg1 HF n=100", "J (gemv)", timeit(lambda: ops.contract("pq", J, "pqrs", g, "rs", D, 2.0, 0.0)), 2.0 * n**4, 8.0 * n**4, parity=errJ)
     report("cfg1 HF n=100", "K (generic)", timeit(lambda: ops.contract("pq", K, "prqs", g, "rs", D, -1.0, 0.0)), 2.0 * n**4, 8.0 * n**4, parity=errK)
-    del g
-if "2" in which:
+
+
+def cfg2(report, wabef=True):
     o, v = 20, 200
-    g, t, Wm, Wa = rnd(o, o, v, v), rnd(o, o, v, v), rnd(o, o, o, o), rnd(v, v, v, v)
-    report("cfg2 CCD o=20 v=200", "Wmnij", timeit(lambda: ops.contract("mnij", Wm, "mnef", g, "ijef", t, 0.25, 1.0)), 2.0 * o**4 * v**2)
-    report("cfg2 CCD o=20 v=200", "Wabef", timeit(lambda: ops.contract("abef", Wa, "mnef", g, "mnab", t, 0.25, 1.0), 1, 3), 2.0 * v**4 * o**2)
-    del Wa
-if "3" in which:
+    g, t, Wm = rnd(o, o, v, v), rnd(o, o, v, v), rnd(o, o, o, o)
+    W0 = Wm.clone()
+    d = ops.contract("mnij", Wm, "mnef", g, "ijef", t, 0.25, 1.0)
+    ref = W0 + 0.25 * torch.einsum("mnef,ijef->mnij", g, t)
+    err = ((Wm - ref).abs().max() / ref.abs().max()).item()
+    report("cfg2 CCD o=20 v=200", "Wmnij", timeit(lambda: ops.contract("mnij", Wm, "mnef", g, "ijef", t, 0.25, 1.0)), 2.0 * o**4 * v**2,
+           kernel=ops.last_kernel(), split_k=int(d.split_k), parity=err)
+    if wabef:
+        Wa = rnd(v, v, v, v)
+        report("cfg2 CCD o=20 v=200", "Wabef", timeit(lambda: ops.contract("abef", Wa, "mnef", g, "mnab", t, 0.25, 1.0), 1, 3), 2.0 * v**4 * o**2,
+               kernel=ops.last_kernel())
+        del Wa
+
+
+def cfg3(report, permuted_k=True):
     o, v = 60, 240
     t, g, W = rnd(o, o, v, v), rnd(o, o, v, v), rnd(o, v, v, o)
     W0 = W[:2].clone()
     d = ops.contract("mbej", W, "jnfb", t, "mnef", g, -0.5, 1.0)
     ref = W0 - 0.5 * torch.einsum("jnfb,mnef->mbej", t, g[:2])
     err = ((W[:2] - ref).abs().max() / ref.abs().max()).item()
-    report("cfg3 o=60 v=240", "Wmbej (generic, fused permutation)", timeit(lambda: ops.contract("mbej", W, "jnfb", t, "mnef", g, -0.5, 1.0), 1, 3), 2.0 * o**3 * v**3,
-           kernel=KF_NAMES[d.kernel_used], parity=err)
+    report("cfg3 o=60 v=240", "Wmbej (generic, fused permutation)", timeit(lambda: ops.contract("mbej", W, "jnfb", t, "mnef", g, -0.5, 1.0), 1, 3),
+           2.0 * o**3 * v**3, kernel=ops.last_kernel(), family=KF_NAMES[d.kernel_used], parity=err)
     del t, g, W
     torch.cuda.empty_cache()
     n = 300
@@ -75,21 +114,26 @@ if "3" in which:
     d = ops.contract("pq", K, "prqs", g, "rs", D, -1.0, 0.0)
     ref = -torch.einsum("rqs,rs->q", g[7], D)
     err = ((K[7] - ref).abs().max() / ref.abs().max()).item()
-    report("cfg3 n=300", "Fock K (generic)", timeit(lambda: ops.contract("pq", K, "prqs", g, "rs", D, -1.0, 0.0), 1, 3), 2.0 * n**4, 8.0 * n**4, kernel=KF_NAMES[d.kernel_used], parity=err)
+    report("cfg3 n=300", "Fock K (generic)", timeit(lambda: ops.contract("pq", K, "prqs", g, "rs", D, -1.0, 0.0), 1, 3), 2.0 * n**4, 8.0 * n**4,
+           family=KF_NAMES[d.kernel_used], parity=err)
     report("cfg3 n=300", "Fock J (gemv)", timeit(lambda: ops.contract("pq", J, "pqrs", g, "rs", D, 2.0, 0.0), 1, 3), 2.0 * n**4, 8.0 * n**4)
-    # permuted-K: permute g[p,r,q,s] -> gp[p,q,r,s] then GEMV; 64.8 GB more memory
-    gp = torch.empty(n, n, n, n, dtype=torch.float64, device="cuda")
-    tp = timeit(lambda: ops.permute("pqrs", gp, "prqs", g), 1, 3)
-    Kp = torch.empty(n, n, dtype=torch.float64, device="cuda")
-    tg = timeit(lambda: ops.contract("pq", Kp, "pqrs", gp, "rs", D, -1.0, 0.0), 1, 3)
-    errp = ((Kp - K).abs().max() / K.abs().max()).item()
-    report("cfg3 n=300", "permuted-K: permute", tp, None, 16.0 * n**4)
-    report("cfg3 n=300", "permuted-K: gemv", tg, 2.0 * n**4, 8.0 * n**4, parity_vs_generic=errp)
-    report("cfg3 n=300", "permuted-K: total (permute + gemv)", tp + tg, 2.0 * n**4, None)
-    del g, gp
+    if permuted_k:
+        # permuted-K: permute g[p,r,q,s] -> gp[p,q,r,s] then GEMV; 64.8 GB more memory
+        gp = torch.empty(n, n, n, n, dtype=torch.float64, device="cuda")
+        tp = timeit(lambda: ops.permute("pqrs", gp, "prqs", g), 1, 3)
+        Kp = torch.empty(n, n, dtype=torch.float64, device="cuda")
+        tg = timeit(lambda: ops.contract("pq", Kp, "pqrs", gp, "rs", D, -1.0, 0.0), 1, 3)
+        errp = ((Kp - K).abs().max() / K.abs().max()).item()
+        report("cfg3 n=300", "permuted-K: permute", tp, None, 16.0 * n**4)
+        report("cfg3 n=300", "permuted-K: gemv", tg, 2.0 * n**4, 8.0 * n**4, parity_vs_generic=errp)
+        report("cfg3 n=300", "permuted-K: total (permute + gemv)", tp + tg, 2.0 * n**4, None)
+        del gp
+    del g
     torch.cuda.empty_cache()
-if "4" in which:
-    for n in (64, 96, 128, 160):
+
+
+def cfg4(report, sizes=(64, 96, 128, 160), per_order=True):
+    for n in sizes:
         A, B = rnd(n, n, n, n), torch.empty(n, n, n, n, dtype=torch.float64, device="cuda")
         res = {}
         for order in itertools.permutations(range(4)):
@@ -99,10 +143,33 @@ if "4" in which:
                 assert torch.equal(B, A.permute(*order)), c
             res[c] = round(16.0 * n**4 / timeit(lambda: ops.permute(c, B, "ijkl", A), 1, 3) / 1e6, 1)
         vals = sorted(res.values())
-        print(json.dumps({"config": f"cfg4 permute n={n}", "gbs_min": vals[0], "gbs_median": vals[12], "gbs_max": vals[-1],
-                          "frac_min": round(vals[0] / HBM, 3), "frac_median": round(vals[12] / HBM, 3), "all": res}), flush=True)
+        worst = min(res, key=res.get)
+        rec = {"config": f"cfg4 permute n={n}", "op": "24 rank-4 orders, alpha=1 beta=0 (16 n^4 bytes)", "gbs_min": vals[0], "gbs_median": vals[12],
+               "gbs_max": vals[-1], "frac_min": round(vals[0] / report.hbm, 3), "frac_median": round(vals[12] / report.hbm, 3), "worst_order": worst,
+               "parity": "bit-exact vs torch.permute (n=64, all orders)" if n == 64 else "checked at n=64"}
+        if per_order:
+            rec["all"] = res
+        report.add(rec)
         Bt = torch.rand(n, n, n, n, dtype=torch.float64, device="cuda")
         ms = timeit(lambda: ops.permute("lkji", Bt, "ijkl", A, 0.5, 2.0), 1, 3)
         report(f"cfg4 permute n={n}", "lkji alpha=0.5 beta=2", ms, None, 24.0 * n**4)
         del A, B, Bt
-print(json.dumps({"peaks": {"fp64_dmma_tflops": FP64, "hbm_copy_gbs": HBM}}))
+    torch.cuda.empty_cache()
+
+
+def run_all(which=("1", "2", "3", "4"), emit=None, wabef=True, permuted_k=True, per_order=True):
+    hbm, hsrc, fp64, fsrc = peaks()
+    report = Recorder(hbm, fp64, emit)
+    if "1" in which: cfg1(report)
+    if "2" in which: cfg2(report, wabef)
+    if "3" in which: cfg3(report, permuted_k)
+    if "4" in which: cfg4(report, per_order=per_order)
+    return report.records, {"fp64_dmma_tflops": fp64, "fp64_source": fsrc, "hbm_copy_gbs": hbm, "hbm_source": hsrc}
+
+
+if __name__ == "__main__":
+    from bench import ClockSampler
+    ops.init(0); torch.cuda.set_device(0)
+    sampler = ClockSampler(0); sampler.start()
+    _, pk = run_all(sys.argv[1:] or ("1", "2", "3", "4"), emit=lambda d: print(json.dumps(d), flush=True))
+    print(json.dumps({"peaks": pk, "clocks": sampler.stop()}))
