@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <complex>
+#include <memory>
 
 namespace einsums::tensor_algebra {
 
@@ -320,6 +321,49 @@ template <bool ConjA = false, bool ConjB = false, DeviceTensorContainer CList, D
 void einsum(std::tuple<CIndices...> const &C_indices, CList *C_list, std::tuple<AIndices...> const &A_indices, AList const &A_list,
             std::tuple<BIndices...> const &B_indices, BList const &B_list, detail::AlgorithmChoice *algorithm_choice = nullptr) {
     einsum<ConjA, ConjB>(0.0, C_indices, C_list, 1.0, A_indices, A_list, B_indices, B_list, algorithm_choice);
+}
+
+// ---- smart-pointer operands (reference: TensorAlgebra/TensorAlgebra.hpp:60-124). Any of A, B, C may be a std::shared_ptr /
+// std::unique_ptr to a device tensor (C as a pointer to the smart pointer); the call is forwarded with the pointees.
+template <typename X>
+concept SmartPointer = requires(std::remove_cvref_t<X> const &p) {
+    typename std::remove_cvref_t<X>::element_type;
+    { p.get() };
+    { *p };
+};
+namespace detail {
+template <typename X, bool = SmartPointer<X>> struct DerefType { using type = X; };
+template <typename X> struct DerefType<X, true> { using type = typename X::element_type; };
+template <typename X> using deref_type_t = typename DerefType<std::remove_cvref_t<X>>::type;
+template <typename X> decltype(auto) auto_deref(X const &x) {
+    if constexpr (SmartPointer<X>) {
+        if (!x) throw bad_logic("einsum: null smart pointer passed as an operand");
+        return (*x);
+    } else return (x);
+}
+template <typename X> auto auto_deref_c(X *p) {
+    if constexpr (SmartPointer<X>) {
+        if (!p || !*p) throw bad_logic("einsum: null smart pointer passed as the result");
+        return p->get();
+    } else return p;
+}
+} // namespace detail
+template <bool ConjA = false, bool ConjB = false, typename AType, typename BType, typename CType, typename U, typename... CIndices,
+          typename... AIndices, typename... BIndices>
+    requires((SmartPointer<AType> || SmartPointer<BType> || SmartPointer<CType>) && DeviceTensorLike<detail::deref_type_t<AType>> &&
+             DeviceTensorLike<detail::deref_type_t<BType>> && (std::is_arithmetic_v<U> || IsComplexV<U>))
+void einsum(U const C_prefactor, std::tuple<CIndices...> const &C_indices, CType *C, U const AB_prefactor, std::tuple<AIndices...> const &A_indices,
+            AType const &A, std::tuple<BIndices...> const &B_indices, BType const &B, detail::AlgorithmChoice *algorithm_choice = nullptr) {
+    einsum<ConjA, ConjB>(C_prefactor, C_indices, detail::auto_deref_c(C), AB_prefactor, A_indices, detail::auto_deref(A), B_indices,
+                         detail::auto_deref(B), algorithm_choice);
+}
+template <bool ConjA = false, bool ConjB = false, typename AType, typename BType, typename CType, typename... CIndices, typename... AIndices,
+          typename... BIndices>
+    requires((SmartPointer<AType> || SmartPointer<BType> || SmartPointer<CType>) && DeviceTensorLike<detail::deref_type_t<AType>> &&
+             DeviceTensorLike<detail::deref_type_t<BType>>)
+void einsum(std::tuple<CIndices...> const &C_indices, CType *C, std::tuple<AIndices...> const &A_indices, AType const &A,
+            std::tuple<BIndices...> const &B_indices, BType const &B, detail::AlgorithmChoice *algorithm_choice = nullptr) {
+    einsum<ConjA, ConjB>(C_indices, detail::auto_deref_c(C), A_indices, detail::auto_deref(A), B_indices, detail::auto_deref(B), algorithm_choice);
 }
 
 /// The analyser's decision alone (DryRun of the reference): no data is touched.

@@ -361,6 +361,32 @@ TEST_CASE(gpu_batched_containers) { // Batched.cpp:13-100
     CHECK_THROWS_AS(einsum(Indices{i, j}, &Cs, Indices{i, k}, As, Indices{k, j}, Bs), bad_logic);
 }
 
+TEST_CASE(gpu_smart_pointer_operands) { // TensorAlgebra/TensorAlgebra.hpp:60-124: any of A, B, C behind a smart pointer
+    using namespace einsums::index;
+    auto A = std::make_shared<DeviceTensor<double, 2>>(create_random_gpu_tensor("A", 11, 13));
+    auto B = std::make_unique<DeviceTensor<double, 2>>(create_random_gpu_tensor("B", 13, 5));
+    auto C = std::make_shared<DeviceTensor<double, 2>>("C", 11, 5);
+    DeviceTensor<double, 2> C2{"C2", 11, 5}, C3{"C3", 11, 5};
+    AlgorithmChoice         alg;
+    einsum(Indices{i, j}, &C, Indices{i, k}, A, Indices{k, j}, B, &alg); // all three
+    CHECK(alg == ta::GEMM);
+    einsum(Indices{i, j}, &C2, Indices{i, k}, A, Indices{k, j}, *B);            // only A
+    einsum(0.0, Indices{i, j}, &C3, 1.0, Indices{i, k}, *A, Indices{k, j}, B);  // only B, prefactor form
+    auto hA = host(*A), hB = host(*B), hC = host(*C), hC2 = host(C2), hC3 = host(C3);
+    for (size_t x = 0; x < 11; x++) for (size_t y = 0; y < 5; y++) {
+        double s = 0;
+        for (size_t k0 = 0; k0 < 13; k0++) s += hA(x, k0) * hB(k0, y);
+        CHECK_CLOSE(hC(x, y), s, 1e-12);
+        CHECK(hC2(x, y) == hC(x, y));
+        CHECK(hC3(x, y) == hC(x, y));
+    }
+    einsum(1.0, Indices{i, j}, &C, 2.0, Indices{i, k}, A, Indices{k, j}, B); // accumulate through the smart-pointer C
+    auto hC4 = host(*C);
+    for (size_t x = 0; x < 11; x++) for (size_t y = 0; y < 5; y++) CHECK_CLOSE(hC4(x, y), 3.0 * hC(x, y), 1e-12);
+    std::shared_ptr<DeviceTensor<double, 2>> none;
+    CHECK_THROWS_AS(einsum(Indices{i, j}, &C2, Indices{i, k}, none, Indices{k, j}, *B), bad_logic);
+}
+
 TEST_CASE(gpu_permute) { // Sort.cpp:18-250, GPUTensorAlgebra.hip:591-838
     using namespace einsums::index;
     auto A = create_random_gpu_tensor("A", 3, 4, 5, 6);

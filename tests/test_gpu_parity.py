@@ -772,8 +772,9 @@ TMA_GENERIC = [
     ("mbej", "jnfb", "mnef", dict(m=6, b=22, e=18, j=7, n=5, f=24)),
     # both operands M/N-major with a split M group (a outer, b inner) and an unmergeable K
     ("abef", "nmef", "mnab", dict(a=9, b=36, e=10, f=34, m=5, n=6)),
-    # both K-major, K = (f inner, e outer) not mergeable because of a padded view is covered by the fuzz test; here a 3-index K
-    ("ij", "ikln", "jnkl", dict(i=70, j=50, k=4, l=18, n=3)),
+    # both K-major with the SAME inner contracted index (l) and two outer ones in opposite order (k, n do not merge): a 3-index K.
+    # (A = [i,k,l,n] with n = 3 would have odd element strides: byte strides not multiples of 16, no tensor map -> gather kernel)
+    ("ij", "iknl", "jnkl", dict(i=70, j=50, k=4, l=18, n=3)),
     # A K-major / B N-major and the reverse
     ("ij", "ik", "kj", dict(i=150, j=132, k=100)),
     ("ij", "ki", "jk", dict(i=150, j=132, k=100)),
