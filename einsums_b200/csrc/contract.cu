@@ -79,17 +79,6 @@ int g_mma_config = 0; // 0 = auto; 1 = 128x128 (1 CTA/SM); 2 = 128x64 (2 CTA/SM)
 std::once_flag g_cfg_once;
 
 // ---------------------------------------------------------------- TMA fast path (plain FP64 GEMM)
-using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
-                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = [] {
-        void                           *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
-        return (EncodeTiledFn)p;
-    }();
-    return fn;
-}
 // tuning / testing knobs (eb200_set_option, defaults from the environment): tma = 0 disables both TMA kernels; tma_generic = 0
 // disables the multi-index one, 2 takes it whenever it is legal (ignores the padding-waste rule); tma_tile = 0 / 1 forces 128x64 / 80x80
 
@@ -260,6 +249,10 @@ int try_run_tma_generic(cudaStream_t s, const Plan &p, eb200_contract_desc &d, c
     a.C = (double *)d.C.data;
     a.alpha = d.alpha[0]; a.beta = beta_eff[0];
     a.vec_c = operand_pairs_ok(p, ROLE_C, p.n, p.m, a.C) ? 1 : 0;
+    {
+        const int stages = ch.cfg ? TmaTile80x80::STAGES : TmaTile128x64::STAGES, want = option(OPT_TMA_DIST);
+        a.dist = (want >= 1 && want < stages) ? want : (stages >= 4 ? stages - 2 : stages - 1);
+    }
     const int64_t tiles = ch.tm * ch.tn, per_launch = std::min<int64_t>(65535, p.b.tot);
     const size_t  tile_elems = ch.cfg ? 80 * 80 : 128 * 64;
     void         *ws = nullptr;

@@ -38,6 +38,7 @@ struct TmaGenArgs {
     unsigned int *counters;  // [batch in launch][tile], zeroed by the host before the launch
     double        alpha, beta;
     int32_t       splits, tiles_m, tiles_n, vec_c;
+    int32_t       dist;      // prefetch distance in k steps (1 .. STAGES-1)
     int32_t       em[TG_MAXI], en[TG_MAXI], ek[TG_MAXI], eb[TG_MAXI]; // extents, inner first (unused slots = 1)
     int32_t       mblk0, nblk0, kstep0;                                // 16-blocks along the inner M / N / K index
     int32_t       KT;                                                  // composite k steps = kstep0 * ek[1] * ek[2]
@@ -48,11 +49,6 @@ struct TmaGenArgs {
     int64_t       batch0;                                              // first batch of this launch (grid.z <= 65535)
 };
 
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
-                 "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-                 : "memory");
-}
 __device__ __forceinline__ double2 ld_cg_f64x2(const double2 *p) {
     double2 v;
     asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
@@ -208,8 +204,12 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_tma_f64(const __g
             if (++k1 == args.ek[1]) { k1 = 0; ++k2; }
         }
     };
+    // Prefetch distance: the loads of step it + dist are issued while step it is consumed. dist = STAGES - 1 keeps every stage busy but
+    // makes the duty lane wait until the SLOWEST warp has left step it - 1, every step (ncu: 22 % of the samples in that spin, tensor
+    // pipe 85 %); dist = STAGES - 2 refills the stage everybody left one step earlier, so the wait is over before it starts.
+    const int dist = args.dist;
     if (lane == 0)
-        while (my_step < STAGES - 1 && my_step < nsteps) issue_my_step(); // prologue: the first STAGES-1 steps
+        while (my_step < dist && my_step < nsteps) issue_my_step(); // prologue: the first `dist` steps
 
     // ===================== consumers =====================
     const int wm0 = (warp % CFG::WARPS_M) * WM, wn0 = (warp / CFG::WARPS_M) * WN;
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_tma_f64(const __g
 
     for (int it = 0; it < nsteps; it++) {
         const int s = it % STAGES;
-        if (lane == 0 && my_step == it + STAGES - 1 && my_step < nsteps) issue_my_step(); // refills the stage everybody left at it-1
+        if (lane == 0 && my_step == it + dist && my_step < nsteps) issue_my_step(); // refills the stage everybody left at it + dist - STAGES
         __syncwarp();
         mbar_wait(full_bar(s), (it / STAGES) & 1);
         const uint32_t a_base = smem_base + s * STAGE_BYTES, b_base = a_base + A_BYTES;

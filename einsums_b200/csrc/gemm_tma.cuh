@@ -18,6 +18,7 @@
 #include <cuda.h>
 
 #include "contract_kernels.cuh"
+#include "tma_util.cuh"
 
 namespace eb200 {
 
@@ -28,35 +29,6 @@ struct TmaGemmArgs {
     double  alpha, beta;
     int32_t tiles_m, tiles_n, vec_c;
 };
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map),
-                 "r"(bar), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ double lds_f64(uint32_t addr) {
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-    return v;
-}
 
 template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(256, 2) gemm_tma_f64(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,

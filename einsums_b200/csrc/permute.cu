@@ -7,10 +7,13 @@
 // Method: axes are sorted by A stride and merged where A and C agree on contiguity; then
 //   * if the fastest axis of A is also the fastest axis of C -> row kernel (both sides coalesced,
 //     16-byte accesses when alignment allows);
-//   * otherwise -> 2-D tile transpose through padded shared memory over the plane spanned by
+//   * otherwise -> 2-D tile transpose through shared memory over the plane spanned by
 //     (fastest axis of A, fastest axis of C); both the read and the write are coalesced, all other
-//     axes are decoded once per tile.
+//     axes are decoded once per tile. FP64 overwrites (beta == 0) stage the tile with the Tensor Memory
+//     Accelerator (permute_tma_f64: one <= 5-D tensor map over A, 128-byte-swizzled boxes, tile extents
+//     fitted to the axis extents so that rows stay long: 80 x 80 for 160, 96 x 96 for 96).
 #include "plan.cuh"
+#include "tma_util.cuh"
 
 #include <algorithm>
 #include <vector>
@@ -321,6 +324,134 @@ template <typename T, bool CONJ, int VEC, bool HAS_BETA> __global__ void __launc
     }
 }
 
+
+// ---------------------------------------------------------------- TMA-staged plane transpose (FP64, beta == 0)
+// One CTA moves one TA x TC tile of the (a, c) plane: lane 0 issues TA/16 bulk tensor loads (boxes of 16 a x TC c, 128-byte rows,
+// hardware swizzle) against one mbarrier; the 8 warps then read the tile TRANSPOSED (ld.shared.v2.f64 of two consecutive a for 32
+// consecutive c: conflict-free under the swizzle) and store rows of C with lanes along c. No thread computes an A address, edge
+// tiles are clipped by the TMA unit (out-of-range elements arrive as zeros and are never stored), and tile extents are run-time
+// values fitted to the extents (ncu, n = 160: 64-tiles leave 256-byte row fragments and reach 69 % of DRAM cycles; see profiles/r2).
+struct PermTmaArgs {
+    int64_t  ea, ec, sc_a;     // extents of the plane axes; C stride of axis a (C stride of axis c is 1)
+    int64_t  rext[3], rsc[3];  // remaining axes: extents and C strides (tensor-map dimensions 2..4 in the same order)
+    double  *C;
+    double   alpha;
+    int32_t  ta, tc, tiles_a, tiles_c;
+};
+
+__global__ void __launch_bounds__(256, 3) permute_tma_f64(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ PermTmaArgs a) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = ((uint32_t)__cvta_generic_to_shared(smem_dyn) + 1023u) & ~1023u;
+    const int      tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t box_bytes = (uint32_t)a.tc * 128u, bar = base + (uint32_t)(a.ta >> 4) * box_bytes;
+
+    uint32_t t = blockIdx.x;
+    const uint32_t ti_a = t % (uint32_t)a.tiles_a; t /= (uint32_t)a.tiles_a;
+    const uint32_t ti_c = t % (uint32_t)a.tiles_c; t /= (uint32_t)a.tiles_c;
+    const uint32_t r0 = t % (uint32_t)a.rext[0]; t /= (uint32_t)a.rext[0];
+    const uint32_t r1 = t % (uint32_t)a.rext[1]; t /= (uint32_t)a.rext[1];
+    const uint32_t r2 = t;
+    const int64_t  a0 = (int64_t)ti_a * a.ta, c0 = (int64_t)ti_c * a.tc;
+    const int      na = (int)min((int64_t)a.ta, a.ea - a0), nc = (int)min((int64_t)a.tc, a.ec - c0); // valid part of the tile (na is even)
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int nbox = (na + 15) >> 4;
+        mbar_expect_tx(bar, (uint32_t)nbox * box_bytes);
+        for (int b = 0; b < nbox; b++) tma_load_5d(base + b * box_bytes, &tmA, bar, (int)a0 + 16 * b, (int)c0, (int)r0, (int)r1, (int)r2);
+    }
+    __syncthreads();
+    double *C = a.C + (int64_t)r0 * a.rsc[0] + (int64_t)r1 * a.rsc[1] + (int64_t)r2 * a.rsc[2] + a0 * a.sc_a + c0;
+    const double alpha = a.alpha;
+    const bool   plain = alpha == 1.0;
+    mbar_wait(bar, 0);
+    for (int p = warp; 2 * p < na; p += 8) { // rows 2p, 2p + 1 of the tile (axis a)
+        const uint32_t row = base + (uint32_t)(p >> 3) * box_bytes;
+        const uint32_t chunk = (uint32_t)(p & 7);
+        double        *dst = C + (int64_t)(2 * p) * a.sc_a;
+#pragma unroll 4
+        for (int c = lane; c < nc; c += 32) {
+            double2 v = lds_f64x2(row + (uint32_t)c * 128u + ((chunk ^ ((uint32_t)c & 7u)) << 4));
+            if (!plain) { v.x *= alpha; v.y *= alpha; }
+            dst[c] = v.x;
+            dst[c + a.sc_a] = v.y;
+        }
+    }
+}
+
+// tile extent for an axis of extent e: as few tiles as possible of at most 128, equal sizes, rounded up to a multiple of q
+inline int64_t perm_tma_tile(int64_t e, int64_t q) {
+    const int64_t nt = (e + 127) / 128, t = (e + nt - 1) / nt;
+    return (t + q - 1) / q * q;
+}
+
+// returns 1 when the TMA kernel ran, 0 when the layout does not qualify, < 0 on error
+int try_permute_tma(cudaStream_t s, const std::vector<int64_t> &ext, const std::vector<int64_t> &sa, const std::vector<int64_t> &sc, size_t ia, size_t ic,
+                    const double *A, double *C, double alpha, int mode) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    const size_t  n = ext.size();
+    if (!enc || n > 5 || n < 2) return 0;
+    PermTmaArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    cuuint64_t gdim[5] = {1, 1, 1, 1, 1}, gstr[4];
+    cuuint32_t box[5] = {16, 1, 1, 1, 1}, es[5] = {1, 1, 1, 1, 1};
+    int64_t    span = 2;
+    for (size_t i = 0; i < n; i++) {
+        if (ext[i] >= (1LL << 31) || sa[i] <= 0 || sa[i] >= (1LL << 36)) return 0;
+        span = std::max(span, sa[i] * ext[i]);
+    }
+    pa.ea = ext[ia]; pa.ec = ext[ic]; pa.sc_a = sc[ia];
+    gdim[0] = (cuuint64_t)ext[ia];
+    gdim[1] = (cuuint64_t)ext[ic];
+    gstr[0] = (cuuint64_t)sa[ic] * 8;
+    int     d = 2;
+    int64_t rest_tot = 1;
+    for (int k = 0; k < 3; k++) pa.rext[k] = 1;
+    for (size_t i = 0; i < n; i++) {
+        if (i == ia || i == ic) continue;
+        gdim[d] = (cuuint64_t)ext[i];
+        gstr[d - 1] = (cuuint64_t)sa[i] * 8;
+        pa.rext[d - 2] = ext[i];
+        pa.rsc[d - 2] = sc[i];
+        rest_tot *= ext[i];
+        d++;
+    }
+    for (; d < 5; d++) gstr[d - 1] = (cuuint64_t)((span + 1) & ~1LL) * 8; // unused dimensions: extent 1, coordinate 0
+    for (int k = 0; k < 4; k++)
+        if (gstr[k] >= (1ULL << 40) || (gstr[k] & 15)) return 0;
+    int64_t ta = perm_tma_tile(pa.ea, 16), tc = perm_tma_tile(pa.ec, 8);
+    while (ta * tc > 9216) { // 72 KB: three CTAs per SM
+        if (ta >= tc) ta = ((ta / 2) + 15) / 16 * 16;
+        else tc = ((tc / 2) + 7) / 8 * 8;
+    }
+    // measured over the 24 rank-4 orders (profiles/r2): n = 96: 5.09 -> 6.24 TB/s worst order, n = 160: 5.35 -> 5.93, n = 128: 6.14 -> 6.27,
+    // n = 64: equal within 2 % -- so whenever the layout has a tensor map this kernel is the one (mode 1 and 2 are the same today)
+    (void)mode;
+    box[1] = (cuuint32_t)tc;
+    pa.ta = (int32_t)ta; pa.tc = (int32_t)tc;
+    const int64_t tiles_a = (pa.ea + ta - 1) / ta, tiles_c = (pa.ec + tc - 1) / tc, ntiles = tiles_a * tiles_c * rest_tot;
+    if (ntiles > 0x7fffffffLL) return 0;
+    pa.tiles_a = (int32_t)tiles_a; pa.tiles_c = (int32_t)tiles_c;
+    pa.C = C; pa.alpha = alpha;
+    CUtensorMap tm;
+    if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void *)A, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 0;
+    const size_t smem = (size_t)ta * tc * 8 + 1024 + 16;
+    static bool  attr_set = false; // per process; the attribute is per function and device-independent in value
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(permute_tma_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, 9216 * 8 + 1024 + 16);
+        if (e != cudaSuccess) return -cuda_fail(e, "cudaFuncSetAttribute(permute_tma_f64)");
+        attr_set = true;
+    }
+    permute_tma_f64<<<(unsigned)ntiles, 256, smem, s>>>(tm, pa);
+    launch_counter()++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return -cuda_fail(e, "permute_tma_f64");
+    return 1;
+}
+
 struct Axis { int64_t ext, sa, sc; };
 
 template <typename T>
@@ -352,6 +483,17 @@ int permute_impl(void *stream, int rank, const int64_t *dimsA, const int64_t *st
         } else i++;
     }
     if (ax.empty()) ax.push_back({1, 1, 1}); // scalar / all-ones tensor
+    // a plain contiguous copy merges into ONE axis; the 2-D patch kernel (8 independent 16-byte loads per thread, 6.8 TB/s) wants two:
+    // split off an inner run of 128..4096 elements when the extent allows it (the 1-D row kernel measured 6.1-6.3 TB/s here)
+    if (ax.size() == 1 && ax[0].sa == 1 && ax[0].sc == 1 && ax[0].ext >= (1 << 16)) {
+        for (int64_t inner = 4096; inner >= 128; inner >>= 1)
+            if (ax[0].ext % inner == 0) {
+                const int64_t outer = ax[0].ext / inner;
+                ax[0].ext = inner;
+                ax.push_back({outer, inner, inner});
+                break;
+            }
+    }
 
     PermArgs pa;
     memset(&pa, 0, sizeof(pa));
@@ -447,6 +589,16 @@ int permute_impl(void *stream, int rank, const int64_t *dimsA, const int64_t *st
                           ((uintptr_t)A % (2 * sizeof(T)) == 0) && ((uintptr_t)C % (2 * sizeof(T)) == 0);
             for (int i = 0; i < pa.rest.n && vec_ok; i++)
                 if (pa.rest.s[ROLE_A][i] % 2 || pa.rest.s[ROLE_C][i] % 2) vec_ok = false;
+            if constexpr (std::is_same_v<T, double>) {
+                const int mode = option(OPT_PERMUTE_TMA);
+                if (vec_ok && mode != 0 && is_zero(beta) && ax.size() <= 5 && ((uintptr_t)A % 16) == 0) {
+                    std::vector<int64_t> e_, sa_, sc_;
+                    for (auto &x : ax) { e_.push_back(x.ext); sa_.push_back(x.sa); sc_.push_back(x.sc); }
+                    const int r = try_permute_tma(s, e_, sa_, sc_, ia, ic, A, C, alpha, mode);
+                    if (r == 1) return EB200_OK;
+                    if (r < 0) return -r;
+                }
+            }
             if (vec_ok) {
                 pa.tiles_a = (pa.ea + 63) / 64;
                 pa.tiles_c = (pa.ec + 63) / 64;

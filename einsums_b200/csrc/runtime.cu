@@ -63,13 +63,15 @@ struct Options {
         v[OPT_TMA] = env("EB200_USE_TMA", 1);
         v[OPT_TMA_GENERIC] = env("EB200_USE_TMA_GENERIC", 1);
         v[OPT_TMA_TILE] = env("EB200_TMA_TILE", -1);
+        v[OPT_TMA_DIST] = env("EB200_TMA_DIST", 0);
+        v[OPT_PERMUTE_TMA] = env("EB200_PERMUTE_TMA", 1);
     }
 };
 Options &options() {
     static Options o;
     return o;
 }
-const char *const kOptionNames[OPT_COUNT] = {"tma", "tma_generic", "tma_tile"};
+const char *const kOptionNames[OPT_COUNT] = {"tma", "tma_generic", "tma_tile", "tma_dist", "permute_tma"};
 thread_local const char *t_last_kernel = "";
 } // namespace
 int  option(int which) { return options().v[which].load(std::memory_order_relaxed); }
@@ -297,6 +299,28 @@ int eb200_free_host(void *ptr) {
     EB_CUDA(cudaFreeHost(ptr));
     return EB200_OK;
 }
+int eb200_host_register(void *ptr, size_t bytes, void **dev_ptr) {
+    if (!ptr || !dev_ptr) return fail(EB200_ERR_INVALID_ARGUMENT, "eb200_host_register: NULL");
+    *dev_ptr = nullptr;
+    if (bytes == 0) return EB200_OK;
+    EB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterMapped));
+    cudaError_t e = cudaHostGetDevicePointer(dev_ptr, ptr, 0);
+    if (e != cudaSuccess) {
+        cudaHostUnregister(ptr);
+        return cuda_fail(e, "cudaHostGetDevicePointer");
+    }
+    return EB200_OK;
+}
+int eb200_host_unregister(void *ptr) {
+    if (!ptr) return EB200_OK;
+    EB_CUDA(cudaHostUnregister(ptr));
+    return EB200_OK;
+}
+int eb200_host_get_device_pointer(void *host_ptr, void **dev_ptr) {
+    if (!host_ptr || !dev_ptr) return fail(EB200_ERR_INVALID_ARGUMENT, "eb200_host_get_device_pointer: NULL");
+    EB_CUDA(cudaHostGetDevicePointer(dev_ptr, host_ptr, 0));
+    return EB200_OK;
+}
 int eb200_mem_get_info(size_t *free_bytes, size_t *total_bytes) {
     size_t f = 0, t = 0;
     EB_CUDA(cudaMemGetInfo(&f, &t));
@@ -307,29 +331,29 @@ int eb200_mem_get_info(size_t *free_bytes, size_t *total_bytes) {
 
 int eb200_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream) {
     if (bytes == 0) return EB200_OK;
-    EB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, as_stream(stream)));
+    EB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, as_stream(stream)));
     EB_CUDA(cudaStreamSynchronize(as_stream(stream)));
     return EB200_OK;
 }
 int eb200_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream) {
     if (bytes == 0) return EB200_OK;
-    EB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
+    EB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, as_stream(stream)));
     EB_CUDA(cudaStreamSynchronize(as_stream(stream)));
     return EB200_OK;
 }
 int eb200_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream) {
     if (bytes == 0) return EB200_OK;
-    EB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    EB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, as_stream(stream)));
     return EB200_OK;
 }
 int eb200_memcpy_h2d_async(void *dst, const void *src, size_t bytes, void *stream) {
     if (bytes == 0) return EB200_OK;
-    EB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, as_stream(stream)));
+    EB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, as_stream(stream)));
     return EB200_OK;
 }
 int eb200_memcpy_d2h_async(void *dst, const void *src, size_t bytes, void *stream) {
     if (bytes == 0) return EB200_OK;
-    EB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
+    EB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, as_stream(stream)));
     return EB200_OK;
 }
 int eb200_memset_zero(void *dst, size_t bytes, void *stream) {

@@ -5,6 +5,7 @@
 // Differences by design: dims/strides are passed to kernels by value (no device-side copies, no per-view
 // hipMalloc + hipMemcpy + device sync); storage comes from eb200_malloc.
 #pragma once
+#include <Einsums/B200/HostTensor.hpp>
 #include <Einsums/B200/Runtime.hpp>
 
 #include <array>
@@ -260,9 +261,23 @@ template <typename T, size_t R> class DeviceTensor : public detail::DeviceTensor
         EB200_CHECK(eb200_memcpy_d2d(this->_data, o._data, sizeof(T) * this->size(), gpu::get_stream()));
         gpu::stream_wait();
     }
-    DeviceTensor(DeviceTensor &&o) noexcept : Base(o), _mode(o._mode) { o._data = nullptr; }
+    DeviceTensor(DeviceTensor &&o) noexcept : Base(o), _mode(o._mode), _host_data(o._host_data), _gpu_dims(o._gpu_dims), _gpu_strides(o._gpu_strides) {
+        o._data = nullptr;
+        o._host_data = nullptr;
+        o._gpu_dims = o._gpu_strides = nullptr;
+    }
     /// dense copy of a view
     explicit DeviceTensor(DeviceTensorView<T, R> const &v);
+    /// from a host tensor of either storage order (reference: DeviceTensor(Tensor<T, rank> const &, mode = MAPPED),
+    /// T/DeviceTensor.hpp:1097); the device copy is always row-major
+    template <HostTensorLike H>
+        requires(std::remove_cvref_t<H>::Rank == R)
+    explicit DeviceTensor(H const &host, detail::HostToDeviceMode mode = detail::MAPPED) : _mode(mode) {
+        this->_name = host.name();
+        for (size_t i = 0; i < R; i++) this->_dims[i] = host.dim(i);
+        allocate();
+        *this = host;
+    }
     DeviceTensor &operator=(DeviceTensor const &o) {
         if (this == &o) return *this;
         if (this->_dims != o._dims) {
@@ -279,9 +294,102 @@ template <typename T, size_t R> class DeviceTensor : public detail::DeviceTensor
             release();
             static_cast<Base &>(*this) = o;
             _mode = o._mode;
+            _host_data = o._host_data;
+            _gpu_dims = o._gpu_dims;
+            _gpu_strides = o._gpu_strides;
             o._data = nullptr;
+            o._host_data = nullptr;
+            o._gpu_dims = o._gpu_strides = nullptr;
         }
         return *this;
+    }
+    /// A = hostTensor with a layout change when the host tensor is not dense row-major (reference: T/Backends/DeviceTensor.hpp:
+    /// 1010-1090 — raw upload, then the copy_to_tensor kernel with both stride sets). Shapes must agree (reference resizes only
+    /// an uninitialised tensor; here a default-constructed one takes the host tensor's shape).
+    template <HostTensorLike H>
+        requires(std::remove_cvref_t<H>::Rank == R)
+    DeviceTensor &operator=(H const &host) {
+        bool same = true;
+        for (size_t i = 0; i < R; i++) same = same && this->_dims[i] == host.dim(i);
+        if (!same) {
+            if (this->_data) throw dimension_error("DeviceTensor = host tensor: shapes differ");
+            release();
+            for (size_t i = 0; i < R; i++) this->_dims[i] = host.dim(i);
+            allocate();
+        }
+        if (this->size() == 0) return *this;
+        Stride<R> hs;
+        bool      dense_rm = true;
+        std::int64_t expect = 1, lo = 0, hi = 0;
+        for (std::ptrdiff_t i = std::ptrdiff_t(R) - 1; i >= 0; i--) {
+            hs[i] = host.stride(i);
+            if (host.dim(i) != 1 && hs[i] != expect) dense_rm = false;
+            expect *= host.dim(i);
+            (hs[i] < 0 ? lo : hi) += (host.dim(i) - 1) * hs[i];
+        }
+        if (dense_rm) {
+            if (_host_data) {
+                gpu::stream_wait();
+                std::memcpy(_host_data, host.data(), sizeof(T) * size_t(this->size()));
+            } else EB200_CHECK(eb200_memcpy_h2d(this->_data, host.data(), sizeof(T) * size_t(this->size()), gpu::get_stream()));
+            return *this;
+        }
+        // raw upload of the span the host tensor occupies, then one strided copy into the row-major device layout
+        const size_t span = size_t(hi - lo + 1);
+        typename Base::DeviceScratch tmp(sizeof(T) * span);
+        EB200_CHECK(eb200_memcpy_h2d(tmp.ptr, host.data() + lo, sizeof(T) * span, gpu::get_stream()));
+        EB200_CHECK(eb200_copy_strided(gpu::get_stream(), detail::DTypeOf<T>::value, int(R), this->_dims.data(), static_cast<T *>(tmp.ptr) - lo, hs.data(),
+                                       this->_data, this->_strides.data()));
+        gpu::stream_wait();
+        return *this;
+    }
+    /// hostTensor = A: the inverse conversion (reference: Tensor<T, rank>(DeviceTensor) / DeviceTensor::operator Tensor, :1099-1104)
+    template <HostTensorLike H>
+        requires(std::remove_cvref_t<H>::Rank == R)
+    void copy_to(H *host) const {
+        for (size_t i = 0; i < R; i++)
+            if (this->_dims[i] != host->dim(i)) throw dimension_error("DeviceTensor -> host tensor: shapes differ");
+        if (this->size() == 0) return;
+        Stride<R>    hs;
+        bool         dense_rm = true;
+        std::int64_t expect = 1, lo = 0, hi = 0;
+        for (std::ptrdiff_t i = std::ptrdiff_t(R) - 1; i >= 0; i--) {
+            hs[i] = host->stride(i);
+            if (host->dim(i) != 1 && hs[i] != expect) dense_rm = false;
+            expect *= host->dim(i);
+            (hs[i] < 0 ? lo : hi) += (host->dim(i) - 1) * hs[i];
+        }
+        if (dense_rm) {
+            this->write(host->data());
+            return;
+        }
+        const size_t span = size_t(hi - lo + 1);
+        if (span != size_t(this->size())) throw tensor_compat_error("DeviceTensor -> host tensor: the host tensor must be dense (any axis order)");
+        typename Base::DeviceScratch tmp(sizeof(T) * span);
+        gpu::stream_wait();
+        EB200_CHECK(eb200_copy_strided(gpu::get_stream(), detail::DTypeOf<T>::value, int(R), this->_dims.data(), this->_data, this->_strides.data(),
+                                       static_cast<T *>(tmp.ptr) - lo, hs.data()));
+        EB200_CHECK(eb200_memcpy_d2h(host->data() + lo, tmp.ptr, sizeof(T) * span, gpu::get_stream()));
+    }
+    explicit operator Tensor<T, R>() const {
+        Tensor<T, R> out = make_host(std::make_index_sequence<R>{});
+        copy_to(&out);
+        return out;
+    }
+
+    /// host-side storage of a MAPPED / PINNED tensor (nullptr for DEV_ONLY); reference T/DeviceTensor.hpp:614-627
+    T                       *data() { return _host_data; }
+    T const                 *data() const { return _host_data; }
+    detail::HostToDeviceMode mode() const { return _mode; }
+    /// dims / strides as device-resident size_t arrays for user kernels (reference T/DeviceTensor.hpp:1000-1053). The backend's own
+    /// kernels take them by value, so the device copies are made on first request only.
+    size_t const *gpu_dims() const {
+        ensure_gpu_meta();
+        return _gpu_dims;
+    }
+    size_t const *gpu_strides() const {
+        ensure_gpu_meta();
+        return _gpu_strides;
     }
     DeviceTensor &operator=(std::vector<T> const &host) {
         this->read(host);
@@ -310,6 +418,8 @@ template <typename T, size_t R> class DeviceTensor : public detail::DeviceTensor
     auto operator()(Args... args);
 
   private:
+    /// storage by mode (reference: T/Backends/DeviceTensor.hpp:62-116): DEV_ONLY = device memory under the byte budget; PINNED = page-locked
+    /// host memory the device reads in place; MAPPED = ordinary host memory registered with the driver and aliased on the device
     void allocate() {
         std::int64_t acc = 1;
         for (std::ptrdiff_t i = std::ptrdiff_t(R) - 1; i >= 0; i--) {
@@ -318,20 +428,68 @@ template <typename T, size_t R> class DeviceTensor : public detail::DeviceTensor
             acc *= this->_dims[i];
         }
         (void)gpu::get_stream(); // makes sure the runtime is up
-        void *p = nullptr;
-        EB200_CHECK(eb200_malloc(&p, sizeof(T) * size_t(acc)));
+        void        *p = nullptr;
+        const size_t bytes = sizeof(T) * size_t(acc);
+        switch (_mode) {
+        case detail::DEV_ONLY:
+            EB200_CHECK(eb200_malloc(&p, bytes));
+            break;
+        case detail::PINNED: {
+            void *h = nullptr;
+            EB200_CHECK(eb200_malloc_host(&h, bytes ? bytes : sizeof(T)));
+            int rc = eb200_host_get_device_pointer(h, &p);
+            if (rc) {
+                eb200_free_host(h);
+                EB200_CHECK(rc);
+            }
+            _host_data = static_cast<T *>(h);
+            break;
+        }
+        case detail::MAPPED: {
+            T  *h = new T[acc ? size_t(acc) : 1]();
+            int rc = eb200_host_register(h, bytes ? bytes : sizeof(T), &p);
+            if (rc) {
+                delete[] h;
+                EB200_CHECK(rc);
+            }
+            _host_data = h;
+            break;
+        }
+        default: throw uninitialized_error("DeviceTensor: unknown host-to-device mode");
+        }
         this->_data = static_cast<T *>(p);
     }
     void release() {
-        if (this->_data) {
-            eb200_device_synchronize();
-            eb200_free(this->_data);
-            this->_data = nullptr;
-        }
+        if (this->_data || _host_data || _gpu_dims) eb200_device_synchronize();
+        if (_mode == detail::PINNED && _host_data) eb200_free_host(_host_data);
+        else if (_mode == detail::MAPPED && _host_data) {
+            eb200_host_unregister(_host_data);
+            delete[] _host_data;
+        } else if (this->_data) eb200_free(this->_data);
+        if (_gpu_dims) eb200_free(_gpu_dims);
+        this->_data = nullptr;
+        _host_data = nullptr;
+        _gpu_dims = _gpu_strides = nullptr;
     }
+    void ensure_gpu_meta() const {
+        if (_gpu_dims) return;
+        void  *p = nullptr;
+        size_t host[2 * (R ? R : 1)];
+        for (size_t i = 0; i < R; i++) {
+            host[i] = size_t(this->_dims[i]);
+            host[R + i] = size_t(this->_strides[i]);
+        }
+        EB200_CHECK(eb200_malloc(&p, sizeof(host)));
+        EB200_CHECK(eb200_memcpy_h2d(p, host, sizeof(host), gpu::get_stream()));
+        _gpu_dims = static_cast<size_t *>(p);
+        _gpu_strides = _gpu_dims + R;
+    }
+    template <size_t... I> Tensor<T, R> make_host(std::index_sequence<I...>) const { return Tensor<T, R>(true, this->_name, this->_dims[I]...); }
     void scale_inplace(T s);
     void axpy_inplace(T a, DeviceTensor const &x);
     detail::HostToDeviceMode _mode = detail::DEV_ONLY;
+    T                       *_host_data = nullptr;
+    mutable size_t          *_gpu_dims = nullptr, *_gpu_strides = nullptr;
 };
 
 /// Rank-0 tensor: one element on the device, convertible to and assignable from its value type.

@@ -123,6 +123,12 @@ int eb200_set_memory_budget(size_t bytes);
 int eb200_memory_stats(size_t *budget_bytes, size_t *in_use_bytes, size_t *peak_bytes, size_t *live_allocations);
 int eb200_malloc_host(void **ptr, size_t bytes); /* pinned host memory (PINNED mode)           */
 int eb200_free_host(void *ptr);
+/* MAPPED mode (T/DeviceTensor.hpp:1309-1312, 1354-1357: hipHostRegister + hipHostGetDevicePointer): page-locks an existing
+ * host range and returns the device-side alias kernels may dereference (zero-copy over PCIe). */
+int eb200_host_register(void *ptr, size_t bytes, void **dev_ptr);
+int eb200_host_unregister(void *ptr);
+/* device-side alias of memory obtained from eb200_malloc_host (PINNED mode, :1313-1316) */
+int eb200_host_get_device_pointer(void *host_ptr, void **dev_ptr);
 int eb200_mem_get_info(size_t *free_bytes, size_t *total_bytes);
 /* contiguous copies; *_async variants only enqueue */
 int eb200_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
@@ -291,10 +297,12 @@ int eb200_contract_plan(eb200_contract_desc *desc);
  * "contract_tma_f64<80x80>", "tile_mma_f64", "gemm_tf32x3_tcgen05", "tile_simt"; "" before the first one). The
  * descriptor's kernel_used names the family; this names the kernel inside the family. */
 const char *eb200_last_kernel_name(void);
-/* Tuning / testing knobs, process-wide (defaults from EB200_USE_TMA, EB200_USE_TMA_GENERIC, EB200_TMA_TILE):
+/* Tuning / testing knobs, process-wide (defaults from EB200_USE_TMA, EB200_USE_TMA_GENERIC, EB200_TMA_TILE, EB200_TMA_DIST, EB200_PERMUTE_TMA):
  *   "tma"          1 | 0: use / avoid both TMA kernels (0 = cp.async gather kernel everywhere)
  *   "tma_generic"  1 | 0 | 2: multi-index TMA kernel by the padding rule / never / whenever it is legal
- *   "tma_tile"     -1 | 0 | 1: automatic / 128x64 / 80x80 tiles in the multi-index TMA kernel */
+ *   "tma_tile"     -1 | 0 | 1: automatic / 128x64 / 80x80 tiles in the multi-index TMA kernel
+ *   "tma_dist"     0 | n: automatic / issue the loads of step t + n while step t is consumed (1 <= n < stages)
+ *   "permute_tma"  1 | 0: TMA-staged FP64 plane transpose whenever the layout has a tensor map / never (register-staged kernels) */
 int eb200_set_option(const char *name, int value);
 int eb200_get_option(const char *name, int *value);
 

@@ -3,6 +3,7 @@
 // this backend. Expected values come from hand loops on host copies, as the reference tests do; tolerances: 1e-12
 // relative (FP64), exact where the reference asserts exact integers.
 #include <Einsums/LinearAlgebra.hpp>
+#include <Einsums/hipBLAS.hpp>
 #include <Einsums/Tensor/BlockTensor.hpp>
 #include <Einsums/Tensor/DeviceTensor.hpp>
 #include <Einsums/Tensor/TiledTensor.hpp>
@@ -385,6 +386,120 @@ TEST_CASE(gpu_smart_pointer_operands) { // TensorAlgebra/TensorAlgebra.hpp:60-12
     for (size_t x = 0; x < 11; x++) for (size_t y = 0; y < 5; y++) CHECK_CLOSE(hC4(x, y), 3.0 * hC(x, y), 1e-12);
     std::shared_ptr<DeviceTensor<double, 2>> none;
     CHECK_THROWS_AS(einsum(Indices{i, j}, &C2, Indices{i, k}, none, Indices{k, j}, *B), bad_logic);
+}
+
+TEST_CASE(gpu_host_modes_and_layout_conversion) { // T/TensorForward.hpp:45, T/Backends/DeviceTensor.hpp:62-116, 1010-1090, T/DeviceTensor.hpp:1000-1053
+    using namespace einsums::index;
+    // column-major host tensor -> row-major device tensor and back
+    Tensor<double, 3> hcm(false, "hcm", 5, 7, 4), hrm(true, "hrm", 5, 7, 4);
+    for (int x = 0; x < 5; x++) for (int y = 0; y < 7; y++) for (int z = 0; z < 4; z++) hcm(x, y, z) = hrm(x, y, z) = 100 * x + 10 * y + z + 0.5;
+    CHECK(hcm.stride(0) == 1 && hrm.stride(2) == 1);
+    DeviceTensor<double, 3> D{"D", 5, 7, 4};
+    D = hcm;
+    CHECK(D.stride(2) == 1 && D.stride(0) == 28);
+    auto flat = D.to_host();
+    for (int x = 0; x < 5; x++) for (int y = 0; y < 7; y++) for (int z = 0; z < 4; z++) CHECK(flat[(x * 7 + y) * 4 + z] == hcm(x, y, z));
+    D.zero();
+    D = hrm;
+    CHECK(D.to_host() == flat);
+    Tensor<double, 3> back_cm(false, "b", 5, 7, 4);
+    D.copy_to(&back_cm);
+    auto back_rm = Tensor<double, 3>(D);
+    for (int x = 0; x < 5; x++) for (int y = 0; y < 7; y++) for (int z = 0; z < 4; z++) {
+        CHECK(back_cm(x, y, z) == hcm(x, y, z));
+        CHECK(back_rm(x, y, z) == hcm(x, y, z));
+    }
+    Tensor<double, 3> wrong(true, "w", 5, 7, 5);
+    CHECK_THROWS_AS(D = wrong, dimension_error);
+
+    // MAPPED / PINNED: host-side storage the device reads in place; results visible through data() after the op's wait
+    for (auto mode : {einsums::detail::MAPPED, einsums::detail::PINNED}) {
+        DeviceTensor<double, 2> A{"A", mode, 9, 6}, B{"B", mode, 6, 8}, C{"C", mode, 9, 8};
+        CHECK(A.data() != nullptr && A.mode() == mode);
+        for (int x = 0; x < 54; x++) A.data()[x] = 0.25 * x - 3;
+        for (int x = 0; x < 48; x++) B.data()[x] = 1.0 / (1 + x);
+        einsum(Indices{i, j}, &C, Indices{i, k}, A, Indices{k, j}, B);
+        for (int x = 0; x < 9; x++) for (int y = 0; y < 8; y++) {
+            double s = 0;
+            for (int k0 = 0; k0 < 6; k0++) s += A.data()[x * 6 + k0] * B.data()[k0 * 8 + y];
+            CHECK_CLOSE(C.data()[x * 8 + y], s, 1e-12);
+            CHECK_CLOSE((double)C(x, y), s, 1e-12);
+        }
+        DeviceTensor<double, 2> Cd(C); // copy keeps the mode and the values
+        CHECK(Cd.mode() == mode && Cd.data() != C.data() && Cd.data()[5] == C.data()[5]);
+        DeviceTensor<double, 3> M(hcm, mode);
+        CHECK(M.data()[(2 * 7 + 3) * 4 + 1] == hcm(2, 3, 1));
+    }
+    DeviceTensor<double, 2> dev{"dev", 3, 4};
+    CHECK(dev.data() == nullptr && dev.mode() == einsums::detail::DEV_ONLY);
+
+    // gpu_dims() / gpu_strides(): device-resident size_t arrays
+    size_t meta[6];
+    EB200_CHECK(eb200_memcpy_d2h(meta, D.gpu_dims(), 3 * sizeof(size_t), gpu::get_stream()));
+    EB200_CHECK(eb200_memcpy_d2h(meta + 3, D.gpu_strides(), 3 * sizeof(size_t), gpu::get_stream()));
+    CHECK(meta[0] == 5 && meta[1] == 7 && meta[2] == 4 && meta[3] == 28 && meta[4] == 4 && meta[5] == 1);
+}
+
+TEST_CASE(gpu_blas_gpu_facade) { // hipBLAS.hpp:63-94 (gemm), :132-160 (gemv), :423 (scal), :545 (dot), :586 (dotc), :621 (axpy), :719 (ger)
+    namespace bg = einsums::blas::gpu;
+    using cd = std::complex<double>;
+    const int m = 7, n = 5, k = 9;
+    // column-major operands held in rank-1 device tensors
+    auto A = create_random_gpu_tensor("A", m * k), B = create_random_gpu_tensor("B", k * n), C = create_random_gpu_tensor("C", m * n);
+    auto hA = A.to_host(), hB = B.to_host(), hC = C.to_host();
+    bg::gemm<double>('n', 'n', m, n, k, 0.5, A.gpu_data(), m, B.gpu_data(), k, 2.0, C.gpu_data(), m);
+    auto out = C.to_host();
+    for (int x = 0; x < m; x++) for (int y = 0; y < n; y++) {
+        double s = 0;
+        for (int q = 0; q < k; q++) s += hA[x + q * m] * hB[q + y * k];
+        CHECK_CLOSE(out[x + y * m], 2.0 * hC[x + y * m] + 0.5 * s, 1e-12);
+    }
+    bg::gemm<double>('t', 'n', k, n, m, 1.0, A.gpu_data(), m, C.gpu_data(), m, 0.0, B.gpu_data(), k); // B = A^T C
+    auto outB = B.to_host();
+    for (int x = 0; x < k; x++) for (int y = 0; y < n; y++) {
+        double s = 0;
+        for (int q = 0; q < m; q++) s += hA[q + x * m] * out[q + y * m];
+        CHECK_CLOSE(outB[x + y * k], s, 1e-12);
+    }
+    CHECK_THROWS_AS(bg::gemm<double>('x', 'n', m, n, k, 1.0, A.gpu_data(), m, B.gpu_data(), k, 0.0, C.gpu_data(), m), std::invalid_argument);
+    CHECK_THROWS_AS(bg::gemm<double>('n', 'n', m, n, k, 1.0, A.gpu_data(), m - 1, B.gpu_data(), k, 0.0, C.gpu_data(), m), std::domain_error);
+    // gemv, axpy, axpby, scal, rscl, dot, ger
+    auto x1 = create_random_gpu_tensor("x", k), y1 = create_random_gpu_tensor("y", m);
+    auto hx = x1.to_host(), hy = y1.to_host();
+    bg::gemv<double>('n', m, k, 1.5, A.gpu_data(), m, x1.gpu_data(), 1, -1.0, y1.gpu_data(), 1);
+    auto oy = y1.to_host();
+    for (int r0 = 0; r0 < m; r0++) {
+        double s = 0;
+        for (int q = 0; q < k; q++) s += hA[r0 + q * m] * hx[q];
+        CHECK_CLOSE(oy[r0], 1.5 * s - hy[r0], 1e-12);
+    }
+    double d0 = bg::dot<double>(m, y1.gpu_data(), 1, A.gpu_data(), 1), want = 0;
+    for (int r0 = 0; r0 < m; r0++) want += oy[r0] * hA[r0];
+    CHECK_CLOSE(d0, want, 1e-12);
+    bg::scal<double>(m, 3.0, y1.gpu_data(), 1);
+    bg::rscl<double>(m, 2.0, y1.gpu_data(), 1);
+    bg::axpy<double>(m, -1.0, A.gpu_data(), 1, y1.gpu_data(), 1);
+    bg::axpby<double>(m, 2.0, A.gpu_data(), 1, 0.5, y1.gpu_data(), 1);
+    auto oy2 = y1.to_host();
+    for (int r0 = 0; r0 < m; r0++) CHECK_CLOSE(oy2[r0], 2.0 * hA[r0] + 0.5 * (1.5 * oy[r0] - hA[r0]), 1e-12);
+    auto G = create_zero_gpu_tensor("G", m * k);
+    bg::ger<double>(m, k, 2.0, y1.gpu_data(), 1, x1.gpu_data(), 1, G.gpu_data(), m);
+    auto hG = G.to_host();
+    for (int r0 = 0; r0 < m; r0++) for (int q = 0; q < k; q++) CHECK_CLOSE(hG[r0 + q * m], 2.0 * oy2[r0] * hx[q], 1e-12);
+    // complex: dotc conjugates the first vector, gerc the second, scal by a real
+    auto zx = create_random_gpu_tensor<cd>("zx", 11), zy = create_random_gpu_tensor<cd>("zy", 11);
+    auto hzx = zx.to_host(), hzy = zy.to_host();
+    cd   dc = bg::dotc<cd>(11, zx.gpu_data(), 1, zy.gpu_data(), 1), du = bg::dot<cd>(11, zx.gpu_data(), 1, zy.gpu_data(), 1), wc = 0, wu = 0;
+    for (int q = 0; q < 11; q++) { wc += std::conj(hzx[q]) * hzy[q]; wu += hzx[q] * hzy[q]; }
+    CHECK_CLOSE(dc, wc, 1e-12);
+    CHECK_CLOSE(du, wu, 1e-12);
+    auto ZG = create_zero_gpu_tensor<cd>("ZG", 11 * 11);
+    bg::gerc<cd>(11, 11, cd(0.5, 1.0), zx.gpu_data(), 1, zy.gpu_data(), 1, ZG.gpu_data(), 11);
+    auto hZG = ZG.to_host();
+    for (int r0 = 0; r0 < 11; r0++) for (int q = 0; q < 11; q++) CHECK_CLOSE(hZG[r0 + q * 11], cd(0.5, 1.0) * hzx[r0] * std::conj(hzy[q]), 1e-12);
+    bg::scal<cd>(11, 2.0, zx.gpu_data(), 1);
+    auto hzx2 = zx.to_host();
+    for (int q = 0; q < 11; q++) CHECK_CLOSE(hzx2[q], 2.0 * hzx[q], 1e-12);
 }
 
 TEST_CASE(gpu_permute) { // Sort.cpp:18-250, GPUTensorAlgebra.hip:591-838

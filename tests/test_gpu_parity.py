@@ -669,6 +669,59 @@ def test_permute_into_larger_output_and_errors(gpu, oracle):
 
 # ---------------------------------------------------------------------------------------------
 # size-independent properties at (near) benchmark sizes, where the oracle would take too long
+@pytest.fixture
+def permute_tma_always(gpu):
+    """Every FP64 overwrite transpose the TMA-staged kernel can legally take goes through it (ignores the tile-fill rule)."""
+    gpu.set_option("permute_tma", 2)
+    yield gpu
+    gpu.set_option("permute_tma", 1)
+
+
+@pytest.mark.parametrize("order", list(itertools.permutations(range(4))), ids=lambda o: "".join("ijkl"[x] for x in o))
+def test_permute_tma_rank4_all_orders(permute_tma_always, oracle, order):
+    """permute_tma_f64 (TMA-staged plane transpose) on all 24 orders: even, non-tile-multiple extents so that edge tiles are clipped by
+    the TMA unit; alpha = 1 bit-exact against the oracle, alpha != 1 bit-exact against alpha * oracle (one multiplication)."""
+    gpu = permute_tma_always
+    rng = np.random.default_rng(113)
+    shape = (18, 34, 10, 46)
+    A = rand(rng, shape)
+    c_idx = "".join("ijkl"[o] for o in order)
+    ref = np.full(tuple(shape[o] for o in order), 7.0); oracle.permute(c_idx, ref, "ijkl", A, 1.0, 0.0)
+    Cd = dev(np.full_like(ref, 7.0)); gpu.permute(c_idx, Cd, "ijkl", dev(A), 1.0, 0.0)
+    assert np.array_equal(Cd.cpu().numpy(), ref)
+    gpu.permute(c_idx, Cd, "ijkl", dev(A), -0.75, 0.0)
+    assert np.array_equal(Cd.cpu().numpy(), -0.75 * ref)
+
+
+def test_permute_tma_shapes_and_views(permute_tma_always, gpu):
+    """Tile fitting (extents 160 -> 80, 96 -> 96, 300 -> 112 x 104 ...), ranks 2-5, and strided views on both sides, against torch's
+    permuted view (bit-exact); the non-TMA kernels are run on the same inputs and must agree bit for bit."""
+    torch.manual_seed(7)
+    cases = [((160, 6, 160), (2, 1, 0)), ((96, 96), (1, 0)), ((300, 258), (1, 0)), ((6, 130, 4, 70), (3, 2, 0, 1)), ((4, 66, 2, 3, 50), (4, 2, 0, 3, 1)),
+             ((2, 2, 2, 2, 40, 36), (5, 3, 1, 0, 2, 4))]
+    for shape, order in cases:
+        letters = "ijklmn"[:len(shape)]
+        c_idx = "".join(letters[o] for o in order)
+        A = torch.rand(*shape, dtype=torch.float64, device="cuda")
+        B = torch.zeros([shape[o] for o in order], dtype=torch.float64, device="cuda")
+        gpu.set_option("permute_tma", 2)
+        gpu.permute(c_idx, B, letters, A)
+        assert torch.equal(B, A.permute(*order)), (shape, order)
+        B2 = torch.zeros_like(B)
+        gpu.set_option("permute_tma", 0)
+        gpu.permute(c_idx, B2, letters, A)
+        assert torch.equal(B2, B)
+    # views: A is a window of a larger tensor (even offsets/strides), C a window of a larger output
+    gpu.set_option("permute_tma", 2)
+    big = torch.rand(40, 70, 52, dtype=torch.float64, device="cuda")
+    Av = big[4:36, 2:66, 8:48]
+    out = torch.full((44, 70, 40), -1.0, dtype=torch.float64, device="cuda")
+    Cv = out[2:42, 4:68, 6:38]
+    gpu.permute("kji", Cv, "ijk", Av)
+    assert torch.equal(Cv, Av.permute(2, 1, 0))
+    assert (out[:2] == -1).all() and (out[:, :4] == -1).all() and (out[:, :, 38:] == -1).all()
+
+
 def test_permute_round_trip_large(gpu):
     n = 96
     A = torch.rand(n, n, n, n, dtype=torch.float64, device="cuda")
@@ -781,7 +834,7 @@ TMA_GENERIC = [
     ("ji", "ik", "kj", dict(i=129, j=70, k=300)),
     # batch index outermost / innermost in C, carried by both operands (3-D and 4-D maps with a batch coordinate)
     ("bij", "bik", "bkj", dict(i=65, j=34, k=40, b=5)),
-    ("ijb", "bik", "kbj", dict(i=66, j=33, k=48, b=3)),
+    ("ijb", "bik", "kbj", dict(i=66, j=34, k=48, b=3)),
     # two batch indices, target groups of two indices each
     ("xyabcd", "xyakb", "ykxcd", dict(x=2, y=3, a=5, b=16, c=4, d=20, k=40)),
 ]
@@ -796,7 +849,10 @@ def test_tma_generic_patterns(tma_generic_always, oracle, case, tile):
     c_idx, a_idx, b_idx, ext = case
     for (alpha, beta, sk) in ((0.25, 1.0, 0), (1.0, 0.0, 1), (-0.5, 2.0, 3)):
         d = run_case(gpu, oracle, c_idx, a_idx, b_idx, ext, np.float64, alpha, beta, force=KF["TILE_MMA"], seed=41, split_k=sk)
-        assert gpu.last_kernel() == ("contract_tma_f64<80x80>" if tile else "contract_tma_f64<128x64>"), (gpu.last_kernel(), case)
+        want = "contract_tma_f64<80x80>" if tile else "contract_tma_f64<128x64>"
+        if len(ext) == 3 and tile == 0 and d.split_k == 1:
+            want = "gemm_tma_f64"   # a plain product on 128x64 tiles without split-K belongs to the 2-D kernel
+        assert gpu.last_kernel() == want, (gpu.last_kernel(), case)
         if sk:
             assert d.split_k == sk
 
@@ -829,8 +885,12 @@ def test_tma_generic_default_routing(gpu, oracle):
     run_case(gpu, oracle, "mbej", "jnfb", "mnef", dict(m=6, b=21, e=19, j=7, n=5, f=23), np.float64, -0.5, 1.0)
     assert gpu.last_kernel() == "tile_mma_f64"
     run_case(gpu, oracle, "bij", "bik", "bkj", dict(i=64, j=64, k=64, b=12), np.float64, 1.0, 0.0)
+    assert gpu.last_kernel() == "contract_tma_f64<80x80>"    # 4 x 4 blocks: one 80x80 tile wastes less than one 128x64 tile
+    run_case(gpu, oracle, "bij", "bik", "bkj", dict(i=128, j=64, k=64, b=12), np.float64, 1.0, 0.0)
     assert gpu.last_kernel() == "contract_tma_f64<128x64>"
-    run_case(gpu, oracle, "ij", "ik", "kj", dict(i=300, j=260, k=64), np.float64, 1.0, 0.0)
+    run_case(gpu, oracle, "ij", "ik", "kj", dict(i=300, j=260, k=64), np.float64, 1.0, 0.0)   # 19 x 17 blocks: 80x80 tiles pad less
+    assert gpu.last_kernel() == "contract_tma_f64<80x80>"
+    run_case(gpu, oracle, "ij", "ik", "kj", dict(i=384, j=256, k=64), np.float64, 1.0, 0.0)
     assert gpu.last_kernel() == "gemm_tma_f64"
     run_case(gpu, oracle, "ij", "ik", "jk", dict(i=80, j=80, k=4000), np.float64, 1.0, 1.0)   # split-K: fused reduction in the generic kernel
     assert gpu.last_kernel().startswith("contract_tma_f64")
@@ -838,33 +898,30 @@ def test_tma_generic_default_routing(gpu, oracle):
 
 @pytest.mark.parametrize("chunk", range(3))
 def test_tma_generic_fuzz(tma_generic_always, oracle, chunk):
-    """Random contractions (3-6 indices, extents 16-aligned or ragged, random axis orders) through the multi-index TMA kernel
-    whenever it is legal, both tile shapes, against the oracle."""
+    """Random tile-family contractions (1-2 indices per target group, 1-3 contracted, 0-1 batch; random axis orders; extents mostly even,
+    16-aligned or ragged) through the multi-index TMA kernel whenever it is legal, both tile shapes, against the oracle. Cases whose
+    layout has no tensor map (odd strides, no common unit-stride contracted index) fall back to the gather kernel and are checked too."""
     from einsums_b200 import KF
     gpu = tma_generic_always
     rng = np.random.default_rng(3000 + chunk)
-    took = 0
-    for n in range(14):
-        letters = "abcdef"
-        nu = int(rng.integers(3, 7))
-        ext = {letters[u]: int(rng.choice([2, 3, 16, 20, 32, 35, 48])) for u in range(nu)}
-        if np.prod([float(v) for v in ext.values()]) > 3e7:
+    took = ran = 0
+    for n in range(48):
+        letters = list("abcdefgh")
+        nm, nn, nk, nb = int(rng.integers(1, 3)), int(rng.integers(1, 3)), int(rng.integers(1, 4)), int(rng.integers(0, 2))
+        if nm + nk + nb > 5 or nn + nk + nb > 5:
             continue
-        c, a, b = [], [], []
-        for u in range(nu):
-            where = int(rng.choice([3, 5, 6, 6, 7, 3, 5]))
-            ch = letters[u]
-            if where & 1: c.append(ch)
-            if where & 2: a.append(ch)
-            if where & 4: b.append(ch)
-        if not a or not b or not c:
+        m, nl, k, bt = letters[:nm], letters[nm:nm + nn], letters[nm + nn:nm + nn + nk], letters[nm + nn + nk:nm + nn + nk + nb]
+        ext = {ch: int(rng.choice([2, 4, 6, 16, 20, 32, 34, 48, 3] if ch not in k[1:] + bt else [2, 3, 4, 5])) for ch in m + nl + k + bt}
+        if np.prod([float(v) for v in ext.values()]) > 2e7:
             continue
+        c, a, b = m + nl + bt, m + k + bt, nl + k + bt
         for lst in (c, a, b):
             rng.shuffle(lst)
         gpu.set_option("tma_tile", int(rng.integers(0, 2)))
         alpha, beta = [(1.0, 0.0), (0.5, 2.0), (-1.0, 1.0)][int(rng.integers(0, 3))]
         d = run_case(gpu, oracle, "".join(c), "".join(a), "".join(b), ext, np.float64, alpha, beta, seed=chunk * 50 + n,
                      split_k=int(rng.choice([0, 0, 2])))
+        ran += 1
         if d.kernel_used == KF["TILE_MMA"] and gpu.last_kernel().startswith("contract_tma_f64"):
             took += 1
-    assert took >= 3, f"only {took} cases reached the multi-index TMA kernel"
+    assert took >= 3, f"only {took} of {ran} cases reached the multi-index TMA kernel"
