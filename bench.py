@@ -208,6 +208,32 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def bind_to_gpu_numa_node(local):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off, so that first-touch pinned allocations land on that node
+    (the e2e path is bound by host memory / PCIe root bandwidth, not by a kernel). Returns what was done, for the JSON line."""
+    import glob
+    import torch
+    nodes = sorted(glob.glob("/sys/devices/system/node/node[0-9]*"))
+    info = {"numa_nodes_visible": len(nodes)}
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip()
+        info["gpu_numa_node"] = node
+        if len(nodes) > 1 and node not in ("-1", ""):
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info["bound_to_cpus"] = len(cpus)
+    except Exception as e:  # noqa: BLE001
+        info["error"] = f"{type(e).__name__}: {e}"[:120]
+    return info
+
+
 def run_sharded(args, world, rank, barrier):
     """BASELINE configs[4]: Wabef[a,b,e,f] = W + 0.25 sum_mn g[m,n,e,f] t[m,n,a,b], o=40, v=400 (W = 204.8 GB, 8.192e13 flop), the
     a-index block-distributed over the ranks (einsums_b200.sharding), g and t REPLICATED (same seed on every rank; 2 x 2.05 GB),
@@ -277,6 +303,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: the backend has no CPU fallback"
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     ops.init(local)
     if world > 1:
         # stdout carries exactly one JSON line: while the communicator comes up, NCCL's banner (NCCL_DEBUG=VERSION prints
@@ -399,6 +426,34 @@ def run_ours(args):
                "note": "pinned host -> device of g, t, Wmnij, Wabef; both einsums; device -> pinned host of both results; "
                        f"Wabef through eb200_contract_host in {args.e2e_slab_mb} MiB slabs with H2D|compute|D2H overlapped"}
         del e2e_step, hWa, oWa, hg, ht, hWm, oWm, ge, te_, chk   # 12.8 GB of pinned host memory per rank goes back before the next section
+        # What the host allows: a bare pinned-memory copy loop, H2D and D2H at the same time on two streams, ALL ranks at once
+        # (1 GiB each way per rank, 6 repetitions). e2e moves h2d + d2h bytes per step per rank; its rate is to be read against this.
+        n8 = (1 << 30) // 8
+        hb_in = torch.empty(n8, dtype=torch.float64, pin_memory=True).fill_(1.0)
+        hb_out = torch.empty(n8, dtype=torch.float64, pin_memory=True)
+        db_in, db_out = torch.empty(n8, dtype=torch.float64, device="cuda"), torch.ones(n8, dtype=torch.float64, device="cuda")
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def both():
+            with torch.cuda.stream(s1):
+                db_in.copy_(hb_in, non_blocking=True)
+            with torch.cuda.stream(s2):
+                hb_out.copy_(db_out, non_blocking=True)
+
+        both(); barrier()
+        t0 = time.perf_counter()
+        for _ in range(6):
+            both()
+        barrier()
+        dtc = time.perf_counter() - t0
+        rate = torch.tensor([6 * 2 * n8 * 8 / dtc / 1e9], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(rate, op=dist.ReduceOp.SUM)
+        e2e_rate = world * (counts["h2d"] + counts["d2h"]) / (e2e["ms_per_step"] * 1e-3) / 1e9
+        e2e["numa"] = numa
+        e2e["host_copy_ceiling"] = {"aggregate_both_directions_gbs": rate.item(), "e2e_copy_rate_gbs": e2e_rate, "frac": e2e_rate / rate.item(),
+                                    "how": "bare pinned H2D + D2H copy loop, 1 GiB each way per rank, all ranks at once, wall clock between barriers"}
+        del hb_in, hb_out, db_in, db_out
 
     # ---- BASELINE configs[4]: Wabef o=40 v=400 sharded over `a` (strong scaling), at every N
     del g, t, Wm

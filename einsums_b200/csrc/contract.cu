@@ -5,6 +5,7 @@
 #include "contract_kernels.cuh"
 #include "gemm_tma.cuh"
 #include "contract_tma.cuh"
+#include "gemm_tma_z.cuh"
 #include "launch_api.cuh"
 
 #include <algorithm>
@@ -150,6 +151,10 @@ int try_run_tma(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const dou
     if (tm * tn > 0x7fffffffLL) return 0;
     a.tiles_m = (int)tm; a.tiles_n = (int)tn;
     a.vec_c = (a.sCn == 1 && !(N & 1) && !(a.sCm & 1) && ((uintptr_t)a.C % 16) == 0) ? 1 : 0;
+    {
+        const int want = option(OPT_TMA_DIST);
+        a.dist = (want >= 1 && want < 4) ? want : 3;
+    }
     d.split_k = 1;
     static const size_t smem_pad = getenv("EB200_TMA_SMEM_PAD") ? (size_t)atoi(getenv("EB200_TMA_SMEM_PAD")) : 0; // debugging: forces 1 CTA/SM
     const size_t        SMEM = 4 * (128 * 16 * 8 + 64 * 16 * 8) + 1024 + 64 + smem_pad;
@@ -290,16 +295,19 @@ int env_int(const char *name, int dflt) {
     const char *e = getenv(name);
     return e ? atoi(e) : dflt;
 }
-bool make_operand_map_f32(CUtensorMap *map, const float *base, int64_t inner, int64_t outer, int64_t ld, uint32_t box_inner, uint32_t box_outer,
-                          bool mn = false) {
+// 3-D map over an FP32 operand: dim0 = the unit-stride direction, dim1 = the other one (ld elements apart), dim2 = batch
+bool make_operand_map_f32(CUtensorMap *map, const float *base, int64_t inner, int64_t outer, int64_t ld, int64_t batch, int64_t batch_stride,
+                          uint32_t box_inner, uint32_t box_outer, bool mn = false) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return false;
-    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {box_inner, box_outer};
-    cuuint32_t es[2] = {1, 1};
+    if (batch <= 1) batch_stride = std::max<int64_t>(ld * outer, 4); // unused dimension: any legal stride
+    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)std::max<int64_t>(batch, 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)batch_stride * 4};
+    cuuint32_t box[3] = {box_inner, box_outer, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    if ((strides[0] & 15) || (strides[1] & 15) || strides[0] >= (1ULL << 40) || strides[1] >= (1ULL << 40)) return false;
     CUtensorMapSwizzle sw = mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B; // see gemm_tf32x3.cuh
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 int try_run_tf32x3(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const double beta_eff[2]) {
@@ -307,11 +315,13 @@ int try_run_tf32x3(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const 
         const char *e = getenv("EB200_USE_TCGEN05");
         g_use_tcgen05 = e ? atoi(e) : 1;
     }
-    if (!g_use_tcgen05 || d.force_kernel != 0 || d.split_k > 1) return 0;
-    if (p.b.n != 0 || p.m.n != 1 || p.n.n != 1 || p.k.n != 1) return 0;
+    if (!g_use_tcgen05 || d.force_kernel != 0 || d.split_k > 1 || p.swapped) return 0;
+    // plain products and products batched over ONE index (strided-batched GEMM, equal-size blocks of the block/tiled algebra)
+    if (p.b.n > 1 || p.m.n != 1 || p.n.n != 1 || p.k.n != 1) return 0;
     const float  *A = (const float *)d.A.data, *B = (const float *)d.B.data;
-    const int64_t M = p.m.tot, N = p.n.tot, K = p.k.tot;
+    const int64_t M = p.m.tot, N = p.n.tot, K = p.k.tot, NB = p.b.n ? p.b.tot : 1;
     const int64_t sAm = p.m.s[ROLE_A][0], sAk = p.k.s[ROLE_A][0], sBn = p.n.s[ROLE_B][0], sBk = p.k.s[ROLE_B][0];
+    const int64_t sAb = p.b.n ? p.b.s[ROLE_A][0] : 0, sBb = p.b.n ? p.b.s[ROLE_B][0] : 0, sCb = p.b.n ? p.b.s[ROLE_C][0] : 0;
     const bool    a_mn = (sAk != 1), b_mn = (sBk != 1); // MN-major: the target index is the contiguous one
     if (a_mn && sAm != 1) return 0;
     if (b_mn && sBn != 1) return 0;
@@ -319,25 +329,76 @@ int try_run_tf32x3(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const 
     if (lda <= 0 || ldb <= 0 || (lda & 3) || (ldb & 3) || ((uintptr_t)A % 16) || ((uintptr_t)B % 16)) return 0;
     if (M >= (1LL << 31) || N >= (1LL << 31) || K >= (1LL << 31) || lda >= (1LL << 36) || ldb >= (1LL << 36)) return 0;
     if ((a_mn ? M : K) > lda || (b_mn ? N : K) > ldb) return 0;
-    if (M * N < 128 * 128 * 4) return 0; // tiny outputs: the FMA kernel (with split-K) is the better fit
+    if (p.b.n && (sAb <= 0 || sBb <= 0 || (sAb & 3) || (sBb & 3) || NB >= (1LL << 31))) return 0; // shared (stride 0) operands: FMA kernel
+    if (M * N * NB < 128 * 128 * 4) return 0; // tiny outputs: the FMA kernel (with split-K) is the better fit
     CUtensorMap tmA, tmB;
-    if (!(a_mn ? make_operand_map_f32(&tmA, A, M, K, lda, 32, 32, true) : make_operand_map_f32(&tmA, A, K, M, lda, 32, 128))) return 0;
-    if (!(b_mn ? make_operand_map_f32(&tmB, B, N, K, ldb, 32, 32, true) : make_operand_map_f32(&tmB, B, K, N, ldb, 32, 128))) return 0;
+    if (!(a_mn ? make_operand_map_f32(&tmA, A, M, K, lda, NB, sAb, 32, 32, true) : make_operand_map_f32(&tmA, A, K, M, lda, NB, sAb, 32, 128))) return 0;
+    if (!(b_mn ? make_operand_map_f32(&tmB, B, N, K, ldb, NB, sBb, 32, 32, true) : make_operand_map_f32(&tmB, B, K, N, ldb, NB, sBb, 32, 128))) return 0;
     Tf32GemmArgs a;
     a.M = M; a.N = N; a.K = K;
     a.sCm = p.m.s[ROLE_C][0]; a.sCn = p.n.s[ROLE_C][0];
     a.C = (float *)d.C.data;
     a.alpha = (float)d.alpha[0]; a.beta = (float)beta_eff[0];
+    a.batch = NB; a.sCb = sCb;
     const int64_t tm = (M + 127) / 128, tn = (N + 127) / 128;
-    if (tm * tn > 0x7fffffffLL) return 0;
+    if (tm * tn > 0x7fffffffLL || tm * tn * NB > (1LL << 40)) return 0;
     a.tiles_m = (int)tm; a.tiles_n = (int)tn;
-    constexpr size_t SMEM = 3 * 65536 + 1024 + 128;
-    int rc = k_launch_tf32x3(s, tmA, tmB, a, dim3((unsigned)(tm * tn), 1, 1), SMEM, a_mn, b_mn);
+    constexpr size_t SMEM = 3 * 65536 + 4 * (32 * 33 * 4) + 1024 + 256;
+    // persistent: one CTA per SM (the kernel needs all of shared memory and all 512 TMEM columns), each walking its share of the tiles
+    const unsigned grid = (unsigned)std::min<int64_t>(tm * tn * NB, sm_count());
+    int rc = k_launch_tf32x3(s, tmA, tmB, a, dim3(grid, 1, 1), SMEM, a_mn, b_mn);
     if (rc) return -rc;
     d.launches++;
     d.split_k = 1;
     d.kernel_used = EB200_KF_TILE_TCGEN05;
     set_last_kernel("gemm_tf32x3_tcgen05");
+    return 1;
+}
+
+// ---------------------------------------------------------------- complex FP64 on the FP64 tensor pipe (plain products)
+int try_run_tma_z(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const double beta_eff[2]) {
+    if (!option(OPT_TMA) || d.force_kernel != 0 || d.split_k > 1 || p.swapped) return 0;
+    if (p.b.n != 0 || p.m.n != 1 || p.n.n != 1 || p.k.n != 1) return 0;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return 0;
+    const double2 *A = (const double2 *)d.A.data, *B = (const double2 *)d.B.data;
+    const int64_t  M = p.m.tot, N = p.n.tot, K = p.k.tot;
+    const int64_t  sAm = p.m.s[ROLE_A][0], sAk = p.k.s[ROLE_A][0], sBn = p.n.s[ROLE_B][0], sBk = p.k.s[ROLE_B][0];
+    const bool     ak = (sAk == 1), bk = (sBk == 1);
+    if (!ak && sAm != 1) return 0;
+    if (!bk && sBn != 1) return 0;
+    const int64_t lda = ak ? sAm : sAk, ldb = bk ? sBn : sBk;
+    if (lda <= 0 || ldb <= 0 || ((uintptr_t)A % 16) || ((uintptr_t)B % 16)) return 0;
+    if (M >= (1LL << 30) || N >= (1LL << 30) || K >= (1LL << 30) || lda >= (1LL << 35) || ldb >= (1LL << 35)) return 0;
+    if ((ak ? K : M) > lda && (ak ? M : K) > 1) return 0;
+    if ((bk ? K : N) > ldb && (bk ? N : K) > 1) return 0;
+    const int64_t tm = (M + 127) / 128, tn = (N + 31) / 32;
+    // small outputs want split-K (the FMA kernel has it); the tensor-pipe kernel needs enough tiles to fill the machine
+    if (tm * tn > 0x7fffffffLL || tm * tn * 2 <= (int64_t)sm_count() * 2) return 0;
+    auto make_map = [&](CUtensorMap *map, const double2 *base, int64_t inner, int64_t outer, int64_t ld, uint32_t box_outer) {
+        cuuint64_t dims[2] = {(cuuint64_t)inner * 2, (cuuint64_t)outer};
+        cuuint64_t strides[1] = {(cuuint64_t)ld * 16};
+        cuuint32_t box[2] = {16, box_outer}, es[2] = {1, 1};
+        return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    CUtensorMap tmA, tmB;
+    if (!(ak ? make_map(&tmA, A, K, M, lda, 128) : make_map(&tmA, A, M, K, lda, 8))) return 0;
+    if (!(bk ? make_map(&tmB, B, K, N, ldb, 32) : make_map(&tmB, B, N, K, ldb, 8))) return 0;
+    TmaZGemmArgs a;
+    a.M = M; a.N = N; a.K = K;
+    a.sCm = p.m.s[ROLE_C][0]; a.sCn = p.n.s[ROLE_C][0];
+    a.C = (double2 *)d.C.data;
+    a.alpha[0] = d.alpha[0]; a.alpha[1] = d.alpha[1];
+    a.beta[0] = beta_eff[0]; a.beta[1] = beta_eff[1];
+    a.tiles_m = (int)tm; a.tiles_n = (int)tn;
+    a.conj_a = d.conj_a; a.conj_b = d.conj_b;
+    const size_t SMEM = 4 * (128 * 8 * 16 + 32 * 8 * 16) + 1024 + 64;
+    int rc = k_launch_tma_z(s, tmA, tmB, a, dim3((unsigned)(tm * tn), 1, 1), SMEM, ak, bk);
+    if (rc) return -rc;
+    d.launches++;
+    d.split_k = 1;
+    set_last_kernel("gemm_tma_z");
     return 1;
 }
 
@@ -360,6 +421,13 @@ template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract
             if (r == 1) return EB200_OK;
             if (r < 0) return -r;
             r = try_run_tma_generic(s, p, d, beta_eff);
+            if (r == 1) return EB200_OK;
+            if (r < 0) return -r;
+        }
+    }
+    if constexpr (std::is_same_v<T, double2>) {
+        if (!mma) {
+            int r = try_run_tma_z(s, p, d, beta_eff);
             if (r == 1) return EB200_OK;
             if (r < 0) return -r;
         }

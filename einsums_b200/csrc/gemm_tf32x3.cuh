@@ -5,15 +5,19 @@
 //        A_hi*B_hi + A_hi*B_lo + A_lo*B_hi          (the lo*lo term is below 2^-20 relative and dropped)
 // with all three tcgen05.mma accumulating into the same FP32 accumulator in tensor memory.
 //
-// Roles (192 threads, warp-specialised, one 128x128 output tile per CTA, BK = 32 floats = one 128-byte swizzle row):
-//   warp 0, one lane : TMA producer — cp.async.bulk.tensor.2d of the raw A and B tiles (SWIZZLE_128B, K-major)
-//   warps 2..5       : splitters — read the raw tile, write hi back in place and lo to a second buffer (same swizzled layout,
-//                      so they just stream 16-byte chunks), fence.proxy.async, arrive; later they run the epilogue
+// Persistent kernel: one CTA per SM walks a static list of 128x128 output tiles (and batch members); BK = 32 floats = one 128-byte
+// swizzle row; 320 threads, warp-specialised:
+//   warp 0, one lane : TMA producer — cp.async.bulk.tensor.3d {k, m|n, batch} of the raw A and B tiles (SWIZZLE_128B), 3 stages that
+//                      run straight across tile boundaries (the next tile's loads start while the last MMAs of this one are in flight)
+//   warps 2..5       : splitters — read the raw tile and write lo = x - trunc_tf32(x) to a second buffer in the same swizzled layout
+//                      (the raw tile itself serves as hi: kind::tf32 ignores the 13 low mantissa bits), fence.proxy.async, arrive
 //   warp 1, one lane : tcgen05.mma issuer — 4 k-slices x 3 products per stage, kind::tf32, M=128 N=128 K=8, cta_group::1;
-//                      tcgen05.commit releases the stage to the producer and finally signals the epilogue
-//   epilogue         : tcgen05.ld 32x32b (each warp its own TMEM lane quadrant) -> alpha*acc + beta*C -> global
-// Two 128-column TMEM accumulators alternate between chunks of 512 k; finished chunks are added into registers with
-// round-to-nearest (the tensor core's own FP32 accumulation truncates).
+//                      tcgen05.commit releases the stage to the producer and hands finished accumulators to the epilogue warps
+//   warps 6..9       : epilogue — tcgen05.ld 32x32b (each warp its own TMEM lane quadrant) -> alpha*acc + beta*C -> global, one tile
+//                      behind the issuer, so the store of tile i overlaps the main loop of tile i + 1
+// Two TMEM accumulator pairs (hi*hi | cross terms; all 512 columns) alternate over chunks of 512 k and over consecutive tiles; finished
+// chunks are added into registers with round-to-nearest (the tensor core's own FP32 accumulation truncates). K <= 512
+// uses the MULTI = false instantiation, whose epilogue streams 32-column blocks TMEM -> registers -> global without a row buffer.
 #pragma once
 #include <cuda.h>
 
@@ -27,6 +31,7 @@ struct Tf32GemmArgs {
     float  *C;
     float   alpha, beta;
     int32_t tiles_m, tiles_n;
+    int64_t batch, sCb;    // number of independent products (1 = plain GEMM) and the element stride of C between them
 };
 
 #ifdef EB200_TF32_KERNEL_IMPL // the kernel itself is compiled by k_tile_tf32.cu only
@@ -56,14 +61,15 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(192, 1) gemm_tf32x3_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+template <bool A_MN, bool B_MN, bool MULTI>
+__global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                              const __grid_constant__ Tf32GemmArgs args) {
-    constexpr int      BM = 128, BN = 128, BK = 32, STAGES = 3;
+    constexpr int      BM = 128, BN = 128, BK = 32, STAGES = 3, NACC = 2;
     constexpr uint32_t TILE_BYTES = BM * BK * 4;                 // 16 KB per operand tile
     constexpr uint32_t RAW_BYTES = 2 * TILE_BYTES;               // A_raw | B_raw
     constexpr uint32_t STAGE_BYTES = 2 * RAW_BYTES;              // + A_lo | B_lo
-    constexpr uint32_t TMEM_COLS = 256;                          // two 128-column accumulators (ping-pong between K chunks)
+    constexpr uint32_t TMEM_COLS = 512;                          // two accumulator PAIRS (hi*hi | cross terms, 128 columns each): chunks and tiles alternate
+    constexpr uint32_t PATCH_BYTES = 32 * 33 * 4;                // per epilogue warp: 32 x 32 transposition patch
     constexpr int      KCB = 16;                                 // k-blocks per accumulation chunk (512 k)
     // instruction descriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
@@ -71,18 +77,30 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32x3_tcgen05(const __grid_const
 
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-    const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
+    const uint32_t patches = smem_base + STAGES * STAGE_BYTES;
+    const uint32_t bars = patches + 4 * PATCH_BYTES;
     auto full_raw = [&](int s) { return bars + 8u * s; };
     auto full_lo = [&](int s) { return bars + 8u * (STAGES + s); };
     auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
     auto chunk_full = [&](int b) { return bars + 8u * (3 * STAGES + b); };
-    auto chunk_drained = [&](int b) { return bars + 8u * (3 * STAGES + 2 + b); };
-    const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 4);    // 4 bytes: TMEM base address written by tcgen05.alloc
+    auto chunk_drained = [&](int b) { return bars + 8u * (3 * STAGES + NACC + b); };
+    const uint32_t tmem_slot = bars + 8u * (3 * STAGES + 2 * NACC);    // 4 bytes: TMEM base address written by tcgen05.alloc
     unsigned char *smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile_m = blockIdx.x % args.tiles_m, tile_n = blockIdx.x / args.tiles_m;
     const int nsteps = (int)((args.K + BK - 1) / BK);
+    const int nchunks = (nsteps + KCB - 1) / KCB;
+    // static tile schedule: this CTA owns tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; tile_m runs fastest, so the CTAs that are
+    // resident together share B panels (and, a little later, A panels) in L2
+    const int64_t tiles_per_batch = (int64_t)args.tiles_m * args.tiles_n, total_tiles = tiles_per_batch * args.batch;
+    const int     my_tiles = (int)((total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    auto decode = [&](int i, int &tile_m, int &tile_n, int &b) {
+        const int64_t t = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
+        b = (int)(t / tiles_per_batch);
+        const int in = (int)(t - (int64_t)b * tiles_per_batch);
+        tile_n = in / args.tiles_m;
+        tile_m = in - tile_n * args.tiles_m;
+    };
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) {
@@ -90,7 +108,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32x3_tcgen05(const __grid_const
             mbar_init(full_lo(s), 128);
             mbar_init(empty(s), 1);
         }
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < NACC; b++) {
             mbar_init(chunk_full(b), 1);
             mbar_init(chunk_drained(b), 128);
         }
@@ -107,156 +125,286 @@ __global__ void __launch_bounds__(192, 1) gemm_tf32x3_tcgen05(const __grid_const
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp == 0) {
+        // ===================== TMA producer =====================
         if (lane == 0) {
-            for (int it = 0; it < nsteps; it++) {
-                const int s = it % STAGES;
-                if (it >= STAGES) mbar_wait(empty(s), ((it / STAGES) - 1) & 1);
-                const uint32_t a_dst = smem_base + s * STAGE_BYTES, b_dst = a_dst + TILE_BYTES;
-                mbar_expect_tx(full_raw(s), RAW_BYTES);
-                if constexpr (A_MN) { // box {32 m, 32 k}: four boxes cover the 128 rows of the tile
+            int gs = 0; // k-steps issued by this CTA since the start (all tiles): stage = gs % STAGES
+            for (int i = 0; i < my_tiles; i++) {
+                int tile_m, tile_n, b;
+                decode(i, tile_m, tile_n, b);
+                for (int it = 0; it < nsteps; it++, gs++) {
+                    const int s = gs % STAGES;
+                    if (gs >= STAGES) mbar_wait(empty(s), ((gs / STAGES) - 1) & 1);
+                    const uint32_t a_dst = smem_base + s * STAGE_BYTES, b_dst = a_dst + TILE_BYTES;
+                    mbar_expect_tx(full_raw(s), RAW_BYTES);
+                    if constexpr (A_MN) { // box {32 m, 32 k}: four boxes cover the 128 rows of the tile
 #pragma unroll
-                    for (int b = 0; b < 4; b++) tma_load_2d(a_dst + b * 4096, &tmA, full_raw(s), tile_m * BM + 32 * b, it * BK);
-                } else tma_load_2d(a_dst, &tmA, full_raw(s), it * BK, tile_m * BM); // box {32 k, 128 m}
-                if constexpr (B_MN) {
+                        for (int q = 0; q < 4; q++) tma_load_3d(a_dst + q * 4096, &tmA, full_raw(s), tile_m * BM + 32 * q, it * BK, b);
+                    } else tma_load_3d(a_dst, &tmA, full_raw(s), it * BK, tile_m * BM, b); // box {32 k, 128 m}
+                    if constexpr (B_MN) {
 #pragma unroll
-                    for (int b = 0; b < 4; b++) tma_load_2d(b_dst + b * 4096, &tmB, full_raw(s), tile_n * BN + 32 * b, it * BK);
-                } else tma_load_2d(b_dst, &tmB, full_raw(s), it * BK, tile_n * BN);
+                        for (int q = 0; q < 4; q++) tma_load_3d(b_dst + q * 4096, &tmB, full_raw(s), tile_n * BN + 32 * q, it * BK, b);
+                    } else tma_load_3d(b_dst, &tmB, full_raw(s), it * BK, tile_n * BN, b);
+                }
             }
         }
     } else if (warp == 1) {
+        // ===================== tcgen05.mma issuer =====================
         if (lane == 0) {
-            for (int it = 0; it < nsteps; it++) {
-                const int s = it % STAGES;
-                const int c = it / KCB, cb = c & 1;               // accumulation chunk and its TMEM accumulator
-                if (it % KCB == 0 && c >= 2) {                     // the accumulator must have been drained (chunk c-2)
-                    mbar_wait(chunk_drained(cb), ((c >> 1) - 1) & 1);
+            int gs = 0, gc = 0; // global k-step and accumulation-chunk counters of this CTA
+            for (int i = 0; i < my_tiles; i++) {
+                for (int it = 0; it < nsteps; it++, gs++) {
+                    const int s = gs % STAGES, ab = gc & (NACC - 1);
+                    if (it % KCB == 0 && gc >= NACC) { // the accumulator must have been drained (chunk gc - NACC)
+                        mbar_wait(chunk_drained(ab), ((gc / NACC) - 1) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    mbar_wait(full_lo(s), (gs / STAGES) & 1); // splitters are done => the raw tile landed too
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                }
-                mbar_wait(full_lo(s), (it / STAGES) & 1);   // splitters are done => the raw tile landed too
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_hi = smem_base + s * STAGE_BYTES, b_hi = a_hi + TILE_BYTES, a_lo = a_hi + RAW_BYTES, b_lo = a_lo + TILE_BYTES;
-                const uint32_t tacc = tmem_base + (uint32_t)cb * 128u;
+                    const uint32_t a_hi = smem_base + s * STAGE_BYTES, b_hi = a_hi + TILE_BYTES, a_lo = a_hi + RAW_BYTES, b_lo = a_lo + TILE_BYTES;
+                    // The hi*hi product and the two cross terms go to DIFFERENT accumulators: every accumulation step truncates the FP32
+                    // accumulator (a one-sided error of up to 1 ulp of the running sum), so the large sum should absorb as few steps as
+                    // possible; the cross terms are 2^-10 of it and their own truncation does not matter.
+                    const uint32_t tacc_hi = tmem_base + (uint32_t)ab * 256u, tacc_x = tacc_hi + 128u;
 #pragma unroll
-                for (int kk = 0; kk < BK / 8; kk++) {
-                    // one MMA consumes 8 k: 32 bytes along the swizzle row of a K-major tile, one 8-row (1024-byte) atom of an MN-major tile
-                    const uint32_t koa = kk * (A_MN ? 1024 : 32), kob = kk * (B_MN ? 1024 : 32);
-                    const uint64_t dah = umma_smem_desc_sw128<A_MN>(a_hi + koa), dbh = umma_smem_desc_sw128<B_MN>(b_hi + kob);
-                    const uint64_t dal = umma_smem_desc_sw128<A_MN>(a_lo + koa), dbl = umma_smem_desc_sw128<B_MN>(b_lo + kob);
-                    umma_tf32(tacc, dal, dbh, IDESC, ((it % KCB) | kk) != 0);
-                    umma_tf32(tacc, dah, dbl, IDESC, 1);
-                    umma_tf32(tacc, dah, dbh, IDESC, 1);
+                    for (int kk = 0; kk < BK / 8; kk++) {
+                        // one MMA consumes 8 k: 32 bytes along the swizzle row of a K-major tile, one 8-row (1024-byte) atom of an MN-major tile
+                        const uint32_t koa = kk * (A_MN ? 1024 : 32), kob = kk * (B_MN ? 1024 : 32);
+                        const uint64_t dah = umma_smem_desc_sw128<A_MN>(a_hi + koa), dbh = umma_smem_desc_sw128<B_MN>(b_hi + kob);
+                        const uint64_t dal = umma_smem_desc_sw128<A_MN>(a_lo + koa), dbl = umma_smem_desc_sw128<B_MN>(b_lo + kob);
+                        const uint32_t first = ((it % KCB) | kk) == 0;
+                        umma_tf32(tacc_x, dal, dbh, IDESC, !first);
+                        umma_tf32(tacc_x, dah, dbl, IDESC, 1);
+                        umma_tf32(tacc_hi, dah, dbh, IDESC, !first);
+                    }
+                    umma_commit(empty(s));
+                    if (it % KCB == KCB - 1 || it == nsteps - 1) {
+                        umma_commit(chunk_full(ab));
+                        gc++;
+                    }
                 }
-                umma_commit(empty(s));
-                if (it % KCB == KCB - 1 || it == nsteps - 1) umma_commit(chunk_full(cb));
             }
         }
-    } else {
-        // ===================== splitters (warps 2..5, 128 threads); they also drain finished K chunks =====================
-        const int     t = tid - 64;
-        const int     quad = warp & 3;                       // TMEM lane quadrant of this warp: warps 2,3,4,5 -> 2,3,0,1
-        const int     nchunks = (nsteps + KCB - 1) / KCB;
-        float         acc[BN];                               // this thread's output row (TMEM lane), summed over chunks in FP32 RN
-#pragma unroll
-        for (int j = 0; j < BN; j++) acc[j] = 0.f;
-        int drained = 0;
-        // The tensor core accumulates into TMEM with truncation, so the error of one accumulator grows linearly with the number of
-        // k-steps it has absorbed. Every KCB k-blocks the issuer switches to the other accumulator and the finished one is added
-        // into registers with round-to-nearest here; signs of the chunk biases are independent, so the total stays at the one-chunk level.
-        auto drain = [&](int d) {
-            const int db = d & 1;
-            mbar_wait(chunk_full(db), (d >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t       r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(db * 128 + c0);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-                      "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-                      "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
-                      "=r"(r[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int j = 0; j < 32; j++) acc[c0 + j] += __uint_as_float(r[j]);
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(chunk_drained(db));
-        };
-        for (int it = 0; it < nsteps; it++) {
-            const int s = it % STAGES;
-            mbar_wait(full_raw(s), (it / STAGES) & 1);
-            float4 *raw = reinterpret_cast<float4 *>(smem_gen + s * STAGE_BYTES);
-            float4 *lo = reinterpret_cast<float4 *>(smem_gen + s * STAGE_BYTES + RAW_BYTES);
-#pragma unroll 4
+    } else if (warp < 6) {
+        // ===================== splitters (warps 2..5, 128 threads) =====================
+        // The tensor core reads only the upper 19 bits of an FP32 container, so the raw tile IS the hi part (x truncated to TF32);
+        // lo = x - trunc(x) is exact in FP32 and goes to the second buffer in the same swizzled layout.
+        const int t = tid - 64;
+        const int total_steps = my_tiles * nsteps;
+        for (int gs = 0; gs < total_steps; gs++) {
+            const int s = gs % STAGES;
+            mbar_wait(full_raw(s), (gs / STAGES) & 1);
+            const float4 *raw = reinterpret_cast<const float4 *>(smem_gen + s * STAGE_BYTES);
+            float4       *lo = reinterpret_cast<float4 *>(smem_gen + s * STAGE_BYTES + RAW_BYTES);
+#pragma unroll 8
             for (int i = 0; i < (int)(RAW_BYTES / 16 / 128); i++) {
-                const int idx = i * 128 + t;
-                float4    x = raw[idx], h, l;
-                // hi = x rounded to nearest TF32 (10-bit mantissa), lo = x - hi (exact) rounded to nearest TF32 as well
-                auto rn_tf32 = [](float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); };
-                h.x = rn_tf32(x.x); l.x = rn_tf32(x.x - h.x);
-                h.y = rn_tf32(x.y); l.y = rn_tf32(x.y - h.y);
-                h.z = rn_tf32(x.z); l.z = rn_tf32(x.z - h.z);
-                h.w = rn_tf32(x.w); l.w = rn_tf32(x.w - h.w);
-                raw[idx] = h;
+                const int    idx = i * 128 + t;
+                const float4 x = raw[idx];
+                float4       l;
+                auto tr = [](float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); };
+                l.x = x.x - tr(x.x);
+                l.y = x.y - tr(x.y);
+                l.z = x.z - tr(x.z);
+                l.w = x.w - tr(x.w);
                 lo[idx] = l;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy stores -> visible to the tensor core's async proxy
             mbar_arrive(full_lo(s));
-            // a chunk is drained two k-blocks after its last k-block was split: its MMAs have normally completed by then, so neither
-            // side waits; the issuer only re-uses an accumulator after this drain (chunk_drained)
-            if (drained < nchunks - 1 && it >= (drained + 1) * KCB + 1) drain(drained++);
         }
-        while (drained < nchunks) drain(drained++);
-
-        // ===================== epilogue: alpha*acc + beta*C, one output row per thread =====================
-        const int64_t m = (int64_t)tile_m * BM + quad * 32 + lane;
-        const float   alpha = args.alpha, beta = args.beta;
-        float        *patch = reinterpret_cast<float *>(smem_gen) + (warp - 2) * (32 * 33);
-#pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            const int64_t n0 = (int64_t)tile_n * BN + c0;
+    } else {
+        // ===================== epilogue warps (6..9): drain finished chunks, store finished tiles =====================
+        // They run one tile behind the issuer: while tile i is converted and stored from here, the tensor core already accumulates
+        // tile i + 1 into the other accumulators.
+        const int quad = warp & 3;                       // TMEM lane quadrant of this warp: warps 6,7,8,9 -> 2,3,0,1
+        float    *patch = reinterpret_cast<float *>(smem_gen + STAGES * STAGE_BYTES) + (warp - 6) * (32 * 33);
+        const float alpha = args.alpha, beta = args.beta;
+        auto tmem_ld32 = [&](uint32_t taddr, uint32_t(&r)[32]) {
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                  "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+                  "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+                  "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        };
+        auto tmem_ld16 = [&](uint32_t taddr, uint32_t(&r)[16]) { // no wait: the caller waits once for several loads
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                           "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                         : "r"(taddr));
+        };
+        // store 32 columns [n0, n0 + 32) of this thread's row: out = alpha * v + beta * C
+        auto store_block = [&](float *Cb, int tile_m, int64_t n0, const float(&v)[32]) {
+            const int64_t m = (int64_t)tile_m * BM + quad * 32 + lane;
             if (args.sCn == 1) {
-                // C rows are contiguous along n: transpose the 32x32 chunk through a warp-private shared-memory patch (the pipeline
-                // stages are idle by now) so that every store/load instruction covers one 128-byte row segment
+                // C rows are contiguous along n: transpose the 32x32 block through a warp-private shared-memory patch so that every
+                // store/load instruction covers one 128-byte row segment
 #pragma unroll
-                for (int j = 0; j < 32; j++) patch[lane * 33 + j] = acc[c0 + j];
+                for (int j = 0; j < 32; j++) patch[lane * 33 + j] = v[j];
                 __syncwarp();
                 const int64_t n = n0 + lane, mrow0 = (int64_t)tile_m * BM + quad * 32;
                 if (n < args.N) {
-                    float old[32];
-                    if (beta != 0.f) { // every old C value of the chunk is requested before the first use
 #pragma unroll
-                        for (int rr = 0; rr < 32; rr++) old[rr] = (mrow0 + rr < args.M) ? args.C[(mrow0 + rr) * args.sCm + n] : 0.f;
-                    }
+                    for (int r0 = 0; r0 < 32; r0 += 16) { // the 16 old C values of a half block are requested before their first use
+                        float old[16];
+                        if (beta != 0.f) {
 #pragma unroll
-                    for (int rr = 0; rr < 32; rr++) {
-                        const int64_t mm = mrow0 + rr;
-                        if (mm < args.M) {
-                            float v = alpha * patch[rr * 33 + lane];
-                            if (beta != 0.f) v = fmaf(beta, old[rr], v);
-                            args.C[mm * args.sCm + n] = v;
+                            for (int rr = 0; rr < 16; rr++) old[rr] = (mrow0 + r0 + rr < args.M) ? Cb[(mrow0 + r0 + rr) * args.sCm + n] : 0.f;
+                        }
+#pragma unroll
+                        for (int rr = 0; rr < 16; rr++) {
+                            const int64_t mm = mrow0 + r0 + rr;
+                            if (mm < args.M) {
+                                float o = alpha * patch[(r0 + rr) * 33 + lane];
+                                if (beta != 0.f) o = fmaf(beta, old[rr], o);
+                                Cb[mm * args.sCm + n] = o;
+                            }
                         }
                     }
                 }
                 __syncwarp();
             } else if (m < args.M) {
                 // lanes are consecutive rows m: coalesced when C is contiguous along m (the "transposed C" case, e.g. Wabef)
-                float *crow = args.C + m * args.sCm;
-                float  old[32];
-                if (beta != 0.f) {
+                float *crow = Cb + m * args.sCm;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) old[j] = (n0 + j < args.N) ? crow[(n0 + j) * args.sCn] : 0.f;
+                for (int j0 = 0; j0 < 32; j0 += 16) {
+                    float old[16];
+                    if (beta != 0.f) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) old[j] = (n0 + j0 + j < args.N) ? crow[(n0 + j0 + j) * args.sCn] : 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const int64_t n = n0 + j0 + j;
+                        if (n < args.N) {
+                            float o = alpha * v[j0 + j];
+                            if (beta != 0.f) o = fmaf(beta, old[j], o);
+                            crow[n * args.sCn] = o;
+                        }
+                    }
+                }
+            }
+        };
+        int gc = 0;
+        for (int i = 0; i < my_tiles; i++) {
+            int tile_m, tile_n, b;
+            decode(i, tile_m, tile_n, b);
+            float *Cb = args.C + (int64_t)b * args.sCb;
+            if constexpr (!MULTI) {
+                // K <= 512: one chunk per tile. Each 32-column block goes TMEM -> registers -> global; the accumulator pair is handed
+                // back after the last block has been read.
+                const int ab = gc & (NACC - 1);
+                if (args.sCn == 1) {
+                    // C rows contiguous along n (the usual case). With beta != 0 the old C tile of the NEXT tile is pulled into L2 now
+                    // (prefetch.global.L2: no registers, no shared memory), and the 32 old values a lane needs for a block are requested
+                    // before the block's accumulator columns are read, so their (L2-hit) latency overlaps the TMEM load and the transposition.
+                    const int64_t mrow0 = (int64_t)tile_m * BM + quad * 32, nbase = (int64_t)tile_n * BN + lane;
+                    if (beta != 0.f) {
+                        auto prefetch_tile = [&](int ti) {
+                            int pm, pn, pb;
+                            decode(ti, pm, pn, pb);
+                            const int64_t row = (int64_t)pm * BM + quad * 32 + lane, col = (int64_t)pn * BN;
+                            if (row < args.M) {
+                                const float *pr = args.C + (int64_t)pb * args.sCb + row * args.sCm;
+#pragma unroll
+                                for (int c = 0; c < BN; c += 32)
+                                    if (col + c < args.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + col + c));
+                            }
+                        };
+                        if (i == 0) prefetch_tile(0);
+                        if (i + 1 < my_tiles) prefetch_tile(i + 1);
+                    }
+                    mbar_wait(chunk_full(ab), (gc / NACC) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                    for (int q = 0; q < BN / 32; q++) {
+                        const int64_t n = nbase + 32 * q;
+                        float         old[32];
+                        if (beta != 0.f && n < args.N) {
+#pragma unroll
+                            for (int rr = 0; rr < 32; rr++) old[rr] = (mrow0 + rr < args.M) ? Cb[(mrow0 + rr) * args.sCm + n] : 0.f;
+                        }
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            uint32_t       r[16], x[16];
+                            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * 256 + 32 * q + 16 * h);
+                            tmem_ld16(taddr, r);
+                            tmem_ld16(taddr + 128u, x);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                            for (int j = 0; j < 16; j++) patch[lane * 33 + 16 * h + j] = __uint_as_float(r[j]) + __uint_as_float(x[j]);
+                        }
+                        if (q == BN / 32 - 1) {
+                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                            mbar_arrive(chunk_drained(ab));
+                        }
+                        __syncwarp();
+                        if (n < args.N) {
+#pragma unroll
+                            for (int rr = 0; rr < 32; rr++) {
+                                const int64_t mm = mrow0 + rr;
+                                if (mm < args.M) {
+                                    float o = alpha * patch[rr * 33 + lane];
+                                    if (beta != 0.f) o = fmaf(beta, old[rr], o);
+                                    Cb[mm * args.sCm + n] = o;
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                } else {
+                    mbar_wait(chunk_full(ab), (gc / NACC) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                    for (int c0 = 0; c0 < BN; c0 += 32) {
+                        uint32_t       r[32], x[32];
+                        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * 256 + c0);
+                        tmem_ld32(taddr, r);
+                        tmem_ld32(taddr + 128u, x);
+                        if (c0 == BN - 32) {
+                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                            mbar_arrive(chunk_drained(ab));
+                        }
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]) + __uint_as_float(x[j]);
+                        store_block(Cb, tile_m, (int64_t)tile_n * BN + c0, v);
+                    }
+                }
+                gc++;
+            } else {
+                // K > 512: finished chunks are added into registers with round-to-nearest (the error of an accumulator grows with the
+                // number of k-steps it has absorbed; chunk biases of mixed-sign data are independent, so the total stays at the one-chunk level)
+                float acc[BN];
+                for (int ch = 0; ch < nchunks; ch++, gc++) {
+                    const int ab = gc & (NACC - 1);
+                    mbar_wait(chunk_full(ab), (gc / NACC) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                    for (int c0 = 0; c0 < BN; c0 += 32) {
+                        uint32_t       r[32];
+                        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * 256 + c0);
+                        tmem_ld32(taddr, r);
+                        if (ch == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) acc[c0 + j] = __uint_as_float(r[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) acc[c0 + j] += __uint_as_float(r[j]);
+                        }
+                        tmem_ld32(taddr + 128u, r);
+#pragma unroll
+                        for (int j = 0; j < 32; j++) acc[c0 + j] += __uint_as_float(r[j]);
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(chunk_drained(ab));
                 }
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const int64_t n = n0 + j;
-                    if (n < args.N) {
-                        float v = alpha * acc[c0 + j];
-                        if (beta != 0.f) v = fmaf(beta, old[j], v);
-                        crow[n * args.sCn] = v;
-                    }
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = acc[c0 + j];
+                    store_block(Cb, tile_m, (int64_t)tile_n * BN + c0, v);
                 }
             }
         }

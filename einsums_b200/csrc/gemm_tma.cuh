@@ -28,6 +28,7 @@ struct TmaGemmArgs {
     double *C;
     double  alpha, beta;
     int32_t tiles_m, tiles_n, vec_c;
+    int32_t dist;          // prefetch distance in k steps (1 .. STAGES-1), see contract_tma.cuh
 };
 
 template <bool A_KMAJOR, bool B_KMAJOR>
@@ -87,8 +88,9 @@ __global__ void __launch_bounds__(256, 2) gemm_tma_f64(const __grid_constant__ C
             for (int b = 0; b < BN / 16; b++) tma_load_2d(b_dst + b * 2048, &tmB, full_bar(s), n0_tile + 16 * b, k0);
         }
     };
+    const int dist = args.dist;
     if (tid == 0)
-        for (int it = 0; it < STAGES - 1 && it < nsteps; it++) issue_loads(it);
+        for (int it = 0; it < dist && it < nsteps; it++) issue_loads(it);
 
     // ===================== consumer warps =====================
     const int wm0 = (warp % 4) * 32, wn0 = (warp / 4) * 32;
@@ -114,8 +116,8 @@ __global__ void __launch_bounds__(256, 2) gemm_tma_f64(const __grid_constant__ C
     for (int it = 0; it < nsteps; it++) {
         const int s = it % STAGES;
         if (tid == 0) {
-            // refill the stage everybody finished one iteration ago
-            const int nxt = it + STAGES - 1;
+            // refill the stage everybody finished STAGES - dist iterations ago
+            const int nxt = it + dist;
             if (nxt < nsteps) {
                 if (nxt >= STAGES) mbar_wait(empty_bar(nxt % STAGES), ((nxt / STAGES) - 1) & 1);
                 issue_loads(nxt);

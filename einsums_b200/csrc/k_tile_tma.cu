@@ -19,6 +19,23 @@ int k_launch_tma(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB,
     return EB200_OK;
 }
 
+int k_launch_tma_z(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB, const TmaZGemmArgs &a, dim3 grid, size_t smem, bool ak, bool bk) {
+#define EB_TMA_CASE(AK, BK_)                                                    \
+    {                                                                           \
+        auto kern = gemm_tma_z<AK, BK_>;                                        \
+        int  rc = set_smem_attr(kern, smem);                                    \
+        if (rc) return rc;                                                      \
+        kern<<<grid, 256, smem, s>>>(tmA, tmB, a);                              \
+    }
+    if (ak && bk) EB_TMA_CASE(true, true)
+    else if (ak && !bk) EB_TMA_CASE(true, false)
+    else if (!ak && bk) EB_TMA_CASE(false, true)
+    else EB_TMA_CASE(false, false)
+#undef EB_TMA_CASE
+    EB_POST_LAUNCH("gemm_tma_z");
+    return EB200_OK;
+}
+
 namespace {
 template <class CFG> int launch_generic(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB, const TmaGenArgs &a, dim3 grid, bool ak, bool bk) {
 #define EB_TMA_CASE(AK, BK_)                                                    \

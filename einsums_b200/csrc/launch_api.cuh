@@ -5,6 +5,7 @@
 #include "gemm_tma.cuh"
 #include "contract_tma.cuh"
 #include "gemm_tf32x3.cuh"
+#include "gemm_tma_z.cuh"
 
 namespace eb200 {
 /// rows a CTA of the row-direction reductions owns. One output column and long rows: 8 rows = 8 independent 16-byte loads per
@@ -21,6 +22,8 @@ int k_launch_tma(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB,
                  bool bk);                                                                       // k_tile_tma.cu
 int k_launch_tma_generic(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB, const TmaGenArgs &a, dim3 grid, int cfg, bool ak,
                          bool bk);                                                               // k_tile_tma.cu
+int k_launch_tma_z(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB, const TmaZGemmArgs &a, dim3 grid, size_t smem, bool ak,
+                   bool bk);                                                                     // k_tile_tma.cu
 int k_launch_tf32x3(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB, const Tf32GemmArgs &a, dim3 grid, size_t smem, bool a_mn,
                     bool b_mn); // k_tile_tf32.cu
 int k_launch_reduce(int dtype, cudaStream_t s, bool row, ReduceArgs &a, dim3 grid);              // k_reduce_{real,cplx}.cu

@@ -565,6 +565,73 @@ def test_sgemm_tcgen05_layouts(gpu, a_idx, b_idx):
     assert rel_err(Wd.cpu().numpy().astype(np.float64), refW) <= 1e-5
 
 
+def test_sgemm_tcgen05_persistent_and_batched(gpu):
+    """The persistent tile loop (more tiles than SMs, so every CTA walks several tiles and the accumulators rotate) and the batched form
+    (one batch index carried by all three tensors: 3-D tensor maps), against float64 matmul; 1e-5 relative (3xTF32 with truncated hi)."""
+    from einsums_b200 import KF
+    torch.manual_seed(11)
+    # 24 x 20 = 480 tiles of 128 x 128 on 148 SMs, ragged edges, K = 3 chunks of 512 + a tail
+    m, n, k = 3000, 2500, 1700
+    A = torch.rand(m, k, dtype=torch.float32, device="cuda") * 2 - 1
+    B = torch.rand(n, k, dtype=torch.float32, device="cuda") * 2 - 1
+    C0 = torch.rand(m, n, dtype=torch.float32, device="cuda")
+    Cd = C0.clone()
+    d = gpu.contract("ij", Cd, "ik", A, "jk", B, 0.5, 2.0)
+    assert d.kernel_used == KF["TILE_TCGEN05"], d.kernel_used
+    ref = 0.5 * (A.double() @ B.double().T) + 2.0 * C0.double()
+    assert ((Cd.double() - ref).abs().max() / ref.abs().max()).item() <= 1e-5
+    # same-sign data: the truncation of hi and lo is a one-sided error; it must stay inside the tolerance
+    Ap, Bp = A.abs(), B.abs()
+    d = gpu.contract("ij", Cd, "ik", Ap, "jk", Bp, 1.0, 0.0)
+    ref = Ap.double() @ Bp.double().T
+    assert ((Cd.double() - ref).abs().max() / ref.abs().max()).item() <= 1e-5
+    # batched: C[b,i,j] = sum_k A[b,i,k] B[b,k,j] (A K-major, B N-major), batch outermost; and batch in the middle of C
+    nb, m, n, k = 7, 200, 264, 96
+    A = torch.rand(nb, m, k, dtype=torch.float32, device="cuda") * 2 - 1
+    B = torch.rand(nb, k, n, dtype=torch.float32, device="cuda") * 2 - 1
+    C0 = torch.rand(nb, m, n, dtype=torch.float32, device="cuda")
+    Cd = C0.clone()
+    d = gpu.contract("bij", Cd, "bik", A, "bkj", B, 2.0, -1.0)
+    assert d.kernel_used == KF["TILE_TCGEN05"], d.kernel_used
+    ref = 2.0 * torch.bmm(A.double(), B.double()) - C0.double()
+    assert ((Cd.double() - ref).abs().max() / ref.abs().max()).item() <= 1e-5
+    Cm = torch.zeros(m, nb, n, dtype=torch.float32, device="cuda")
+    d = gpu.contract("ibj", Cm, "bik", A, "bkj", B)
+    assert d.kernel_used == KF["TILE_TCGEN05"], d.kernel_used
+    ref = torch.bmm(A.double(), B.double()).permute(1, 0, 2)
+    assert ((Cm.double() - ref).abs().max() / ref.abs().max()).item() <= 1e-5
+
+
+@pytest.mark.parametrize("a_idx,b_idx", [("ik", "jk"), ("ki", "jk"), ("ik", "kj"), ("ki", "kj")])
+def test_zgemm_tensor_pipe(gpu, oracle, a_idx, b_idx):
+    """c128 plain products on the FP64 tensor pipe (gemm_tma_z: interleaved complex tiles by TMA, four real DMMA products per complex
+    product): all four operand layouts, ragged M/N/K, complex alpha/beta, both conjugation flags, against the oracle's generic loops."""
+    ext = dict(i=1100, j=712, k=101)
+    for (alpha, beta, ca, cb) in ((1.0, 0.0, False, False), (0.5 - 0.25j, 2.0 + 1.0j, True, False), (-1.0j, 1.0, False, True), (1.0, 0.0, True, True)):
+        run_case(gpu, oracle, "ij", a_idx, b_idx, ext, np.complex128, alpha, beta, ca, cb, seed=91)
+        assert gpu.last_kernel() == "gemm_tma_z", gpu.last_kernel()
+    run_case(gpu, oracle, "ji", a_idx, b_idx, ext, np.complex128, 0.5, 0.5, seed=92)        # C stored transposed
+    assert gpu.last_kernel() == "gemm_tma_z"
+
+
+def test_zgemm_seam_tensor_pipe(gpu):
+    """eb200_zgemm (column-major flat seam) at a size that takes the tensor-pipe kernel: 'n', 't' and 'c' operands against numpy."""
+    rng = np.random.default_rng(93)
+    m, n, k = 1024, 640, 200
+    z = lambda *s: (rng.uniform(-1, 1, s) + 1j * rng.uniform(-1, 1, s))
+    for ta, tb in (("n", "n"), ("c", "n"), ("n", "c"), ("t", "c")):
+        A = z(m, k) if ta == "n" else z(k, m)      # column-major (ld = rows): stored here as the transpose in C order
+        B = z(k, n) if tb == "n" else z(n, k)
+        C0 = z(m, n)
+        op = lambda X, t: X if t == "n" else (X.T if t == "t" else X.conj().T)
+        ref = (0.5 + 0.5j) * (op(A, ta) @ op(B, tb)) + (2.0 - 1.0j) * C0
+        Ad, Bd, Cd = dev(np.asfortranarray(A).T), dev(np.asfortranarray(B).T), dev(np.asfortranarray(C0).T)
+        gpu.gemm(ta, tb, m, n, k, 0.5 + 0.5j, Ad, A.shape[0], Bd, B.shape[0], 2.0 - 1.0j, Cd, m)
+        assert gpu.last_kernel() == "gemm_tma_z", (ta, tb, gpu.last_kernel())
+        out = Cd.cpu().numpy().T
+        assert rel_err(out, ref) <= 1e-12, (ta, tb)
+
+
 def test_sgemm_zgemm(gpu, oracle):
     import ctypes as C
     rng = np.random.default_rng(9)
