@@ -275,7 +275,6 @@ template <typename T, size_t R> class BlockDeviceTensor {
     T                        *_store = nullptr;
 };
 
-template <typename X> struct IsBlockDeviceTensor : std::false_type {};
 template <typename T, size_t R> struct IsBlockDeviceTensor<BlockDeviceTensor<T, R>> : std::true_type {};
 template <typename X>
 concept BlockDeviceTensorLike = IsBlockDeviceTensor<std::remove_cvref_t<X>>::value;
@@ -329,7 +328,9 @@ template <typename A, typename B> auto const &first_block_tensor(A const &a, B c
 /// DeviceTensor or host value: the per-block results are summed). One grouped launch sequence, one wait.
 template <bool ConjA = false, bool ConjB = false, typename AType, typename BType, typename CType, typename U, typename... CIndices,
           typename... AIndices, typename... BIndices>
-    requires((BlockDeviceTensorLike<AType> || BlockDeviceTensorLike<BType>) && (std::is_arithmetic_v<U> || IsComplexV<U>))
+    requires((BlockDeviceTensorLike<AType> || BlockDeviceTensorLike<BType>) && (std::is_arithmetic_v<U> || IsComplexV<U>) &&
+             !IsTiledDeviceTensor<std::remove_cvref_t<AType>>::value && !IsTiledDeviceTensor<std::remove_cvref_t<BType>>::value &&
+             !IsTiledDeviceTensor<std::remove_cvref_t<CType>>::value)
 void einsum(U const UC_prefactor, std::tuple<CIndices...> const &, CType *C, U const UAB_prefactor, std::tuple<AIndices...> const &,
             AType const &A, std::tuple<BIndices...> const &, BType const &B, detail::AlgorithmChoice *algorithm_choice = nullptr) {
     using namespace detail;
@@ -391,7 +392,8 @@ void einsum(U const UC_prefactor, std::tuple<CIndices...> const &, CType *C, U c
 
 template <bool ConjA = false, bool ConjB = false, typename AType, typename BType, typename CType, typename... CIndices, typename... AIndices,
           typename... BIndices>
-    requires(BlockDeviceTensorLike<AType> || BlockDeviceTensorLike<BType>)
+    requires((BlockDeviceTensorLike<AType> || BlockDeviceTensorLike<BType>) && !IsTiledDeviceTensor<std::remove_cvref_t<AType>>::value &&
+             !IsTiledDeviceTensor<std::remove_cvref_t<BType>>::value && !IsTiledDeviceTensor<std::remove_cvref_t<CType>>::value)
 void einsum(std::tuple<CIndices...> const &C_indices, CType *C, std::tuple<AIndices...> const &A_indices, AType const &A,
             std::tuple<BIndices...> const &B_indices, BType const &B, detail::AlgorithmChoice *algorithm_choice = nullptr) {
     using V = typename detail::BlockValueOf<CType>::type;

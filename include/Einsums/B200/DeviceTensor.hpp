@@ -685,6 +685,12 @@ template <typename T = double, typename... Dims> DeviceTensor<T, sizeof...(Dims)
 }
 template <typename TensorT> void zero(TensorT &t) { t.zero(); }
 
+/// true for TiledDeviceTensor (specialised in TiledTensor.hpp); declared here so that the block-tensor overloads can step aside for the
+/// mixed block x tiled algebra (BlockTileAlgebra.hpp) without including the tiled header
+template <typename X> struct IsTiledDeviceTensor : std::false_type {};
+/// likewise for BlockDeviceTensor (specialised in BlockTensor.hpp)
+template <typename X> struct IsBlockDeviceTensor : std::false_type {};
+
 template <typename X>
 concept DeviceTensorLike = requires(X const &x) {
     typename std::remove_cvref_t<X>::ValueType;

@@ -279,7 +279,6 @@ template <typename T, size_t R> class TiledDeviceTensor {
     std::unique_ptr<detail::DeviceArena>         _arena;
 };
 
-template <typename X> struct IsTiledDeviceTensor : std::false_type {};
 template <typename T, size_t R> struct IsTiledDeviceTensor<TiledDeviceTensor<T, R>> : std::true_type {};
 template <typename X>
 concept TiledDeviceTensorLike = IsTiledDeviceTensor<std::remove_cvref_t<X>>::value;
@@ -431,7 +430,7 @@ template <typename Tuple, size_t N> void fill_table(IdPack const &all, IdPack co
 /// einsum over tiled tensors; C is a tiled tensor or a scalar (host value / rank-0 DeviceTensor)
 template <bool ConjA = false, bool ConjB = false, TiledDeviceTensorLike AType, TiledDeviceTensorLike BType, typename CType, typename U,
           typename... CIndices, typename... AIndices, typename... BIndices>
-    requires(std::is_arithmetic_v<U> || IsComplexV<U>)
+    requires((std::is_arithmetic_v<U> || IsComplexV<U>) && !IsBlockDeviceTensor<std::remove_cvref_t<CType>>::value)
 void einsum(U const UC_prefactor, std::tuple<CIndices...> const &, CType *C, U const UAB_prefactor, std::tuple<AIndices...> const &,
             AType const &A, std::tuple<BIndices...> const &, BType const &B, detail::AlgorithmChoice *algorithm_choice = nullptr) {
     using namespace detail;
@@ -459,6 +458,7 @@ void einsum(U const UC_prefactor, std::tuple<CIndices...> const &, CType *C, U c
 }
 template <bool ConjA = false, bool ConjB = false, TiledDeviceTensorLike AType, TiledDeviceTensorLike BType, typename CType, typename... CIndices,
           typename... AIndices, typename... BIndices>
+    requires(!IsBlockDeviceTensor<std::remove_cvref_t<CType>>::value)
 void einsum(std::tuple<CIndices...> const &C_indices, CType *C, std::tuple<AIndices...> const &A_indices, AType const &A,
             std::tuple<BIndices...> const &B_indices, BType const &B, detail::AlgorithmChoice *algorithm_choice = nullptr) {
     using V = typename AType::ValueType;

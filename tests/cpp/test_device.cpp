@@ -7,6 +7,7 @@
 #include <Einsums/Tensor/BlockTensor.hpp>
 #include <Einsums/Tensor/DeviceTensor.hpp>
 #include <Einsums/Tensor/TiledTensor.hpp>
+#include <Einsums/Tensor/BlockTileAlgebra.hpp>
 #include <Einsums/TensorAlgebra.hpp>
 
 #include "mini_test.hpp"
@@ -895,6 +896,97 @@ TEST_CASE(gpu_tiled_tensor_sparse_random) { // absent tiles, ragged grids, prefa
     // incompatible grids
     TiledDeviceTensor<double, 2> Bad("Bad", einsums::detail::DEV_ONLY, std::array{4, 4});
     CHECK_THROWS_AS(einsum(Indices{i, j}, &C, Indices{i, k}, A, Indices{k, j}, Bad), tensor_compat_error);
+}
+
+TEST_CASE(gpu_block_tile_mixed_algebra) { // TA/Backends/BlockTileAlgebra.hpp:18-174: a block tensor acts as a tiled one with diagonal tiles only
+    using namespace einsums::index;
+    std::vector<int64_t> sizes{6, 0, 9, 4};
+    BlockDeviceTensor<double, 2> Ab("Ab", sizes), Cb("Cb", sizes);
+    TiledDeviceTensor<double, 2> Bt("Bt", sizes), Ct("Ct", sizes), At("At", sizes);
+    std::mt19937_64 eng(17);
+    std::uniform_real_distribution<double> dist(-1, 1);
+    for (size_t b = 0; b < Ab.num_blocks(); b++) {
+        if (!Ab.block_dim(b)) continue;
+        std::vector<double> h(size_t(Ab.block(b).size()));
+        for (auto &v : h) v = dist(eng);
+        Ab.block(b).read(h);
+        for (auto &v : h) v = dist(eng);
+        Cb.block(b).read(h);
+    }
+    int n = 0;
+    auto fill = [&](auto &X, int skip_mod) {
+        X.for_each_grid([&](auto idx) {
+            if (X.has_zero_size(idx) || (n++ % skip_mod) == 2) return;
+            auto &t = X.tile(idx);
+            std::vector<double> h(size_t(t.size()));
+            for (auto &v : h) v = dist(eng);
+            t.read(h);
+        });
+    };
+    fill(Bt, 4); fill(At, 3); fill(Ct, 2);
+    auto dense_mm = [](Host<double, 2> &a, Host<double, 2> &b, int64_t nn) {
+        std::vector<double> out(size_t(nn * nn), 0.0);
+        for (int64_t x = 0; x < nn; x++) for (int64_t y = 0; y < nn; y++) { double s = 0; for (int64_t q = 0; q < nn; q++) s += a(x, q) * b(q, y); out[size_t(x * nn + y)] = s; }
+        return out;
+    };
+    const int64_t N = Ab.dim(0);
+    auto hA = host((DeviceTensor<double, 2>)Ab), hB = host((DeviceTensor<double, 2>)Bt), hAt = host((DeviceTensor<double, 2>)At);
+    // (1) tiled <- block x tiled, with prefactors
+    auto hC0 = host((DeviceTensor<double, 2>)Ct);
+    AlgorithmChoice alg;
+    einsum(0.5, Indices{i, j}, &Ct, 2.0, Indices{i, k}, Ab, Indices{k, j}, Bt, &alg);
+    CHECK(alg == ta::GENERIC);
+    auto ref = dense_mm(hA, hB, N);
+    auto hC = host((DeviceTensor<double, 2>)Ct);
+    double worst = 0;
+    for (size_t q = 0; q < ref.size(); q++) worst = std::max(worst, std::abs(hC.v[q] - (0.5 * hC0.v[q] + 2.0 * ref[q])));
+    CHECK(worst <= 1e-12);
+    // (2) tiled <- tiled x block (beta = 0)
+    TiledDeviceTensor<double, 2> C2("C2", sizes);
+    einsum(Indices{i, j}, &C2, Indices{i, k}, At, Indices{k, j}, Ab);
+    ref = dense_mm(hAt, hA, N);
+    auto hC2 = host((DeviceTensor<double, 2>)C2);
+    worst = 0;
+    for (size_t q = 0; q < ref.size(); q++) worst = std::max(worst, std::abs(hC2.v[q] - ref[q]));
+    CHECK(worst <= 1e-12);
+    // (3) block <- tiled x tiled: only the diagonal blocks of the product are kept
+    auto hCb0 = host((DeviceTensor<double, 2>)Cb);
+    einsum(1.0, Indices{i, j}, &Cb, -1.0, Indices{i, k}, At, Indices{k, j}, Bt);
+    ref = dense_mm(hAt, hB, N);
+    auto hCb = host((DeviceTensor<double, 2>)Cb);
+    worst = 0;
+    for (size_t b = 0; b < Cb.num_blocks(); b++) {
+        Range r = Cb.block_range(b);
+        for (int64_t x = r[0]; x < r[1]; x++) for (int64_t y = r[0]; y < r[1]; y++)
+            worst = std::max(worst, std::abs(hCb(x, y) - (hCb0(x, y) - ref[size_t(x * N + y)])));
+    }
+    CHECK(worst <= 1e-12);
+    // incompatible grids
+    BlockDeviceTensor<double, 2> Bad("Bad", std::vector<int64_t>{5, 5});
+    CHECK_THROWS_AS(einsum(Indices{i, j}, &Ct, Indices{i, k}, Bad, Indices{k, j}, Bt), tensor_compat_error);
+
+    // tiled ger / direct_product (LinearAlgebra/TiledTensor.hpp:356-430)
+    TiledDeviceTensor<double, 1> X("X", sizes), Y("Y", sizes);
+    for (int t = 0; t < 4; t++) {
+        if (!sizes[size_t(t)]) continue;
+        std::vector<double> h(size_t(sizes[size_t(t)]));
+        for (auto &v : h) v = dist(eng);
+        X.tile(t).read(h);
+        if (t != 2) { for (auto &v : h) v = dist(eng); Y.tile(t).read(h); } // Y has no tile 2
+    }
+    auto hX = host((DeviceTensor<double, 1>)X), hY = host((DeviceTensor<double, 1>)Y);
+    auto hG0 = host((DeviceTensor<double, 2>)Ct);
+    linear_algebra::ger(0.75, X, Y, &Ct);
+    auto hG = host((DeviceTensor<double, 2>)Ct);
+    worst = 0;
+    for (int64_t x = 0; x < N; x++) for (int64_t y = 0; y < N; y++) worst = std::max(worst, std::abs(hG(x, y) - (hG0(x, y) + 0.75 * hX(x) * hY(y))));
+    CHECK(worst <= 1e-12);
+    TiledDeviceTensor<double, 2> D("D", sizes);
+    linear_algebra::direct_product(2.0, At, Bt, 0.0, &D);
+    auto hD = host((DeviceTensor<double, 2>)D);
+    worst = 0;
+    for (int64_t x = 0; x < N; x++) for (int64_t y = 0; y < N; y++) worst = std::max(worst, std::abs(hD(x, y) - 2.0 * hAt(x, y) * hB(x, y)));
+    CHECK(worst <= 1e-12);
 }
 
 int main() {
