@@ -808,6 +808,24 @@ template <typename T> __global__ void __launch_bounds__(256) dot_contig(const __
 #pragma unroll
     for (int u = 0; u < UNR; u++) acc[u] = zero_of<T>();
     int64_t k = k0 + threadIdx.x;
+    if constexpr (sizeof(T) == 8 && !Scalar<T>::is_complex) {
+        // 16-byte loads when both segments start on a 16-byte boundary: half the load instructions for the same bytes in flight
+        if ((((uintptr_t)(A + k0) | (uintptr_t)(B + k0)) & 15) == 0) {
+            struct alignas(16) P2 { T x, y; };
+            const P2     *A2 = reinterpret_cast<const P2 *>(A + k0), *B2 = reinterpret_cast<const P2 *>(B + k0);
+            const int64_t np = (k1 - k0) / 2;
+            int64_t       q = threadIdx.x;
+            for (; q + (int64_t)(UNR - 1) * NT < np; q += (int64_t)UNR * NT) {
+                P2 x[UNR], y[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; u++) { x[u] = A2[q + (int64_t)u * NT]; y[u] = B2[q + (int64_t)u * NT]; }
+#pragma unroll
+                for (int u = 0; u < UNR; u++) { acc[u] = fma_(x[u].x, y[u].x, acc[u]); acc[u] = fma_(x[u].y, y[u].y, acc[u]); }
+            }
+            for (; q < np; q += NT) { acc[0] = fma_(A2[q].x, B2[q].x, acc[0]); acc[0] = fma_(A2[q].y, B2[q].y, acc[0]); }
+            k = k0 + 2 * np + threadIdx.x; // an odd tail element (at most one) goes through the scalar loop below
+        }
+    }
     for (; k + (int64_t)(UNR - 1) * NT < k1; k += (int64_t)UNR * NT) {
         T x[UNR], y[UNR];
 #pragma unroll
@@ -979,8 +997,9 @@ template <typename T, bool CONJ_A, bool CONJ_B> __global__ void __launch_bounds_
 
 // elementwise_pairs: the same operation when the innermost target index is unit-stride in C with an even extent and every other C
 // stride is even (outer products, direct products on contiguous tensors): a thread owns two neighbouring elements (one 16-byte C
-// access for 8-byte types), decodes the index once per pair and keeps four pairs in flight. A and B inner strides may be 0 or anything.
-template <typename T, bool CONJ_A, bool CONJ_B> __global__ void __launch_bounds__(256) elementwise_pairs(const __grid_constant__ ElemArgs a) {
+// access for 8-byte types), decodes the index once per pair and keeps UNR = 4 pairs in flight (8 was tried for ger, where C is the only
+// large stream: no gain, 4.7 TB/s either way). A and B inner strides may be 0 or anything.
+template <typename T, bool CONJ_A, bool CONJ_B, int UNR> __global__ void __launch_bounds__(256) elementwise_pairs(const __grid_constant__ ElemArgs a) {
     struct alignas(2 * sizeof(T)) P2 { T x, y; };
     const T      *A = reinterpret_cast<const T *>(a.A);
     const T      *B = reinterpret_cast<const T *>(a.B);
@@ -989,25 +1008,25 @@ template <typename T, bool CONJ_A, bool CONJ_B> __global__ void __launch_bounds_
     const bool    has_beta = !is_zero(beta);
     const int64_t pairs = a.t.tot / 2, stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t sa0 = a.t.s[0][0], sb0 = a.t.s[1][0];
-    constexpr int UNR = 4;
     for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < pairs; x += stride * UNR) {
-        int64_t oa[UNR], ob[UNR], oc[UNR];
+        int64_t oc[UNR];
         T       a0[UNR], a1[UNR], b0[UNR], b1[UNR];
         P2      c[UNR];
+        // decode and issue the loads of one pair at a time: the A / B offsets die at once (all three offset sets of four pairs kept live
+        // cost 118 registers = 2 CTAs per SM, and a C-only stream such as ger then had too few bytes in flight: 4.7 TB/s)
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
             const int64_t xx = x + u * stride;
             oc[u] = -1;
-            if (xx < pairs) grp_offset3(a.t, 2 * xx, oa[u], ob[u], oc[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; u++)
-            if (oc[u] >= 0) {
-                a0[u] = A[oa[u]]; a1[u] = A[oa[u] + sa0];
-                b0[u] = B[ob[u]]; b1[u] = B[ob[u] + sb0];
+            if (xx < pairs) {
+                int64_t oa, ob;
+                grp_offset3(a.t, 2 * xx, oa, ob, oc[u]);
+                a0[u] = A[oa]; a1[u] = A[oa + sa0];
+                b0[u] = B[ob]; b1[u] = B[ob + sb0];
                 if (has_beta) c[u] = *reinterpret_cast<const P2 *>(C + oc[u]);
                 else c[u].x = c[u].y = zero_of<T>();
             }
+        }
 #pragma unroll
         for (int u = 0; u < UNR; u++)
             if (oc[u] >= 0) {

@@ -8,7 +8,7 @@ template <typename T, bool CA, bool CB> int launch_elem(cudaStream_t s, ElemArgs
     for (int i = 1; i < a.t.n && pairs; i++)
         if (a.t.s[2][i] % 2) pairs = false;
     if (pairs) {
-        elementwise_pairs<T, CA, CB><<<grid, 256, 0, s>>>(a);
+        elementwise_pairs<T, CA, CB, 4><<<grid, 256, 0, s>>>(a);
         EB_POST_LAUNCH("elementwise_pairs");
         return EB200_OK;
     }
