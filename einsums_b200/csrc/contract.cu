@@ -154,6 +154,12 @@ int try_run_tma(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const dou
     {
         const int want = option(OPT_TMA_DIST);
         a.dist = (want >= 1 && want < 4) ? want : 3;
+        // Rasterisation: groups of `group` tile rows sweep across all tile columns. The A panels of a group stay in L2 for the sweep; the B
+        // panels (N x K x 8 bytes: 128 MB for Wabef) do not survive until the next group, so they come from DRAM once per group. 8 rows cost
+        // 5 GB of re-reads on Wabef o=20 v=200 (ncu: 30.8 GB moved for 25.9 GB algorithmic); 32 rows keep the live set at ~15 MB and cut
+        // the re-reads by four.
+        static const int group_env = getenv("EB200_TMA_GROUP") ? atoi(getenv("EB200_TMA_GROUP")) : 0;
+        a.group = group_env > 0 ? group_env : 32;
     }
     d.split_k = 1;
     static const size_t smem_pad = getenv("EB200_TMA_SMEM_PAD") ? (size_t)atoi(getenv("EB200_TMA_SMEM_PAD")) : 0; // debugging: forces 1 CTA/SM

@@ -29,6 +29,7 @@ struct TmaGemmArgs {
     double  alpha, beta;
     int32_t tiles_m, tiles_n, vec_c;
     int32_t dist;          // prefetch distance in k steps (1 .. STAGES-1), see contract_tma.cuh
+    int32_t group;         // tile rows per rasterisation group (B panels are re-read from DRAM once per group when they exceed L2)
 };
 
 template <bool A_KMAJOR, bool B_KMAJOR>
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(256, 2) gemm_tma_f64(const __grid_constant__ C
 
     int tile_m, tile_n;
     {
-        constexpr int GROUP = 8;
+        const int GROUP = args.group;
         int id = blockIdx.x, per_group = GROUP * args.tiles_n;
         int g = id / per_group, first = g * GROUP;
         int gsize = min(args.tiles_m - first, GROUP);
