@@ -439,11 +439,9 @@ int try_permute_tma(cudaStream_t s, const std::vector<int64_t> &ext, const std::
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return 0;
     const size_t smem = (size_t)ta * tc * 8 + 1024 + 16;
-    static bool  attr_set = false; // per process; the attribute is per function and device-independent in value
-    if (!attr_set) {
+    {   // per call: the attribute belongs to the (function, device) pair and several host threads / devices may come through here
         cudaError_t e = cudaFuncSetAttribute(permute_tma_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, 9216 * 8 + 1024 + 16);
         if (e != cudaSuccess) return -cuda_fail(e, "cudaFuncSetAttribute(permute_tma_f64)");
-        attr_set = true;
     }
     permute_tma_f64<<<(unsigned)ntiles, 256, smem, s>>>(tm, pa);
     launch_counter()++;
