@@ -112,6 +112,10 @@ def _declare(lib):
     lib.eb200_event_synchronize.argtypes = [vp]
     lib.eb200_event_elapsed_ms.argtypes = [vp, vp, C.POINTER(C.c_float)]
     lib.eb200_mem_get_info.argtypes = [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.eb200_ipc_get_handle.argtypes = [vp, vp]
+    lib.eb200_ipc_open_handle.argtypes = [vp, C.POINTER(vp)]
+    lib.eb200_ipc_close_handle.argtypes = [vp]
+    lib.eb200_reduce_slots.argtypes = [vp, ci, ci, vp, i64, i64, C.c_double, vp]
     lib.eb200_copy_strided.argtypes = [vp, ci, ci, C.POINTER(i64), vp, C.POINTER(i64), vp, C.POINTER(i64)]
     for p, rt in _REAL.items():
         sp = C.POINTER(rt)

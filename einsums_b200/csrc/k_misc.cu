@@ -1,5 +1,7 @@
 // k_misc.cu — elementwise / scale / split finalize / type conversion kernels.
 #include "launch_api.cuh"
+
+#include <algorithm>
 namespace eb200 {
 namespace {
 template <typename T, bool CA, bool CB> int launch_elem(cudaStream_t s, ElemArgs &a, int grid) {
@@ -84,3 +86,71 @@ int k_launch_dot(int dtype, cudaStream_t s, ReduceArgs &a, int grid) { EB_BY_DTY
 #undef EB_BY_DTYPE
 int k_launch_convert(cudaStream_t s, int src_dtype, int dst_dtype, const ConvArgs &a, int grid) { return launch_convert_any(s, src_dtype, dst_dtype, a, grid); }
 } // namespace eb200
+
+// ---------------------------------------------------------------- K-split sharding: fixed-order sum of the ranks' partial results
+namespace eb200 {
+namespace {
+// One thread owns VEC consecutive elements; the n_slots loads of a thread are independent (all issued before the adds), the sum runs
+// slot 0, 1, ... so that the result does not depend on which rank finished first. Streams n_slots * count elements once: HBM bound.
+template <typename T, int VEC> __global__ void __launch_bounds__(256) reduce_slots_kernel(int n_slots, const T *__restrict__ slots, int64_t slot_stride,
+                                                                                       int64_t count, T beta, T *__restrict__ C) {
+    struct alignas(sizeof(T) * VEC) Pack { T v[VEC]; };
+    const int64_t npack = count / VEC, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npack; i += stride) {
+        Pack acc;
+        if (beta != T(0)) {
+            acc = *reinterpret_cast<const Pack *>(C + i * VEC);
+#pragma unroll
+            for (int e = 0; e < VEC; e++) acc.v[e] *= beta;
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; e++) acc.v[e] = T(0);
+        }
+        constexpr int BATCH = 8;
+        for (int s0 = 0; s0 < n_slots; s0 += BATCH) {
+            Pack p[BATCH];
+#pragma unroll
+            for (int b = 0; b < BATCH; b++)
+                if (s0 + b < n_slots) p[b] = *reinterpret_cast<const Pack *>(slots + (int64_t)(s0 + b) * slot_stride + i * VEC);
+#pragma unroll
+            for (int b = 0; b < BATCH; b++)
+                if (s0 + b < n_slots) {
+#pragma unroll
+                    for (int e = 0; e < VEC; e++) acc.v[e] += p[b].v[e];
+                }
+        }
+        *reinterpret_cast<Pack *>(C + i * VEC) = acc;
+    }
+    // tail (count % VEC elements), by the first threads of the grid
+    const int64_t t = npack * VEC + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < count) {
+        T acc = (beta != T(0)) ? beta * C[t] : T(0);
+        for (int s = 0; s < n_slots; s++) acc += slots[(int64_t)s * slot_stride + t];
+        C[t] = acc;
+    }
+}
+template <typename T> int reduce_slots_typed(cudaStream_t st, int n_slots, const void *slots, int64_t slot_stride, int64_t count, double beta, void *C) {
+    constexpr int VEC = 16 / sizeof(T);
+    const bool    vec = ((uintptr_t)slots % 16) == 0 && ((uintptr_t)C % 16) == 0 && (slot_stride % VEC) == 0;
+    const int64_t work = vec ? (count + VEC - 1) / VEC : count;
+    const int     grid = (int)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)sm_count() * 8));
+    if (vec) reduce_slots_kernel<T, VEC><<<grid, 256, 0, st>>>(n_slots, (const T *)slots, slot_stride, count, (T)beta, (T *)C);
+    else reduce_slots_kernel<T, 1><<<grid, 256, 0, st>>>(n_slots, (const T *)slots, slot_stride, count, (T)beta, (T *)C);
+    EB_POST_LAUNCH("reduce_slots");
+    return EB200_OK;
+}
+} // namespace
+} // namespace eb200
+
+extern "C" int eb200_reduce_slots(void *stream, int dtype, int n_slots, const void *slots, int64_t slot_stride, int64_t count, double beta, void *C) {
+    using namespace eb200;
+    if (n_slots < 1 || count < 0 || slot_stride < count) return fail(EB200_ERR_DOMAIN, "reduce_slots: n_slots %d, count %lld, slot_stride %lld", n_slots, (long long)count, (long long)slot_stride);
+    if (count == 0) return EB200_OK;
+    if (!slots || !C) return fail(EB200_ERR_INVALID_ARGUMENT, "reduce_slots: NULL pointer");
+    switch (dtype) {
+    case EB200_F32: return reduce_slots_typed<float>(as_stream(stream), n_slots, slots, slot_stride, count, beta, C);
+    case EB200_F64: return reduce_slots_typed<double>(as_stream(stream), n_slots, slots, slot_stride, count, beta, C);
+    default: return fail(EB200_ERR_INVALID_ARGUMENT, "reduce_slots: dtype %d (pass complex data as reals)", dtype);
+    }
+}
+

@@ -321,6 +321,27 @@ int eb200_host_get_device_pointer(void *host_ptr, void **dev_ptr) {
     EB_CUDA(cudaHostGetDevicePointer(dev_ptr, host_ptr, 0));
     return EB200_OK;
 }
+int eb200_ipc_get_handle(void *dev_ptr, void *handle) {
+    if (!dev_ptr || !handle) return fail(EB200_ERR_INVALID_ARGUMENT, "eb200_ipc_get_handle: NULL");
+    static_assert(sizeof(cudaIpcMemHandle_t) <= EB200_IPC_HANDLE_BYTES, "IPC handle does not fit");
+    cudaIpcMemHandle_t h;
+    EB_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+    memset(handle, 0, EB200_IPC_HANDLE_BYTES);
+    memcpy(handle, &h, sizeof(h));
+    return EB200_OK;
+}
+int eb200_ipc_open_handle(const void *handle, void **peer_ptr) {
+    if (!handle || !peer_ptr) return fail(EB200_ERR_INVALID_ARGUMENT, "eb200_ipc_open_handle: NULL");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    EB_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return EB200_OK;
+}
+int eb200_ipc_close_handle(void *peer_ptr) {
+    if (!peer_ptr) return EB200_OK;
+    EB_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    return EB200_OK;
+}
 int eb200_mem_get_info(size_t *free_bytes, size_t *total_bytes) {
     size_t f = 0, t = 0;
     EB_CUDA(cudaMemGetInfo(&f, &t));

@@ -32,8 +32,39 @@ def _stream(stream=None) -> int:
     return int(stream)
 
 
+class DeviceView:
+    """A dense row-major view of device memory given by a raw pointer -- memory torch did not allocate, e.g. a PEER GPU's buffer opened
+    with eb200_ipc_open_handle (torch would attribute such a pointer to the peer's device). Accepted wherever a CUDA tensor is."""
+    is_cuda = True
+
+    def __init__(self, ptr: int, shape, dtype):
+        self._ptr, self.shape, self.dtype = int(ptr), tuple(int(x) for x in shape), dtype
+        st, acc = [], 1
+        for e in reversed(self.shape):
+            st.append(acc)
+            acc *= e
+        self._strides = tuple(reversed(st))
+
+    def data_ptr(self):
+        return self._ptr
+
+    def dim(self):
+        return len(self.shape)
+
+    def stride(self, ax=None):
+        return self._strides if ax is None else self._strides[ax]
+
+    def numel(self):
+        n = 1
+        for e in self.shape:
+            n *= e
+        return n
+
+
 def _need_cuda(*ts):
     for t in ts:
+        if isinstance(t, DeviceView):
+            continue
         if not isinstance(t, torch.Tensor) or not t.is_cuda:
             raise TypeError("einsums_b200 operates on CUDA tensors only (there is no CPU fallback)")
 

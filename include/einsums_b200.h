@@ -130,6 +130,20 @@ int eb200_host_unregister(void *ptr);
 /* device-side alias of memory obtained from eb200_malloc_host (PINNED mode, :1313-1316) */
 int eb200_host_get_device_pointer(void *host_ptr, void **dev_ptr);
 int eb200_mem_get_info(size_t *free_bytes, size_t *total_bytes);
+/* Peer memory across the processes of one node (one process per GPU): the owner exports an allocation made with eb200_malloc, the
+ * peers open it and may then pass the returned pointer to ANY entry point of this library as a device pointer -- loads and stores go
+ * over NVLink / NVSwitch. Used by the K-split sharding (einsums_b200/sharding.py): the partial result of a contraction is written by
+ * the GEMM epilogue straight into the owning rank's receive slot. `handle` is EB200_IPC_HANDLE_BYTES opaque bytes, to be sent to the
+ * peers by any means (torch.distributed.all_gather_object here). */
+#define EB200_IPC_HANDLE_BYTES 64
+int eb200_ipc_get_handle(void *dev_ptr, void *handle);
+int eb200_ipc_open_handle(const void *handle, void **peer_ptr);
+int eb200_ipc_close_handle(void *peer_ptr);
+/* C[i] = beta * C[i] + sum_{s = 0 .. n_slots-1} slots[s * slot_stride + i],  i < count: the fixed-order (slot 0 first) sum of the partial
+ * results the ranks deposited in this rank's receive slots; beta == 0 never reads C. dtype: EB200_F32 / EB200_F64 (complex data can
+ * be passed as twice as many reals when beta is real). */
+int eb200_reduce_slots(void *stream, int dtype, int n_slots, const void *slots, int64_t slot_stride, int64_t count, double beta, void *C);
+
 /* contiguous copies; *_async variants only enqueue */
 int eb200_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
 int eb200_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
