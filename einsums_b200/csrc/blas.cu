@@ -51,9 +51,57 @@ __global__ void __launch_bounds__(256) l1_kernel(int64_t n, T alpha, T beta, con
     for (; i < n; i += stride) l1_apply<T, OP>(alpha, beta, x, i * incx, y, i * incy, z, i * incz);
 }
 
+// Unit increments, 16-byte aligned: one small CTA per 2 KB chunk (128 threads x one 16-byte pack of every stream), no loop, ~20 registers,
+// so 2048 threads per SM are resident. In-place streams (scal: 5.5 -> ... TB/s) need that many independent CTAs in different phases of
+// "load, then store the same lines"; the grid-stride kernel above keeps 8 x fewer threads resident.
+template <typename T, int OP>
+__global__ void __launch_bounds__(128) l1_kernel_contig(int64_t npack, T alpha, T beta, const T *__restrict__ x, const T *__restrict__ y, T *__restrict__ z) {
+    constexpr int VEC = 16 / sizeof(T) > 0 ? 16 / sizeof(T) : 1;
+    struct alignas(sizeof(T) * VEC) Pack { T v[VEC]; };
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npack) return;
+    Pack px, py, pz;
+    constexpr bool reads_x = OP == L1_AXPY || OP == L1_AXPBY || OP == L1_COPY || OP == L1_DIRPROD || OP == L1_DIRDIV || OP == L1_DIRMUL;
+    constexpr bool reads_y = OP == L1_DIRPROD;
+    constexpr bool reads_z = OP != L1_COPY && OP != L1_FILL;
+    if constexpr (reads_x) px = reinterpret_cast<const Pack *>(x)[i];
+    if constexpr (reads_y) py = reinterpret_cast<const Pack *>(y)[i];
+    if constexpr (reads_z) {
+        if (OP != L1_AXPBY || !is_zero(beta)) pz = reinterpret_cast<const Pack *>(z)[i];
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; e++) {
+        if constexpr (OP == L1_AXPY) pz.v[e] = fma_(alpha, px.v[e], pz.v[e]);
+        else if constexpr (OP == L1_AXPBY) pz.v[e] = is_zero(beta) ? mul_(alpha, px.v[e]) : fma_(alpha, px.v[e], mul_(beta, pz.v[e]));
+        else if constexpr (OP == L1_SCAL) pz.v[e] = mul_(alpha, pz.v[e]);
+        else if constexpr (OP == L1_COPY) pz.v[e] = px.v[e];
+        else if constexpr (OP == L1_FILL) pz.v[e] = alpha;
+        else if constexpr (OP == L1_DIRPROD) pz.v[e] = fma_(mul_(alpha, px.v[e]), py.v[e], pz.v[e]);
+        else if constexpr (OP == L1_CONJ) pz.v[e] = conj_(pz.v[e]);
+        else if constexpr (OP == L1_DIRDIV) pz.v[e] = div_(pz.v[e], px.v[e]);
+        else if constexpr (OP == L1_DIRMUL) pz.v[e] = mul_(pz.v[e], px.v[e]);
+    }
+    reinterpret_cast<Pack *>(z)[i] = pz;
+}
+
 template <typename T, int OP>
 int l1_launch(void *stream, int64_t n, T alpha, T beta, const T *x, int64_t incx, const T *y, int64_t incy, T *z, int64_t incz, const char *name) {
     if (n <= 0) return EB200_OK;
+    constexpr int VEC = 16 / sizeof(T) > 0 ? 16 / sizeof(T) : 1;
+    const bool    contig = incz == 1 && (!x || incx == 1) && (!y || incy == 1) && (((uintptr_t)z | (uintptr_t)x | (uintptr_t)y) % 16) == 0 && n >= 4096;
+    if (contig) {
+        const int64_t npack = n / VEC, blocks = (npack + 127) / 128;
+        if (blocks <= 0x7fffffffLL) {
+            l1_kernel_contig<T, OP><<<(unsigned)blocks, 128, 0, as_stream(stream)>>>(npack, alpha, beta, x, y, z);
+            EB_POST_LAUNCH(name);
+            const int64_t done = npack * VEC;
+            if (done == n) return EB200_OK;
+            // tail of n % VEC elements through the strided kernel
+            l1_kernel<T, OP><<<1, 32, 0, as_stream(stream)>>>(n - done, alpha, beta, x ? x + done : x, 1, y ? y + done : y, 1, z + done, 1);
+            EB_POST_LAUNCH(name);
+            return EB200_OK;
+        }
+    }
     l1_kernel<T, OP><<<grid_for_n(n, 256, 4), 256, 0, as_stream(stream)>>>(n, alpha, beta, x, incx, y, incy, z, incz);
     EB_POST_LAUNCH(name);
     return EB200_OK;

@@ -1038,6 +1038,46 @@ template <typename T, bool CONJ_A, bool CONJ_B, int UNR> __global__ void __launc
     }
 }
 
+// elementwise_pairs_2d: the pair kernel for TWO target indices (outer products / ger, direct products and broadcasts on matrices).
+// One small CTA (128 threads) owns 256 columns x 2 rows: a thread loads its two 16-byte C pairs and the operand values, no index decode and
+// no loop (ncu on dger with the generic pair kernel: two thirds of the warp samples in the multiply-shift decode, a third waiting on the C
+// loads, 16 warps per SM). ~32 registers, so 2048 threads per SM are resident, like the contiguous level-1 kernels.
+template <typename T, bool CONJ_A, bool CONJ_B> __global__ void __launch_bounds__(128) elementwise_pairs_2d(const __grid_constant__ ElemArgs a) {
+    struct alignas(2 * sizeof(T)) P2 { T x, y; };
+    constexpr int ROWS = 2;
+    const T      *A = reinterpret_cast<const T *>(a.A);
+    const T      *B = reinterpret_cast<const T *>(a.B);
+    T            *C = reinterpret_cast<T *>(a.C);
+    const T       alpha = make_scalar<T>(a.alpha[0], a.alpha[1]), beta = make_scalar<T>(a.beta[0], a.beta[1]);
+    const bool    has_beta = !is_zero(beta);
+    const int64_t e0 = a.t.ext[0], e1 = a.t.ext[1];
+    const int64_t sa0 = a.t.s[0][0], sa1 = a.t.s[0][1], sb0 = a.t.s[1][0], sb1 = a.t.s[1][1], sc1 = a.t.s[2][1];
+    const int64_t c0 = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (c0 >= e0) return;
+    const int64_t r0 = (int64_t)blockIdx.y * ROWS;
+    P2 c[ROWS];
+    T  a0[ROWS], a1[ROWS], b0[ROWS], b1[ROWS];
+#pragma unroll
+    for (int u = 0; u < ROWS; u++) {
+        const int64_t r = r0 + u;
+        if (r < e1) {
+            if (has_beta) c[u] = *reinterpret_cast<const P2 *>(C + c0 + r * sc1);
+            a0[u] = A[c0 * sa0 + r * sa1]; a1[u] = A[(c0 + 1) * sa0 + r * sa1];
+            b0[u] = B[c0 * sb0 + r * sb1]; b1[u] = B[(c0 + 1) * sb0 + r * sb1];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < ROWS; u++) {
+        const int64_t r = r0 + u;
+        if (r < e1) {
+            P2 o;
+            o.x = axpby_(alpha, mul_(maybe_conj<CONJ_A>(a0[u]), maybe_conj<CONJ_B>(b0[u])), beta, has_beta ? c[u].x : zero_of<T>(), has_beta);
+            o.y = axpby_(alpha, mul_(maybe_conj<CONJ_A>(a1[u]), maybe_conj<CONJ_B>(b1[u])), beta, has_beta ? c[u].y : zero_of<T>(), has_beta);
+            *reinterpret_cast<P2 *>(C + c0 + r * sc1) = o;
+        }
+    }
+}
+
 struct ScaleArgs {
     Grp    t; // ROLE_C strides only
     void  *C;

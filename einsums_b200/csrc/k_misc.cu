@@ -9,6 +9,17 @@ template <typename T, bool CA, bool CB> int launch_elem(cudaStream_t s, ElemArgs
     bool pairs = sizeof(T) <= 8 && a.t.n >= 1 && a.t.s[2][0] == 1 && (a.t.ext[0] % 2) == 0 && ((uintptr_t)a.C % (2 * sizeof(T))) == 0;
     for (int i = 1; i < a.t.n && pairs; i++)
         if (a.t.s[2][i] % 2) pairs = false;
+    if (pairs && a.t.n == 1 && a.t.ext[0] >= 256) { // one merged index (contiguous direct products): a single "row" for the 2-D kernel
+        a.t.ext[1] = 1;
+        a.t.s[0][1] = a.t.s[1][1] = a.t.s[2][1] = 0;
+        a.t.n = 2;
+    }
+    if (pairs && a.t.n == 2 && a.t.ext[0] >= 256 && (a.t.ext[1] + 1) / 2 <= 65535 && (a.t.ext[0] / 2 + 127) / 128 <= 0x7fffffffLL) {
+        dim3 g2((unsigned)((a.t.ext[0] / 2 + 127) / 128), (unsigned)((a.t.ext[1] + 1) / 2), 1);
+        elementwise_pairs_2d<T, CA, CB><<<g2, 128, 0, s>>>(a);
+        EB_POST_LAUNCH("elementwise_pairs_2d");
+        return EB200_OK;
+    }
     if (pairs) {
         elementwise_pairs<T, CA, CB, 4><<<grid, 256, 0, s>>>(a);
         EB_POST_LAUNCH("elementwise_pairs");

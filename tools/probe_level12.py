@@ -25,3 +25,5 @@ t = timeit(lambda: ops.ger(m, m, 0.5, x, 1, x, 1, A, m)); print(json.dumps({"op"
 Bm = torch.rand(m, m, dtype=torch.float64, device="cuda"); Cm = torch.zeros(m, m, dtype=torch.float64, device="cuda")
 t = timeit(lambda: ops.contract("ij", Cm, "ij", A, "ij", Bm, 1.0, 0.0)); print(json.dumps({"op": f"direct product {m}x{m} (beta=0)", "ms": round(t * 1e3, 3), "gbs": round(24.0 * m * m / t / 1e9, 1)}), flush=True)
 t = timeit(lambda: ops.contract("ij", Cm, "ij", A, "ij", Bm, 0.5, 2.0)); print(json.dumps({"op": f"direct product {m}x{m} (beta=2)", "ms": round(t * 1e3, 3), "gbs": round(32.0 * m * m / t / 1e9, 1)}), flush=True)
+t = timeit(lambda: ops.scal(N, 1.0000001, u, 1)); print(json.dumps({"op": "dscal 2^28 (in place)", "ms": round(t * 1e3, 3), "gbs": round(16.0 * N / t / 1e9, 1)}), flush=True)
+t = timeit(lambda: ops.copy(N, u, 1, w, 1)); print(json.dumps({"op": "dcopy 2^28", "ms": round(t * 1e3, 3), "gbs": round(16.0 * N / t / 1e9, 1)}), flush=True)
