@@ -441,6 +441,30 @@ TEST_CASE(gpu_host_modes_and_layout_conversion) { // T/TensorForward.hpp:45, T/B
     CHECK(meta[0] == 5 && meta[1] == 7 && meta[2] == 4 && meta[3] == 28 && meta[4] == 4 && meta[5] == 1);
 }
 
+TEST_CASE(gpu_memory_budget) { // GPUMemory/src/InitModule.cpp:39-55 (--einsums:gpu-buffer-size), GPUAllocator.hpp:157-191
+    size_t budget = 0, in_use0 = 0, peak = 0, live0 = 0;
+    EB200_CHECK(eb200_memory_stats(&budget, &in_use0, &peak, &live0));
+    CHECK(budget == 0); // unlimited by default
+    EB200_CHECK(eb200_set_memory_budget(in_use0 + (size_t(8) << 20)));
+    {
+        DeviceTensor<double, 2> small{"small", 512, 512};   // 2 MiB: fits
+        size_t in_use = 0, live = 0;
+        EB200_CHECK(eb200_memory_stats(nullptr, &in_use, nullptr, &live));
+        CHECK(in_use == in_use0 + 512 * 512 * 8 && live == live0 + 1);
+        bool refused = false;
+        try { DeviceTensor<double, 2> big{"big", 1024, 1024}; } catch (gpu_out_of_memory const &) { refused = true; } // 8 MiB more: over the budget
+        CHECK(refused);
+        DeviceTensor<double, 2> pinned{"pinned", einsums::detail::PINNED, 1024, 1024};   // host memory is not charged to the device budget
+        CHECK(pinned.data() != nullptr);
+    }
+    size_t in_use1 = 0;
+    EB200_CHECK(eb200_memory_stats(nullptr, &in_use1, nullptr, nullptr));
+    CHECK(in_use1 == in_use0); // everything returned
+    EB200_CHECK(eb200_set_memory_budget(0));
+    DeviceTensor<double, 2> big{"big", 1024, 1024};   // unlimited again
+    CHECK(big.size() == 1024 * 1024);
+}
+
 TEST_CASE(gpu_blas_gpu_facade) { // hipBLAS.hpp:63-94 (gemm), :132-160 (gemv), :423 (scal), :545 (dot), :586 (dotc), :621 (axpy), :719 (ger)
     namespace bg = einsums::blas::gpu;
     using cd = std::complex<double>;

@@ -924,6 +924,25 @@ def test_tma_generic_patterns(tma_generic_always, oracle, case, tile):
             assert d.split_k == sk
 
 
+def test_wmnij_full_size_80x80_fused_split_k(gpu):
+    """BASELINE configs[1], first einsum at full size: Wmnij = W + 0.25 sum_ef g t is a 400 x 400 x 40000 product. 128x64 tiles would pad the
+    output by 43 %, so it runs on 5 x 5 tiles of 80 x 80 with the K range split over the SMs and the partials summed by the last CTA
+    (contract_tma_f64<80x80>); against a float64 matmul on the device (different summation order: 1e-12) and bit-identical run to run."""
+    o, v = 20, 200
+    gen = torch.Generator(device="cuda").manual_seed(20251017 + 2)
+    g = torch.rand(o, o, v, v, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+    t = torch.rand(o, o, v, v, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+    W0 = torch.rand(o, o, o, o, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+    W = W0.clone()
+    d = gpu.contract("mnij", W, "mnef", g, "ijef", t, 0.25, 1.0)
+    assert gpu.last_kernel() == "contract_tma_f64<80x80>" and d.split_k > 1, (gpu.last_kernel(), d.split_k)
+    ref = W0 + 0.25 * (g.reshape(o * o, -1) @ t.reshape(o * o, -1).T).reshape(o, o, o, o)
+    assert ((W - ref).abs().max() / ref.abs().max()).item() <= 1e-12
+    W2 = W0.clone()
+    gpu.contract("mnij", W2, "mnef", g, "ijef", t, 0.25, 1.0)
+    assert torch.equal(W, W2)
+
+
 def test_tma_generic_split_k_is_reproducible(tma_generic_always):
     """Fused split-K: whichever CTA arrives last, the partials are added in split order, so repeated runs are bit-identical."""
     gpu = tma_generic_always
