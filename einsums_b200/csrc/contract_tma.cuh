@@ -10,11 +10,11 @@
 //     outer target indices, outer contracted indices, batch indices}. Composite M / N / K positions are enumerated with the
 //     INNER index padded to a multiple of 16, so a box never straddles two values of an outer index; ragged edges and
 //     padding are zero-filled by the TMA out-of-bounds rule (no predicates anywhere in the main loop).
-//   * Producer duty rotates over the warps: step t is issued by lane 0 of warp t % NWARPS, STAGES-1 steps ahead of its use
-//     (a dedicated producer warp would cap the CTA at 96 registers per thread and spill the accumulators; a single
-//     producer lane would make its warp the slowest one - a generic step issues 12 boxes with 5 coordinates each). The
-//     duty lane walks the contracted indices with counters (no division in the loop), adds the per-step K coordinates to
-//     the per-box target coordinates decoded once per CTA, and issues cp.async.bulk.tensor.5d (SASS UTMALDG.5D).
+//   * Producer duty rotates over the warps: step t is issued by warp t % NWARPS, STAGES-2 steps ahead of its use (a dedicated
+//     producer warp would cap the CTA at 96 registers per thread and spill the accumulators; a fixed producer would make its
+//     warp the slowest one). Inside the duty warp lane b owns box b, so the twelve boxes of a step cost ONE coordinate
+//     computation and ONE cp.async.bulk.tensor.5d instruction (SASS UTMALDG.5D) in SIMT. The warp walks the contracted indices
+//     with counters (no division in the loop) and adds the per-step K coordinates to the lane's target coordinates.
 //     full[s] mbarriers carry the transaction bytes, empty[s] one arrival per warp: no CTA-wide barrier in the main loop.
 //   * Consumer warps run LDS.64 + DMMA.8x8x4 only, with the same swizzle-aware fragment addressing as gemm_tma_f64
 //     (conflict-free for K-major and M-major tiles alike).
@@ -166,36 +166,37 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_tma_f64(const __g
     __syncthreads();
 
     // ===================== producer duty (rotating) =====================
-    // step t (local, 0-based) belongs to warp t % NCONS; a warp keeps the K counters of ITS next step and moves them NCONS steps at a time
+    // step t (local, 0-based) belongs to warp t % NCONS; a warp keeps the K counters of ITS next step and moves them NCONS steps at a time.
+    // The boxes of a step are issued by DIFFERENT LANES of the duty warp in one SIMT pass (lane b owns box b: BMB boxes of A, then BNB
+    // boxes of B): one coordinate computation and one UTMALDG instruction per step instead of twelve serial ones by a single lane.
+    static_assert(BMB + BNB <= 32, "one lane per box");
     int my_step = warp, s0 = 0, k1 = 0, k2 = 0;
-    if (lane == 0) {
+    {
         const int t = ks0 + warp, q0 = t / args.kstep0;
         s0 = t - q0 * args.kstep0;
         k2 = q0 / args.ek[1];
         k1 = q0 - k2 * args.ek[1];
     }
-    auto issue_my_step = [&]() { // lane 0 only
+    auto issue_my_step = [&]() { // the whole duty warp
         const int s = my_step % STAGES;
-        if (my_step >= STAGES) mbar_wait(empty_bar(s), ((my_step / STAGES) - 1) & 1);
-        int kA[5], kB[5];
-#pragma unroll
-        for (int d = 0; d < 5; d++) {
-            kA[d] = (args.dAk[0] == d ? 16 * s0 : 0) + (args.dAk[1] == d ? k1 : 0) + (args.dAk[2] == d ? k2 : 0);
-            kB[d] = (args.dBk[0] == d ? 16 * s0 : 0) + (args.dBk[1] == d ? k1 : 0) + (args.dBk[2] == d ? k2 : 0);
+        if (lane == 0) { // one lane polls the barrier (32 lanes polling load the mbarrier unit 32 x), the others park at the __syncwarp
+            if (my_step >= STAGES) mbar_wait(empty_bar(s), ((my_step / STAGES) - 1) & 1);
+            mbar_expect_tx(full_bar(s), STAGE_BYTES);
         }
-        const uint32_t a_dst = smem_base + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
-        mbar_expect_tx(full_bar(s), STAGE_BYTES);
+        __syncwarp();
+        if (lane < BMB + BNB) {
+            // this lane's box: operand, slot inside the stage, base coordinates (target + batch part, decoded once per CTA into shared
+            // memory: re-read here rather than kept in registers, the accumulators need them), K dimension slots
+            const bool     is_a = lane < BMB;
+            const int      b = is_a ? lane : lane - BMB;
+            const int32_t *co = (is_a ? coordA : coordB) + b * 8;
+            const int4     c03 = *reinterpret_cast<const int4 *>(co);
+            const int      kd0 = is_a ? args.dAk[0] : args.dBk[0], kd1 = is_a ? args.dAk[1] : args.dBk[1], kd2 = is_a ? args.dAk[2] : args.dBk[2];
+            int            c[5] = {c03.x, c03.y, c03.z, c03.w, co[4]};
 #pragma unroll
-        for (int b = 0; b < BMB; b++) {
-            const int4 c = *reinterpret_cast<const int4 *>(coordA + b * 8);
-            const int  c4 = coordA[b * 8 + 4];
-            tma_load_5d(a_dst + b * 2048, &tmA, full_bar(s), c.x + kA[0], c.y + kA[1], c.z + kA[2], c.w + kA[3], c4 + kA[4]);
-        }
-#pragma unroll
-        for (int b = 0; b < BNB; b++) {
-            const int4 c = *reinterpret_cast<const int4 *>(coordB + b * 8);
-            const int  c4 = coordB[b * 8 + 4];
-            tma_load_5d(b_dst + b * 2048, &tmB, full_bar(s), c.x + kB[0], c.y + kB[1], c.z + kB[2], c.w + kB[3], c4 + kB[4]);
+            for (int d = 0; d < 5; d++) c[d] += (kd0 == d ? 16 * s0 : 0) + (kd1 == d ? k1 : 0) + (kd2 == d ? k2 : 0);
+            tma_load_5d(smem_base + s * STAGE_BYTES + (is_a ? 0u : (uint32_t)A_BYTES) + (uint32_t)b * 2048u, is_a ? &tmA : &tmB, full_bar(s), c[0], c[1],
+                        c[2], c[3], c[4]);
         }
         my_step += NCONS;
         s0 += NCONS;
@@ -205,11 +206,10 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_tma_f64(const __g
         }
     };
     // Prefetch distance: the loads of step it + dist are issued while step it is consumed. dist = STAGES - 1 keeps every stage busy but
-    // makes the duty lane wait until the SLOWEST warp has left step it - 1, every step (ncu: 22 % of the samples in that spin, tensor
+    // makes the duty warp wait until the SLOWEST warp has left step it - 1, every step (ncu: 22 % of the samples in that spin, tensor
     // pipe 85 %); dist = STAGES - 2 refills the stage everybody left one step earlier, so the wait is over before it starts.
     const int dist = args.dist;
-    if (lane == 0)
-        while (my_step < dist && my_step < nsteps) issue_my_step(); // prologue: the first `dist` steps
+    while (my_step < dist && my_step < nsteps) issue_my_step(); // prologue: the first `dist` steps
 
     // ===================== consumers =====================
     const int wm0 = (warp % CFG::WARPS_M) * WM, wn0 = (warp / CFG::WARPS_M) * WN;
@@ -234,6 +234,25 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_tma_f64(const __g
         return kmajor ? base + blk + off + hi * 1024u : base + blk + (off ^ (hi * 64u));
     };
 
+    // warp tiles that start on a 16-row block boundary (the 128x64 configuration): the block of fragment i is a compile-time offset from
+    // the warp's first block, as in gemm_tma_f64 -- LDS with immediate offsets instead of an address computation per fragment load
+    constexpr bool ALIGNED_WARP_TILES = (WM % 16 == 0) && (WN % 16 == 0);
+    if constexpr (ALIGNED_WARP_TILES) {
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            a_off[kk] += (uint32_t)(wm0 >> 4) * 2048u;
+            b_off[kk] += (uint32_t)(wn0 >> 4) * 2048u;
+        }
+    }
+    auto frag_a = [&](uint32_t base, uint32_t off, int i) -> uint32_t {
+        if constexpr (ALIGNED_WARP_TILES) return A_KMAJOR ? base + off + (uint32_t)i * 1024u : base + ((off + (uint32_t)(i >> 1) * 2048u) ^ ((uint32_t)(i & 1) * 64u));
+        else return frag_addr(base, off, wm0 + 8 * i, A_KMAJOR);
+    };
+    auto frag_b = [&](uint32_t base, uint32_t off, int jj) -> uint32_t {
+        if constexpr (ALIGNED_WARP_TILES) return B_KMAJOR ? base + off + (uint32_t)jj * 1024u : base + ((off + (uint32_t)(jj >> 1) * 2048u) ^ ((uint32_t)(jj & 1) * 64u));
+        else return frag_addr(base, off, wn0 + 8 * jj, B_KMAJOR);
+    };
+
     double acc[FM][FN][2];
 #pragma unroll
     for (int i = 0; i < FM; i++)
@@ -242,7 +261,7 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_tma_f64(const __g
 
     for (int it = 0; it < nsteps; it++) {
         const int s = it % STAGES;
-        if (lane == 0 && my_step == it + dist && my_step < nsteps) issue_my_step(); // refills the stage everybody left at it + dist - STAGES
+        if (my_step == it + dist && my_step < nsteps) issue_my_step(); // (warp-uniform) refills the stage everybody left at it + dist - STAGES
         __syncwarp();
         mbar_wait(full_bar(s), (it / STAGES) & 1);
         const uint32_t a_base = smem_base + s * STAGE_BYTES, b_base = a_base + A_BYTES;
@@ -250,9 +269,9 @@ __global__ void __launch_bounds__(CFG::NT, CFG::MINB) contract_tma_f64(const __g
         for (int kk = 0; kk < 4; kk++) {
             double a[FM], b[FN];
 #pragma unroll
-            for (int i = 0; i < FM; i++) a[i] = lds_f64(frag_addr(a_base, a_off[kk], wm0 + 8 * i, A_KMAJOR));
+            for (int i = 0; i < FM; i++) a[i] = lds_f64(frag_a(a_base, a_off[kk], i));
 #pragma unroll
-            for (int jj = 0; jj < FN; jj++) b[jj] = lds_f64(frag_addr(b_base, b_off[kk], wn0 + 8 * jj, B_KMAJOR));
+            for (int jj = 0; jj < FN; jj++) b[jj] = lds_f64(frag_b(b_base, b_off[kk], jj));
 #pragma unroll
             for (int i = 0; i < FM; i++)
 #pragma unroll
