@@ -121,23 +121,44 @@ class KSplitContraction:
         if self.mode in ("p2p", "push"):
             import ctypes as C
             from ._lib import check, lib
-            raw = C.c_void_p()
-            check(lib().eb200_malloc(C.byref(raw), n * self.itemsize))
-            self._raw = raw.value
-            check(lib().eb200_memset_zero(raw, n * self.itemsize, torch.cuda.current_stream().cuda_stream))
-            handle = C.create_string_buffer(64)
-            check(lib().eb200_ipc_get_handle(raw, handle))
+            # every step that can fail locally is followed by an agreement among the ranks, so that either ALL of them end up in peer mode
+            # or ALL raise (and the caller may fall back to mode "nccl") -- never a mix, which would hang the next collective
+            raw, handle, err = C.c_void_p(), C.create_string_buffer(64), None
+            try:
+                check(lib().eb200_malloc(C.byref(raw), n * self.itemsize))
+                self._raw = raw.value
+                check(lib().eb200_memset_zero(raw, n * self.itemsize, torch.cuda.current_stream().cuda_stream))
+                check(lib().eb200_ipc_get_handle(raw, handle))
+            except Exception as e:  # noqa: BLE001
+                err = f"{type(e).__name__}: {e}"
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle.raw), group=self.group)
+            dist.all_gather_object(handles, (err, bytes(handle.raw)), group=self.group)
+            bad = [h[0] for h in handles if h[0]]
+            if bad:
+                self._release_local()
+                raise RuntimeError("K-split peer buffers: " + bad[0])
             self.peers = []                                   # raw device pointers of every rank's receive buffer
-            for d in range(self.world):
-                if d == self.rank:
-                    self.peers.append(self._raw)
-                else:
-                    p = C.c_void_p()
-                    check(lib().eb200_ipc_open_handle(C.create_string_buffer(handles[d], 64), C.byref(p)))
-                    self._opened.append(p.value)
-                    self.peers.append(p.value)
+            try:
+                for d in range(self.world):
+                    if d == self.rank:
+                        self.peers.append(self._raw)
+                    else:
+                        p = C.c_void_p()
+                        check(lib().eb200_ipc_open_handle(C.create_string_buffer(handles[d][1], 64), C.byref(p)))
+                        self._opened.append(p.value)
+                        self.peers.append(p.value)
+            except Exception as e:  # noqa: BLE001
+                err = f"{type(e).__name__}: {e}"
+            errs = [None] * self.world
+            dist.all_gather_object(errs, err, group=self.group)
+            bad = [e for e in errs if e]
+            if bad:
+                for p in self._opened:
+                    lib().eb200_ipc_close_handle(p)
+                self._opened = []
+                dist.barrier(group=self.group)
+                self._release_local()
+                raise RuntimeError("K-split peer buffers: " + bad[0])
             self.recv_ptr = self._raw
             dev = torch.device("cuda", torch.cuda.current_device())
             if self.mode == "push":
@@ -149,6 +170,12 @@ class KSplitContraction:
             self.recv_ptr = self.recv.data_ptr()
             dev = self.recv.device
         self._barrier_buf = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def _release_local(self):
+        if self._raw:
+            from ._lib import lib
+            lib().eb200_free(self._raw)
+            self._raw = None
 
     def close(self):
         if self.mode in ("p2p", "push") and self._raw:
