@@ -422,6 +422,107 @@ int try_run_tma_z(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const d
     return 1;
 }
 
+// ---------------------------------------------------------------- generic FP32 contraction on tcgen05 (multi-index groups, batches)
+// Same scheme as the FP64 multi-index TMA kernel: one <= 5-D tensor map per operand, 32 x 32 boxes over (the operand's unit-stride
+// index, the inner index of the other group); composite M / N / K positions enumerate the INNER index padded to a multiple of 32.
+bool make_generic_map_f32(CUtensorMap *map, const float *base, const Grp &tgt, const Grp &k, const Grp &b, int role, bool kmajor, int32_t *d_t,
+                          int32_t *d_k, int32_t *d_b) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || ((uintptr_t)base % 16)) return false;
+    if (tgt.n < 1 || k.n < 1 || tgt.n > 3 || k.n > 3 || b.n > 3 || tgt.n + k.n + b.n > 5) return false;
+    std::vector<GenMapDim> dims;
+    for (int i = 0; i < tgt.n; i++) dims.push_back({tgt.ext[i], tgt.s[role][i], 0, i});
+    for (int i = 0; i < k.n; i++) dims.push_back({k.ext[i], k.s[role][i], 1, i});
+    for (int i = 0; i < b.n; i++) dims.push_back({b.ext[i], b.s[role][i], 2, i});
+    for (auto &x : dims)
+        if (x.stride <= 0 || x.ext < 1 || x.ext >= (1LL << 31) || x.stride >= (1LL << 36)) return false;
+    const int unit_grp = kmajor ? 1 : 0;
+    std::stable_sort(dims.begin(), dims.end(), [&](const GenMapDim &x, const GenMapDim &y) {
+        const bool ux = x.grp == unit_grp && x.idx == 0, uy = y.grp == unit_grp && y.idx == 0;
+        if (ux != uy) return ux;
+        return x.stride < y.stride;
+    });
+    if (dims[0].stride != 1) return false;
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t box[5], es[5] = {1, 1, 1, 1, 1};
+    int64_t    span = 4;
+    for (int i = 0; i < 3; i++) d_t[i] = d_k[i] = d_b[i] = -1;
+    for (int dd = 0; dd < 5; dd++) {
+        if (dd < (int)dims.size()) {
+            const GenMapDim &x = dims[dd];
+            if (dd > 0 && (x.stride & 3)) return false; // byte strides must be multiples of 16
+            gdim[dd] = (cuuint64_t)x.ext;
+            if (dd > 0) gstr[dd - 1] = (cuuint64_t)x.stride * 4;
+            box[dd] = (x.idx == 0 && x.grp != 2) ? 32 : 1;
+            (x.grp == 0 ? d_t : x.grp == 1 ? d_k : d_b)[x.idx] = dd;
+            span = std::max(span, x.stride * x.ext);
+        } else {
+            gdim[dd] = 1;
+            gstr[dd - 1] = (cuuint64_t)((span + 3) & ~3LL) * 4;
+            box[dd] = 1;
+        }
+    }
+    for (int dd = 0; dd < 4; dd++)
+        if (gstr[dd] >= (1ULL << 40)) return false;
+    // K-major tiles: 128-byte rows along k, plain 128-byte swizzle; MN-major tiles: rows along m/n need the 32-byte-atom swizzle
+    const CUtensorMapSwizzle sw = kmajor ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void *)base, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int try_run_tf32x3_generic(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const double beta_eff[2]) {
+    if (g_use_tcgen05 < 0) {
+        const char *e = getenv("EB200_USE_TCGEN05");
+        g_use_tcgen05 = e ? atoi(e) : 1;
+    }
+    const int mode = option(OPT_TCGEN05_GENERIC); // 1: by the rules below; 0: never; 2: whenever a tensor map exists (tests)
+    if (!g_use_tcgen05 || !mode || d.force_kernel != 0 || d.split_k > 1 || p.swapped) return 0;
+    const float *A = (const float *)d.A.data, *B = (const float *)d.B.data;
+    const bool   ak = p.a_kmajor != 0, bk = p.b_kmajor != 0;
+    Tf32GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    CUtensorMap tmA, tmB;
+    if (!make_generic_map_f32(&tmA, A, p.m, p.k, p.b, ROLE_A, ak, a.dAm, a.dAk, a.dAb)) return 0;
+    if (!make_generic_map_f32(&tmB, B, p.n, p.k, p.b, ROLE_B, bk, a.dBn, a.dBk, a.dBb)) return 0;
+    for (int i = 0; i < 3; i++) {
+        a.em[i] = i < p.m.n ? (int32_t)p.m.ext[i] : 1;
+        a.en[i] = i < p.n.n ? (int32_t)p.n.ext[i] : 1;
+        a.ek[i] = i < p.k.n ? (int32_t)p.k.ext[i] : 1;
+        a.eb[i] = i < p.b.n ? (int32_t)p.b.ext[i] : 1;
+        a.gCm[i] = i < p.m.n ? p.m.s[ROLE_C][i] : 0;
+        a.gCn[i] = i < p.n.n ? p.n.s[ROLE_C][i] : 0;
+        a.gCb[i] = i < p.b.n ? p.b.s[ROLE_C][i] : 0;
+    }
+    a.mblk0 = (a.em[0] + 31) / 32; a.nblk0 = (a.en[0] + 31) / 32; a.kstep0 = (a.ek[0] + 31) / 32;
+    a.MB = (int64_t)a.mblk0 * a.em[1] * a.em[2];
+    a.NB = (int64_t)a.nblk0 * a.en[1] * a.en[2];
+    const int64_t KT = (int64_t)a.kstep0 * a.ek[1] * a.ek[2];
+    if (KT > 0x7fffffffLL || p.b.tot >= (1LL << 31)) return 0;
+    a.KT = (int32_t)KT;
+    // padding the inner indices to multiples of 32 costs tensor-pipe work; the FMA-pipe kernel (no padding) is ~5 x slower, so a factor
+    // of 2.5 is still a clear win
+    const double waste = (double)a.MB * 32 / (double)p.m.tot * ((double)a.NB * 32 / (double)p.n.tot) * ((double)KT * 32 / (double)p.k.tot);
+    if (waste > 2.5 && mode != 2) return 0;
+    const int64_t tm = (a.MB + 3) / 4, tn = (a.NB + 3) / 4;
+    if (tm * tn > 0x7fffffffLL || tm * tn * p.b.tot > (1LL << 40)) return 0;
+    if (tm * tn * p.b.tot * 4 < sm_count() && mode != 2) return 0; // too few tiles to fill the machine: the FMA kernel has split-K
+    a.tiles_m = (int)tm; a.tiles_n = (int)tn;
+    a.batch = p.b.tot;
+    a.M = p.m.tot; a.N = p.n.tot; a.K = p.k.tot;
+    a.C = (float *)d.C.data;
+    a.alpha = (float)d.alpha[0]; a.beta = (float)beta_eff[0];
+    a.c_n_unit = (p.n.n > 0 && p.n.s[ROLE_C][0] == 1) ? 1 : 0;
+    constexpr size_t SMEM = 3 * 65536 + 4 * (32 * 33 * 4) + 1024 + 256 + 2048;
+    const unsigned   grid = (unsigned)std::min<int64_t>(tm * tn * p.b.tot, sm_count());
+    int rc = k_launch_tf32x3_generic(s, tmA, tmB, a, dim3(grid, 1, 1), SMEM, !ak, !bk);
+    if (rc) return -rc;
+    d.launches++;
+    d.split_k = 1;
+    d.kernel_used = EB200_KF_TILE_TCGEN05;
+    set_last_kernel("gemm_tf32x3_tcgen05<generic>");
+    return 1;
+}
+
 template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const double beta_eff[2]) {
     TileArgs args;
     args.p = p;
@@ -455,6 +556,9 @@ template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract
     if constexpr (std::is_same_v<T, float>) {
         if (!mma) {
             int r = try_run_tf32x3(s, p, d, beta_eff);
+            if (r == 1) return EB200_OK;
+            if (r < 0) return -r;
+            r = try_run_tf32x3_generic(s, p, d, beta_eff);
             if (r == 1) return EB200_OK;
             if (r < 0) return -r;
         }

@@ -32,6 +32,14 @@ struct Tf32GemmArgs {
     float   alpha, beta;
     int32_t tiles_m, tiles_n;
     int64_t batch, sCb;    // number of independent products (1 = plain GEMM) and the element stride of C between them
+    // ---- GENERIC instantiation only (multi-index M / N / K / batch groups, <= 5-D tensor maps with 32 x 32 boxes; see contract_tma.cuh
+    //      for the scheme: composite positions are enumerated with the INNER index padded to a multiple of 32)
+    int32_t em[3], en[3], ek[3], eb[3];                 // extents, inner first (unused slots = 1)
+    int32_t mblk0, nblk0, kstep0, KT;                   // 32-blocks along the inner M / N / K index; composite k steps
+    int64_t MB, NB;                                     // composite 32-row block counts
+    int32_t dAm[3], dAk[3], dAb[3], dBn[3], dBk[3], dBb[3]; // tensor-map dimension of each index (-1: absent)
+    int64_t gCm[3], gCn[3], gCb[3];                     // element strides in C
+    int32_t c_n_unit;                                   // the inner N index is unit-stride in C: transposed (row-segment) stores
 };
 
 #ifdef EB200_TF32_KERNEL_IMPL // the kernel itself is compiled by k_tile_tf32.cu only
@@ -61,7 +69,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-template <bool A_MN, bool B_MN, bool MULTI>
+template <bool A_MN, bool B_MN, bool MULTI, bool GENERIC = false>
 __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                              const __grid_constant__ Tf32GemmArgs args) {
     constexpr int      BM = 128, BN = 128, BK = 32, STAGES = 3, NACC = 2;
@@ -88,7 +96,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
     unsigned char *smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nsteps = (int)((args.K + BK - 1) / BK);
+    const int nsteps = GENERIC ? args.KT : (int)((args.K + BK - 1) / BK);
     const int nchunks = (nsteps + KCB - 1) / KCB;
     // static tile schedule: this CTA owns tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; tile_m runs fastest, so the CTAs that are
     // resident together share B panels (and, a little later, A panels) in L2
@@ -126,7 +134,63 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if constexpr (GENERIC) {
+            // lanes 0..3 own the four 32-row M blocks of the tile, lanes 4..7 the four N blocks: per tile each lane decodes its block into
+            // tensor-map coordinates, per k-step it adds the K coordinates and issues its box (one SIMT pass per step); lane 0 alone polls
+            // the empty barrier and posts the transaction bytes
+            const bool is_a = lane < 4;
+            const int  blk = lane & 3;
+            int        gs = 0;
+            for (int i = 0; i < my_tiles; i++) {
+                int tile_m, tile_n, b;
+                decode(i, tile_m, tile_n, b);
+                int c0[5] = {0, 0, 0, 0, 0};
+                if (lane < 8) {
+                    const int64_t  cb = (int64_t)(is_a ? tile_m : tile_n) * 4 + blk;
+                    const int32_t *ext = is_a ? args.em : args.en, *dt = is_a ? args.dAm : args.dBn, *db = is_a ? args.dAb : args.dBb;
+                    const int      blk0n = is_a ? args.mblk0 : args.nblk0;
+                    int            blk0 = blk0n, i1 = 0, i2 = 0; // out of range: an inner coordinate past the extent zero-fills the whole box
+                    if (cb < (is_a ? args.MB : args.NB)) {
+                        const int64_t q0 = cb / blk0n;
+                        blk0 = (int)(cb - q0 * blk0n);
+                        const int64_t q1 = q0 / ext[1];
+                        i1 = (int)(q0 - q1 * ext[1]);
+                        i2 = (int)q1;
+                    }
+#pragma unroll
+                    for (int d = 0; d < 5; d++) c0[d] = (dt[0] == d ? 32 * blk0 : 0) + (dt[1] == d ? i1 : 0) + (dt[2] == d ? i2 : 0);
+                    int x = b;
+#pragma unroll
+                    for (int q = 0; q < 3; q++) {
+                        const int bi = x % args.eb[q];
+                        x /= args.eb[q];
+#pragma unroll
+                        for (int d = 0; d < 5; d++) c0[d] += (db[q] == d ? bi : 0);
+                    }
+                }
+                const int kd0 = is_a ? args.dAk[0] : args.dBk[0], kd1 = is_a ? args.dAk[1] : args.dBk[1], kd2 = is_a ? args.dAk[2] : args.dBk[2];
+                int       s0 = 0, k1 = 0, k2 = 0;
+                for (int it = 0; it < nsteps; it++, gs++) {
+                    const int s = gs % STAGES;
+                    if (lane == 0) {
+                        if (gs >= STAGES) mbar_wait(empty(s), ((gs / STAGES) - 1) & 1);
+                        mbar_expect_tx(full_raw(s), RAW_BYTES);
+                    }
+                    __syncwarp();
+                    if (lane < 8) {
+                        int c[5];
+#pragma unroll
+                        for (int d = 0; d < 5; d++) c[d] = c0[d] + (kd0 == d ? 32 * s0 : 0) + (kd1 == d ? k1 : 0) + (kd2 == d ? k2 : 0);
+                        tma_load_5d(smem_base + s * STAGE_BYTES + (is_a ? 0u : TILE_BYTES) + (uint32_t)blk * 4096u, is_a ? &tmA : &tmB, full_raw(s), c[0], c[1],
+                                    c[2], c[3], c[4]);
+                    }
+                    if (++s0 == args.kstep0) {
+                        s0 = 0;
+                        if (++k1 == args.ek[1]) { k1 = 0; ++k2; }
+                    }
+                }
+            }
+        } else if (lane == 0) {
             int gs = 0; // k-steps issued by this CTA since the start (all tiles): stage = gs % STAGES
             for (int i = 0; i < my_tiles; i++) {
                 int tile_m, tile_n, b;
@@ -290,7 +354,116 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
             int tile_m, tile_n, b;
             decode(i, tile_m, tile_n, b);
             float *Cb = args.C + (int64_t)b * args.sCb;
-            if constexpr (!MULTI) {
+            if constexpr (GENERIC) {
+                // ---- multi-index C: offset tables for the tile's 128 rows and 128 columns (thread e fills entry e of both), accumulate the
+                // chunks in registers as in the MULTI path, then store through the tables
+                constexpr int64_t INVALID = INT64_MIN;
+                int64_t          *moffC = reinterpret_cast<int64_t *>(smem_gen + STAGES * STAGE_BYTES + 4 * PATCH_BYTES + 256);
+                int64_t          *noffC = moffC + BM;
+                const int         e = tid - 192; // 0 .. 127
+                {
+                    int64_t baseC = 0;
+                    int     x = b;
+#pragma unroll
+                    for (int q = 0; q < 3; q++) {
+                        baseC += (int64_t)(x % args.eb[q]) * args.gCb[q];
+                        x /= args.eb[q];
+                    }
+                    Cb = args.C + baseC;
+                    auto offset_of = [&](int64_t p, const int32_t *ext, int blk0n, int64_t nblocks, const int64_t *st) -> int64_t {
+                        const int64_t cb = p >> 5;
+                        if (cb >= nblocks) return INVALID;
+                        const int64_t q0 = cb / blk0n, q1 = q0 / ext[1];
+                        const int64_t x0 = (cb - q0 * blk0n) * 32 + (p & 31);
+                        if (x0 >= ext[0]) return INVALID;
+                        return x0 * st[0] + (q0 - q1 * ext[1]) * st[1] + q1 * st[2];
+                    };
+                    asm volatile("bar.sync 1, 128;" ::: "memory"); // the previous tile's stores have read the tables
+                    moffC[e] = offset_of((int64_t)tile_m * BM + e, args.em, args.mblk0, args.MB, args.gCm);
+                    noffC[e] = offset_of((int64_t)tile_n * BN + e, args.en, args.nblk0, args.NB, args.gCn);
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                float acc[BN];
+                for (int ch = 0; ch < nchunks; ch++, gc++) {
+                    const int ab = gc & (NACC - 1);
+                    mbar_wait(chunk_full(ab), (gc / NACC) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                    for (int c0 = 0; c0 < BN; c0 += 32) {
+                        uint32_t       r[32];
+                        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * 256 + c0);
+                        tmem_ld32(taddr, r);
+                        if (ch == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) acc[c0 + j] = __uint_as_float(r[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) acc[c0 + j] += __uint_as_float(r[j]);
+                        }
+                        tmem_ld32(taddr + 128u, r);
+#pragma unroll
+                        for (int j = 0; j < 32; j++) acc[c0 + j] += __uint_as_float(r[j]);
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(chunk_drained(ab));
+                }
+#pragma unroll
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    if (args.c_n_unit) {
+                        // lanes along n (contiguous in C): transpose the 32 x 32 block through the warp's patch
+#pragma unroll
+                        for (int j = 0; j < 32; j++) patch[lane * 33 + j] = acc[c0 + j];
+                        __syncwarp();
+                        const int64_t on = noffC[c0 + lane];
+                        if (on != INVALID) {
+#pragma unroll
+                            for (int r0 = 0; r0 < 32; r0 += 16) { // the 16 old C values of a half block are requested before their first use
+                                int64_t om[16];
+                                float   old[16];
+#pragma unroll
+                                for (int rr = 0; rr < 16; rr++) om[rr] = moffC[quad * 32 + r0 + rr];
+                                if (beta != 0.f) {
+#pragma unroll
+                                    for (int rr = 0; rr < 16; rr++) old[rr] = (om[rr] != INVALID) ? Cb[om[rr] + on] : 0.f;
+                                }
+#pragma unroll
+                                for (int rr = 0; rr < 16; rr++) {
+                                    if (om[rr] != INVALID) {
+                                        float o = alpha * patch[(r0 + rr) * 33 + lane];
+                                        if (beta != 0.f) o = fmaf(beta, old[rr], o);
+                                        Cb[om[rr] + on] = o;
+                                    }
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    } else {
+                        // lanes along m
+                        const int64_t om = moffC[quad * 32 + lane];
+                        if (om != INVALID) {
+#pragma unroll
+                            for (int j0 = 0; j0 < 32; j0 += 16) { // fully unrolled: acc[] must stay in registers
+                                int64_t on[16];
+                                float   old[16];
+#pragma unroll
+                                for (int j = 0; j < 16; j++) on[j] = noffC[c0 + j0 + j];
+                                if (beta != 0.f) {
+#pragma unroll
+                                    for (int j = 0; j < 16; j++) old[j] = (on[j] != INVALID) ? Cb[om + on[j]] : 0.f;
+                                }
+#pragma unroll
+                                for (int j = 0; j < 16; j++) {
+                                    if (on[j] != INVALID) {
+                                        float o = alpha * acc[c0 + j0 + j];
+                                        if (beta != 0.f) o = fmaf(beta, old[j], o);
+                                        Cb[om + on[j]] = o;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            } else if constexpr (!MULTI) {
                 // K <= 512: one chunk per tile. Each 32-column block goes TMEM -> registers -> global; the accumulator pair is handed
                 // back after the last block has been read.
                 const int ab = gc & (NACC - 1);

@@ -25,4 +25,20 @@ int k_launch_tf32x3(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &t
     EB_POST_LAUNCH("gemm_tf32x3_tcgen05");
     return EB200_OK;
 }
+int k_launch_tf32x3_generic(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB, const Tf32GemmArgs &a, dim3 grid, size_t smem, bool a_mn, bool b_mn) {
+#define EB_TF32_GEN(AM, BM_)                                                    \
+    {                                                                           \
+        auto kern = gemm_tf32x3_tcgen05<AM, BM_, true, true>;                   \
+        int  rc = set_smem_attr(kern, smem);                                    \
+        if (rc) return rc;                                                      \
+        kern<<<grid, 320, smem, s>>>(tmA, tmB, a);                              \
+    }
+    if (a_mn && b_mn) EB_TF32_GEN(true, true)
+    else if (a_mn && !b_mn) EB_TF32_GEN(true, false)
+    else if (!a_mn && b_mn) EB_TF32_GEN(false, true)
+    else EB_TF32_GEN(false, false)
+#undef EB_TF32_GEN
+    EB_POST_LAUNCH("gemm_tf32x3_tcgen05<generic>");
+    return EB200_OK;
+}
 } // namespace eb200

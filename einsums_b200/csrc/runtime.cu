@@ -65,13 +65,14 @@ struct Options {
         v[OPT_TMA_TILE] = env("EB200_TMA_TILE", -1);
         v[OPT_TMA_DIST] = env("EB200_TMA_DIST", 0);
         v[OPT_PERMUTE_TMA] = env("EB200_PERMUTE_TMA", 1);
+        v[OPT_TCGEN05_GENERIC] = env("EB200_TCGEN05_GENERIC", 1);
     }
 };
 Options &options() {
     static Options o;
     return o;
 }
-const char *const kOptionNames[OPT_COUNT] = {"tma", "tma_generic", "tma_tile", "tma_dist", "permute_tma"};
+const char *const kOptionNames[OPT_COUNT] = {"tma", "tma_generic", "tma_tile", "tma_dist", "permute_tma", "tcgen05_generic"};
 thread_local const char *t_last_kernel = "";
 } // namespace
 int  option(int which) { return options().v[which].load(std::memory_order_relaxed); }

@@ -316,7 +316,9 @@ const char *eb200_last_kernel_name(void);
  *   "tma_generic"  1 | 0 | 2: multi-index TMA kernel by the padding rule / never / whenever it is legal
  *   "tma_tile"     -1 | 0 | 1: automatic / 128x64 / 80x80 tiles in the multi-index TMA kernel
  *   "tma_dist"     0 | n: automatic / issue the loads of step t + n while step t is consumed (1 <= n < stages)
- *   "permute_tma"  1 | 0: TMA-staged FP64 plane transpose whenever the layout has a tensor map / never (register-staged kernels) */
+ *   "permute_tma"  1 | 0: TMA-staged FP64 plane transpose whenever the layout has a tensor map / never (register-staged kernels)
+ *   "tcgen05_generic" 1 | 0 | 2: multi-index FP32 contractions on the tcgen05 kernel by the padding / fill rules / never / whenever legal
+ *                  (default from EB200_TCGEN05_GENERIC) */
 int eb200_set_option(const char *name, int value);
 int eb200_get_option(const char *name, int *value);
 

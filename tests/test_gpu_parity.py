@@ -1011,3 +1011,88 @@ def test_tma_generic_fuzz(tma_generic_always, oracle, chunk):
         if d.kernel_used == KF["TILE_MMA"] and gpu.last_kernel().startswith("contract_tma_f64"):
             took += 1
     assert took >= 3, f"only {took} of {ran} cases reached the multi-index TMA kernel"
+
+
+# ---------------------------------------------------------------------------------------------
+# gemm_tf32x3_tcgen05<generic>: multi-index FP32 contractions on the tcgen05 kernel (<= 5-D tensor maps, 32 x 32 boxes)
+@pytest.fixture
+def tcgen05_generic_always(gpu):
+    """Route every FP32 contraction that has tensor maps through the tcgen05 kernel (ignores the padding and machine-fill rules)."""
+    gpu.set_option("tcgen05_generic", 2)
+    yield gpu
+    gpu.set_option("tcgen05_generic", 1)
+
+
+# the TMA_GENERIC patterns with every non-unit stride a multiple of 4 floats (FP32 tensor maps need 16-byte strides)
+TCGEN05_GENERIC = [
+    ("mbej", "jnfb", "mnef", dict(m=6, b=32, e=48, j=7, n=5, f=32)),
+    ("mbej", "jnfb", "mnef", dict(m=6, b=24, e=20, j=7, n=5, f=28)),
+    ("abef", "nmef", "mnab", dict(a=9, b=36, e=10, f=36, m=5, n=6)),
+    ("ij", "iknl", "jnkl", dict(i=70, j=50, k=4, l=20, n=3)),
+    ("ij", "ik", "kj", dict(i=150, j=132, k=100)),
+    ("ij", "ki", "jk", dict(i=152, j=132, k=100)),
+    ("ji", "ik", "kj", dict(i=129, j=72, k=300)),
+    ("bij", "bik", "bkj", dict(i=65, j=36, k=40, b=5)),
+    ("ijb", "bik", "kbj", dict(i=66, j=36, k=48, b=3)),
+    ("xyabcd", "xyakb", "ykxcd", dict(x=2, y=3, a=5, b=16, c=4, d=20, k=40)),
+]
+
+
+@pytest.mark.parametrize("case", TCGEN05_GENERIC, ids=lambda c: f"{c[0]}<-{c[1]},{c[2]}")
+def test_tcgen05_generic_patterns(tcgen05_generic_always, oracle, case):
+    """The index patterns of the FP64 multi-index TMA kernel, in FP32, against the oracle (1e-5: 3xTF32 keeps FP32 accuracy)."""
+    from einsums_b200 import KF
+    gpu = tcgen05_generic_always
+    c_idx, a_idx, b_idx, ext = case
+    for (alpha, beta) in ((0.25, 1.0), (1.0, 0.0), (-0.5, 2.0)):
+        d = run_case(gpu, oracle, c_idx, a_idx, b_idx, ext, np.float32, alpha, beta, seed=43)
+        assert d.kernel_used == KF["TILE_TCGEN05"], (d.kernel_used, gpu.last_kernel(), case)
+        if len(ext) > 3:
+            assert gpu.last_kernel() == "gemm_tf32x3_tcgen05<generic>", (gpu.last_kernel(), case)
+
+
+def test_tcgen05_generic_default_routing_and_long_k(gpu, oracle):
+    """Without any knob: an FP32 Wmbej with enough 128 x 128 tiles to fill the SMs takes the tcgen05 kernel (K = 2 x 544 > 512: several
+    accumulation chunks); the same pattern with a handful of tiles stays on the FMA-pipe kernel; beta = 0 must not read C."""
+    from einsums_b200 import KF
+    ext = dict(m=14, b=64, e=64, j=12, n=2, f=544)
+    d = run_case(gpu, oracle, "mbej", "jnfb", "mnef", ext, np.float32, -0.5, 1.0, seed=7)
+    assert d.kernel_used == KF["TILE_TCGEN05"] and gpu.last_kernel() == "gemm_tf32x3_tcgen05<generic>", gpu.last_kernel()
+    d = run_case(gpu, oracle, "mbej", "jnfb", "mnef", dict(m=3, b=32, e=32, j=3, n=2, f=40), np.float32, -0.5, 1.0, seed=8)
+    assert d.kernel_used == KF["TILE_SIMT"], gpu.last_kernel()
+    rng = np.random.default_rng(9)
+    t, g = rand(rng, (12, 2, 96, 64), np.float32), rand(rng, (14, 2, 64, 96), np.float32)
+    Wd = torch.full((14, 64, 64, 12), float("nan"), dtype=torch.float32, device="cuda")
+    gpu.contract("mbej", Wd, "jnfb", dev(t), "mnef", dev(g), 1.0, 0.0)
+    assert gpu.last_kernel() == "gemm_tf32x3_tcgen05<generic>"
+    ref = np.zeros((14, 64, 64, 12), np.float32)
+    oracle.einsum_generic("mbej", ref, "jnfb", t, "mnef", g, 1.0, 0.0)
+    assert_close(Wd.cpu().numpy(), ref, np.float32)
+
+
+@pytest.mark.parametrize("chunk", range(2))
+def test_tcgen05_generic_fuzz(tcgen05_generic_always, oracle, chunk):
+    """Random FP32 tile-family contractions (as test_tma_generic_fuzz) through the tcgen05 kernel whenever both operands have a tensor
+    map; the rest falls back to the FMA-pipe kernel and is checked too."""
+    from einsums_b200 import KF
+    gpu = tcgen05_generic_always
+    rng = np.random.default_rng(4000 + chunk)
+    took = ran = 0
+    for n in range(48):
+        letters = list("abcdefgh")
+        nm, nn, nk, nb = int(rng.integers(1, 3)), int(rng.integers(1, 3)), int(rng.integers(1, 4)), int(rng.integers(0, 2))
+        if nm + nk + nb > 5 or nn + nk + nb > 5:
+            continue
+        m, nl, k, bt = letters[:nm], letters[nm:nm + nn], letters[nm + nn:nm + nn + nk], letters[nm + nn + nk:nm + nn + nk + nb]
+        ext = {ch: int(rng.choice([4, 8, 12, 16, 20, 32, 36, 48, 72] if ch not in k[1:] + bt else [2, 3, 4, 5])) for ch in m + nl + k + bt}
+        if np.prod([float(v) for v in ext.values()]) > 2e7:
+            continue
+        c, a, b = m + nl + bt, m + k + bt, nl + k + bt
+        for lst in (c, a, b):
+            rng.shuffle(lst)
+        alpha, beta = [(1.0, 0.0), (0.5, 2.0), (-1.0, 1.0)][int(rng.integers(0, 3))]
+        d = run_case(gpu, oracle, "".join(c), "".join(a), "".join(b), ext, np.float32, alpha, beta, seed=chunk * 50 + n)
+        ran += 1
+        if d.kernel_used == KF["TILE_TCGEN05"]:
+            took += 1
+    assert took >= 8, f"only {took} of {ran} cases reached the tcgen05 kernel"
