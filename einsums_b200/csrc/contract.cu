@@ -523,6 +523,150 @@ int try_run_tf32x3_generic(cudaStream_t s, const Plan &p, eb200_contract_desc &d
     return 1;
 }
 
+// ---------------------------------------------------------------- c64 contractions on tcgen05 (through the real 3xTF32 kernel)
+// A complex product is a real product of twice the size: with A' = A viewed as real rows [re, im interleaved along k] and
+//     B'[re-plane][n] = (Bre, -Bim ...),  B'[im-plane][n] = (Bim, Bre ...)
+// the real GEMM  A' (M x 2K) . B'^T (2K x 2N)  yields the real parts in the first plane's columns and the imaginary parts in the second
+// plane's — 8 M N K real flops, exactly the complex product's count. Both operands are first PACKED (one strided-copy launch each: the
+// index permutation, conjugation and alpha are absorbed there), so every tile-family pattern becomes one batched K-major product whose
+// multi-index C is written by the generic epilogue as (re, im) pairs. Packing moves O((M + N) K) bytes against O(M N K) flops.
+int try_run_c64_tcgen05(cudaStream_t s, const Plan &p, eb200_contract_desc &d, double beta_eff[2]) {
+    if (g_use_tcgen05 < 0) g_use_tcgen05 = env_int("EB200_USE_TCGEN05", 1);
+    const int mode = option(OPT_TCGEN05_GENERIC);
+    if (!g_use_tcgen05 || !mode || d.force_kernel != 0 || d.split_k > 1 || p.swapped) return 0;
+    if (p.m.n < 1 || p.n.n < 1 || p.k.n < 1 || p.m.n > 3 || p.n.n > 2 || p.b.n > 3) return 0;
+    if (p.b.n + p.m.n + p.k.n > EB200_MAX_RANK || p.b.n + p.n.n + p.k.n > EB200_MAX_RANK) return 0;
+    if (!encode_tiled_fn()) return 0;
+    for (int i = 0; i < MAXG; i++) // broadcast / one-sided sums (stride 0) and negative strides stay on the gather kernel
+        if ((i < p.m.n && p.m.s[ROLE_A][i] <= 0) || (i < p.n.n && p.n.s[ROLE_B][i] <= 0) || (i < p.k.n && (p.k.s[ROLE_A][i] <= 0 || p.k.s[ROLE_B][i] <= 0)) ||
+            (i < p.b.n && (p.b.s[ROLE_A][i] <= 0 || p.b.s[ROLE_B][i] <= 0)))
+            return 0;
+    const int64_t M = p.m.tot, N = p.n.tot, K = p.k.tot, NBt = p.b.tot, Kp = (K + 1) & ~1LL;
+    if (2 * K >= (1LL << 31) || NBt >= (1LL << 31) || M >= (1LL << 40) || N >= (1LL << 40)) return 0;
+    // enumeration order of the M and N groups: the index that pads least to a multiple of 32 goes innermost
+    auto order = [](const Grp &g, int *ord) {
+        int best = 0;
+        double bw = 1e30;
+        for (int i = 0; i < g.n; i++) {
+            const double w = (double)((g.ext[i] + 31) / 32 * 32) / (double)g.ext[i];
+            if (w < bw - 1e-12 || (std::fabs(w - bw) <= 1e-12 && g.ext[i] > g.ext[best])) { bw = w; best = i; }
+        }
+        int c = 0;
+        ord[c++] = best;
+        for (int i = 0; i < g.n; i++)
+            if (i != best) ord[c++] = i;
+    };
+    int om[3] = {0, 0, 0}, on[3] = {0, 0, 0};
+    order(p.m, om);
+    order(p.n, on);
+    Tf32GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < 3; i++) {
+        a.em[i] = i < p.m.n ? (int32_t)p.m.ext[om[i]] : 1;
+        a.en[i] = i < p.n.n ? (int32_t)p.n.ext[on[i]] : 1;
+        a.ek[i] = 1;
+        a.eb[i] = i < p.b.n ? (int32_t)p.b.ext[i] : 1;
+        a.gCm[i] = i < p.m.n ? 2 * p.m.s[ROLE_C][om[i]] : 0; // C strides in floats
+        a.gCn[i] = i < p.n.n ? 2 * p.n.s[ROLE_C][on[i]] : 0;
+        a.gCb[i] = i < p.b.n ? 2 * p.b.s[ROLE_C][i] : 0;
+        if ((i < p.m.n && p.m.ext[om[i]] >= (1LL << 31)) || (i < p.n.n && p.n.ext[on[i]] >= (1LL << 31))) return 0;
+    }
+    a.ek[0] = (int32_t)(2 * K);
+    a.mblk0 = (a.em[0] + 31) / 32; a.nblk0 = (a.en[0] + 31) / 32;
+    a.kstep0 = (int32_t)((2 * K + 31) / 32);
+    a.KT = a.kstep0;
+    a.MB = (int64_t)a.mblk0 * a.em[1] * a.em[2];
+    a.NB = (int64_t)a.nblk0 * a.en[1] * a.en[2];
+    const int64_t tm = (a.MB + 3) / 4, tn = (a.NB + 1) / 2; // 128 rows x 64 complex columns per tile
+    if (tm * tn > 0x7fffffffLL || tm * tn * NBt > (1LL << 40)) return 0;
+    if (mode != 2) {
+        const double waste = (double)(tm * 128) / (double)M * ((double)(tn * 64) / (double)N);
+        if (waste > 2.0) return 0;
+        if (tm * tn * NBt * 2 < sm_count()) return 0;      // too few tiles: the FMA-pipe kernel has split-K
+        if (std::min(M, N) < 128 || K < 16) return 0;       // packing would not pay
+    }
+    // ---- pack: A' [b][m composite][Kp] complex (alpha and conj folded in), Bc [b][n composite][K] complex, B' two planes of rows
+    void  *Ap = nullptr, *Bc = nullptr, *Bp = nullptr;
+    int    rc = EB200_OK;
+    auto   pack = [&](const Grp &tgt, const int *ord, int role, const void *src, void *dst, int64_t row_len, const float *al, int conj) -> int {
+        int64_t dims[EB200_MAX_RANK], ss[EB200_MAX_RANK], ds[EB200_MAX_RANK];
+        int     perm[EB200_MAX_RANK], r = 0;
+        int64_t st = 1;
+        for (int i = 0; i < p.k.n; i++, r++) { dims[r] = p.k.ext[i]; ss[r] = p.k.s[role][i]; ds[r] = st; st *= p.k.ext[i]; }
+        st = row_len;
+        for (int i = 0; i < tgt.n; i++, r++) { dims[r] = tgt.ext[ord[i]]; ss[r] = tgt.s[role][ord[i]]; ds[r] = st; st *= tgt.ext[ord[i]]; }
+        for (int i = 0; i < p.b.n; i++, r++) { dims[r] = p.b.ext[i]; ss[r] = p.b.s[role][i]; ds[r] = st; st *= p.b.ext[i]; }
+        for (int i = 0; i < r; i++) perm[i] = i;
+        const float zero[2] = {0.f, 0.f};
+        return eb200_cpermute((void *)s, r, dims, ss, perm, ds, al, (const float *)src, zero, (float *)dst, conj);
+    };
+    const float alpha_c[2] = {(float)d.alpha[0], (float)d.alpha[1]}, one_c[2] = {1.f, 0.f};
+    const size_t bytesA = (size_t)NBt * M * Kp * 8, bytesBc = (size_t)NBt * N * K * 8, bytesBp = (size_t)NBt * 2 * N * Kp * 8;
+    if ((rc = scratch_alloc(&Ap, bytesA, s)) || (rc = scratch_alloc(&Bc, bytesBc, s)) || (rc = scratch_alloc(&Bp, bytesBp, s))) {
+        if (Ap) cudaFreeAsync(Ap, s);
+        if (Bc) cudaFreeAsync(Bc, s);
+        return -rc;
+    }
+    auto release = [&]() {
+        cudaFreeAsync(Ap, s);
+        cudaFreeAsync(Bc, s);
+        cudaFreeAsync(Bp, s);
+    };
+    int64_t launches0 = launch_counter();
+    if ((rc = pack(p.m, om, ROLE_A, d.A.data, Ap, Kp, alpha_c, d.conj_a)) || (rc = pack(p.n, on, ROLE_B, d.B.data, Bc, K, one_c, d.conj_b)) ||
+        (rc = k_launch_c64_expand(s, Bc, Bp, NBt * N, N, K, Kp))) {
+        release();
+        return -rc;
+    }
+    // ---- tensor maps over the packed operands (real view: rows of 2 Kp floats, 2 K of them valid — the rest is out of bounds = zero)
+    Grp gk, gb, gm, gn;
+    memset(&gk, 0, sizeof(gk)); memset(&gb, 0, sizeof(gb)); memset(&gm, 0, sizeof(gm)); memset(&gn, 0, sizeof(gn));
+    gk.n = 1; gk.ext[0] = 2 * K; gk.s[ROLE_A][0] = gk.s[ROLE_B][0] = 1;
+    int64_t st = 2 * Kp;
+    gm.n = p.m.n;
+    for (int i = 0; i < p.m.n; i++) { gm.ext[i] = a.em[i]; gm.s[ROLE_A][i] = st; st *= a.em[i]; }
+    if (NBt > 1) { gb.n = 1; gb.ext[0] = NBt; gb.s[ROLE_A][0] = st; }
+    st = 2 * Kp;
+    gn.n = p.n.n + 1;
+    for (int i = 0; i < p.n.n; i++) { gn.ext[i] = a.en[i]; gn.s[ROLE_B][i] = st; st *= a.en[i]; }
+    gn.ext[p.n.n] = 2; gn.s[ROLE_B][p.n.n] = st; st *= 2; // the (real | imaginary)-output planes
+    if (NBt > 1) gb.s[ROLE_B][0] = st;
+    CUtensorMap tmA, tmB;
+    int32_t     dBn[3];
+    if (!make_generic_map_f32(&tmA, (const float *)Ap, gm, gk, gb, ROLE_A, true, a.dAm, a.dAk, a.dAb) ||
+        !make_generic_map_f32(&tmB, (const float *)Bp, gn, gk, gb, ROLE_B, true, dBn, a.dBk, a.dBb)) {
+        release(); // nothing of C has been touched yet: the FMA-pipe kernel takes over
+        return 0;
+    }
+    for (int i = 0; i < 3; i++) a.dBn[i] = i < p.n.n ? dBn[i] : -1;
+    a.dBc = dBn[p.n.n];
+    a.cplx = 1;
+    a.b_flat = 1;
+    // the epilogue multiplies by a REAL beta per component; a beta with an imaginary part scales C beforehand
+    if (beta_eff[1] != 0.0) {
+        rc = launch_scale<float2>(s, p.t, d.C.data, beta_eff, d);
+        if (rc) { release(); return -rc; }
+        d.launches--; // counted below with the other launches of this call
+        beta_eff[0] = 1.0; beta_eff[1] = 0.0;
+    }
+    a.tiles_m = (int)tm; a.tiles_n = (int)tn;
+    a.batch = NBt;
+    a.M = M; a.N = 2 * N; a.K = 2 * K;
+    a.C = (float *)d.C.data;
+    a.alpha = 1.f; a.beta = (float)beta_eff[0];
+    a.c_n_unit = (p.n.s[ROLE_C][on[0]] == 1 && p.m.s[ROLE_C][om[0]] != 1) ? 1 : 0;
+    constexpr size_t SMEM = 3 * 65536 + 4 * (32 * 33 * 4) + 1024 + 256 + 2048;
+    const unsigned   grid = (unsigned)std::min<int64_t>(tm * tn * NBt, sm_count());
+    rc = k_launch_tf32x3_generic(s, tmA, tmB, a, dim3(grid, 1, 1), SMEM, false, false);
+    release();
+    if (rc) return -rc;
+    d.launches += (int)(launch_counter() - launches0);
+    d.split_k = 1;
+    d.kernel_used = EB200_KF_TILE_TCGEN05;
+    set_last_kernel("gemm_tf32x3_tcgen05<c64>");
+    return 1;
+}
+
 template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const double beta_eff[2]) {
     TileArgs args;
     args.p = p;
@@ -549,6 +693,14 @@ template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract
     if constexpr (std::is_same_v<T, double2>) {
         if (!mma) {
             int r = try_run_tma_z(s, p, d, beta_eff);
+            if (r == 1) return EB200_OK;
+            if (r < 0) return -r;
+        }
+    }
+    if constexpr (std::is_same_v<T, float2>) {
+        if (!mma) {
+            double be[2] = {beta_eff[0], beta_eff[1]};
+            int    r = try_run_c64_tcgen05(s, p, d, be);
             if (r == 1) return EB200_OK;
             if (r < 0) return -r;
         }

@@ -40,6 +40,12 @@ struct Tf32GemmArgs {
     int32_t dAm[3], dAk[3], dAb[3], dBn[3], dBk[3], dBb[3]; // tensor-map dimension of each index (-1: absent)
     int64_t gCm[3], gCn[3], gCb[3];                     // element strides in C
     int32_t c_n_unit;                                   // the inner N index is unit-stride in C: transposed (row-segment) stores
+    // ---- c64 through the real kernel (contract.cu, try_run_c64_tcgen05): A' = packed [b][m][re,im interleaved along k], B' = two planes of
+    //      rows (real-output rows | imaginary-output rows). A tile covers 64 complex columns: boxes 0,1 come from plane 0, boxes 2,3 from
+    //      plane 1 of the same columns, so accumulator column j is the real and column j + 64 the imaginary part of complex column j.
+    int32_t cplx;                                       // 1: complex-interleaved C (strides given in floats), 64 complex columns per tile
+    int32_t dBc;                                        // tensor-map dimension of B'-plane index
+    int32_t b_flat;                                     // the operands carry ONE merged batch dimension (dAb[0] / dBb[0]); C keeps eb / gCb
 };
 
 #ifdef EB200_TF32_KERNEL_IMPL // the kernel itself is compiled by k_tile_tf32.cu only
@@ -146,7 +152,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
                 decode(i, tile_m, tile_n, b);
                 int c0[5] = {0, 0, 0, 0, 0};
                 if (lane < 8) {
-                    const int64_t  cb = (int64_t)(is_a ? tile_m : tile_n) * 4 + blk;
+                    const int64_t  cb = is_a ? (int64_t)tile_m * 4 + blk : (args.cplx ? (int64_t)tile_n * 2 + (blk & 1) : (int64_t)tile_n * 4 + blk);
                     const int32_t *ext = is_a ? args.em : args.en, *dt = is_a ? args.dAm : args.dBn, *db = is_a ? args.dAb : args.dBb;
                     const int      blk0n = is_a ? args.mblk0 : args.nblk0;
                     int            blk0 = blk0n, i1 = 0, i2 = 0; // out of range: an inner coordinate past the extent zero-fills the whole box
@@ -159,13 +165,22 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
                     }
 #pragma unroll
                     for (int d = 0; d < 5; d++) c0[d] = (dt[0] == d ? 32 * blk0 : 0) + (dt[1] == d ? i1 : 0) + (dt[2] == d ? i2 : 0);
-                    int x = b;
+                    if (args.b_flat) {
 #pragma unroll
-                    for (int q = 0; q < 3; q++) {
-                        const int bi = x % args.eb[q];
-                        x /= args.eb[q];
+                        for (int d = 0; d < 5; d++) c0[d] += (db[0] == d ? b : 0);
+                    } else {
+                        int x = b;
 #pragma unroll
-                        for (int d = 0; d < 5; d++) c0[d] += (db[q] == d ? bi : 0);
+                        for (int q = 0; q < 3; q++) {
+                            const int bi = x % args.eb[q];
+                            x /= args.eb[q];
+#pragma unroll
+                            for (int d = 0; d < 5; d++) c0[d] += (db[q] == d ? bi : 0);
+                        }
+                    }
+                    if (args.cplx && !is_a) {
+#pragma unroll
+                        for (int d = 0; d < 5; d++) c0[d] += (args.dBc == d ? (blk >> 1) : 0);
                     }
                 }
                 const int kd0 = is_a ? args.dAk[0] : args.dBk[0], kd1 = is_a ? args.dAk[1] : args.dBk[1], kd2 = is_a ? args.dAk[2] : args.dBk[2];
@@ -380,7 +395,10 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
                     };
                     asm volatile("bar.sync 1, 128;" ::: "memory"); // the previous tile's stores have read the tables
                     moffC[e] = offset_of((int64_t)tile_m * BM + e, args.em, args.mblk0, args.MB, args.gCm);
-                    noffC[e] = offset_of((int64_t)tile_n * BN + e, args.en, args.nblk0, args.NB, args.gCn);
+                    if (args.cplx) { // column e: complex column e & 63 of the tile, real (e < 64) or imaginary part
+                        const int64_t o = offset_of((int64_t)tile_n * (BN / 2) + (e & 63), args.en, args.nblk0, args.NB, args.gCn);
+                        noffC[e] = (o == INVALID) ? INVALID : o + (e >> 6);
+                    } else noffC[e] = offset_of((int64_t)tile_n * BN + e, args.en, args.nblk0, args.NB, args.gCn);
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
                 float acc[BN];
@@ -440,7 +458,34 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
                     } else {
                         // lanes along m
                         const int64_t om = moffC[quad * 32 + lane];
-                        if (om != INVALID) {
+                        if (args.cplx) {
+                            // (re, im) = accumulator columns (j, j + 64): one 8-byte access per complex element
+                            if (c0 < BN / 2 && om != INVALID) {
+#pragma unroll
+                                for (int j0 = 0; j0 < 32; j0 += 16) {
+                                    int64_t on[16];
+                                    float2  old[16];
+#pragma unroll
+                                    for (int j = 0; j < 16; j++) on[j] = noffC[c0 + j0 + j];
+                                    if (beta != 0.f) {
+#pragma unroll
+                                        for (int j = 0; j < 16; j++)
+                                            old[j] = (on[j] != INVALID) ? *reinterpret_cast<const float2 *>(Cb + om + on[j]) : make_float2(0.f, 0.f);
+                                    }
+#pragma unroll
+                                    for (int j = 0; j < 16; j++) {
+                                        if (on[j] != INVALID) {
+                                            float2 o = make_float2(alpha * acc[c0 + j0 + j], alpha * acc[(c0 + j0 + j + BN / 2) & (BN - 1)]);
+                                            if (beta != 0.f) {
+                                                o.x = fmaf(beta, old[j].x, o.x);
+                                                o.y = fmaf(beta, old[j].y, o.y);
+                                            }
+                                            *reinterpret_cast<float2 *>(Cb + om + on[j]) = o;
+                                        }
+                                    }
+                                }
+                            }
+                        } else if (om != INVALID) {
 #pragma unroll
                             for (int j0 = 0; j0 < 32; j0 += 16) { // fully unrolled: acc[] must stay in registers
                                 int64_t on[16];

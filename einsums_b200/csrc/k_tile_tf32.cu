@@ -41,4 +41,25 @@ int k_launch_tf32x3_generic(cudaStream_t s, const CUtensorMap &tmA, const CUtens
     EB_POST_LAUNCH("gemm_tf32x3_tcgen05<generic>");
     return EB200_OK;
 }
+
+// B' of the c64 path (contract.cu, try_run_c64_tcgen05): Bc = B gathered to [rows = batch x n][K] complex; B' holds, per batch, a plane
+// of real-output rows (Bre, -Bim interleaved along k) and a plane of imaginary-output rows (Bim, Bre); rows are 2 * Kp floats long
+__global__ void __launch_bounds__(256) c64_expand_b(const float2 *__restrict__ Bc, float *__restrict__ Bp, int64_t total, int64_t N, int64_t K, int64_t Kp) {
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = idx / K, k = idx - r * K, b = r / N, n = r - b * N;
+        const float2  v = Bc[idx];
+        float2       *re_row = reinterpret_cast<float2 *>(Bp + ((b * 2 + 0) * N + n) * 2 * Kp);
+        float2       *im_row = reinterpret_cast<float2 *>(Bp + ((b * 2 + 1) * N + n) * 2 * Kp);
+        re_row[k] = make_float2(v.x, -v.y);
+        im_row[k] = make_float2(v.y, v.x);
+    }
+}
+int k_launch_c64_expand(cudaStream_t s, const void *Bc, void *Bp, int64_t rows, int64_t N, int64_t K, int64_t Kp) {
+    const int64_t total = rows * K;
+    if (total <= 0) return EB200_OK;
+    const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 32);
+    c64_expand_b<<<grid, 256, 0, s>>>((const float2 *)Bc, (float *)Bp, total, N, K, Kp);
+    EB_POST_LAUNCH("c64_expand_b");
+    return EB200_OK;
+}
 } // namespace eb200

@@ -1096,3 +1096,44 @@ def test_tcgen05_generic_fuzz(tcgen05_generic_always, oracle, chunk):
         if d.kernel_used == KF["TILE_TCGEN05"]:
             took += 1
     assert took >= 8, f"only {took} of {ran} cases reached the tcgen05 kernel"
+
+
+# c64 on the tcgen05 kernel: both operands packed to real K-major form (alpha, conj and the index permutation absorbed by the pack),
+# the product done by gemm_tf32x3_tcgen05 in complex mode (64 complex columns per tile, (re, im) stores)
+C64_TCGEN05 = [
+    ("ij", "ik", "kj", dict(i=150, j=132, k=100)),
+    ("ij", "ki", "jk", dict(i=130, j=70, k=33)),                       # odd K: packed rows padded to an even length
+    ("ji", "ik", "jk", dict(i=129, j=71, k=64)),                       # C transposed: the inner N index is unit-stride in C
+    ("mbej", "jnfb", "mnef", dict(m=6, b=22, e=18, j=7, n=5, f=24)),   # no alignment rule: operands are packed
+    ("abef", "nmef", "mnab", dict(a=9, b=36, e=10, f=34, m=5, n=6)),
+    ("bij", "bik", "bkj", dict(i=65, j=34, k=40, b=5)),
+    ("xyabcd", "xyakb", "ykxcd", dict(x=2, y=3, a=5, b=16, c=4, d=20, k=40)),
+]
+
+
+@pytest.mark.parametrize("case", C64_TCGEN05, ids=lambda c: f"{c[0]}<-{c[1]},{c[2]}")
+def test_c64_tcgen05_patterns(tcgen05_generic_always, oracle, case):
+    from einsums_b200 import KF
+    gpu = tcgen05_generic_always
+    c_idx, a_idx, b_idx, ext = case
+    for (alpha, beta, ca, cb) in ((0.25, 1.0, False, False), (1.0 - 0.5j, 0.0, True, False), (-0.5 + 0.25j, 2.0 - 1.0j, False, True), (1.0, 0.5, True, True)):
+        d = run_case(gpu, oracle, c_idx, a_idx, b_idx, ext, np.complex64, alpha, beta, conj_a=ca, conj_b=cb, seed=47)
+        assert d.kernel_used == KF["TILE_TCGEN05"] and gpu.last_kernel() == "gemm_tf32x3_tcgen05<c64>", (d.kernel_used, gpu.last_kernel(), case)
+
+
+def test_c64_tcgen05_default_routing_and_beta_zero(gpu, oracle):
+    """Without any knob a c64 product with enough tiles takes the tcgen05 kernel; a small one stays on the FMA-pipe kernel; beta = 0
+    must not read C (NaN-filled); the flat seam's cgemm lands on the same kernel."""
+    from einsums_b200 import KF
+    d = run_case(gpu, oracle, "ij", "ik", "jk", dict(i=1280, j=640, k=96), np.complex64, 1.0 + 0.5j, 1.0, seed=3)
+    assert d.kernel_used == KF["TILE_TCGEN05"] and gpu.last_kernel() == "gemm_tf32x3_tcgen05<c64>", gpu.last_kernel()
+    d = run_case(gpu, oracle, "ij", "ik", "jk", dict(i=96, j=64, k=96), np.complex64, 1.0, 1.0, seed=4)
+    assert d.kernel_used == KF["TILE_SIMT"]
+    rng = np.random.default_rng(5)
+    A, B = rand(rng, (1280, 96), np.complex64), rand(rng, (96, 640), np.complex64)
+    Cd = torch.full((1280, 640), float("nan"), dtype=torch.complex64, device="cuda")
+    gpu.contract("ij", Cd, "ik", dev(A), "kj", dev(B), 1.0, 0.0)
+    assert gpu.last_kernel() == "gemm_tf32x3_tcgen05<c64>"
+    ref = np.zeros((1280, 640), np.complex64)
+    oracle.einsum_generic("ij", ref, "ik", A, "kj", B, 1.0, 0.0)
+    assert_close(Cd.cpu().numpy(), ref, np.complex64)
