@@ -376,15 +376,12 @@ int try_run_tf32x3(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const 
 }
 
 // ---------------------------------------------------------------- complex FP64 on the FP64 tensor pipe (plain products)
-int try_run_tma_z(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const double beta_eff[2]) {
-    if (!option(OPT_TMA) || d.force_kernel != 0 || d.split_k > 1 || p.swapped) return 0;
-    if (p.b.n != 0 || p.m.n != 1 || p.n.n != 1 || p.k.n != 1) return 0;
+// one plain c128 product on gemm_tma_z: 0 = not taken (layout / size), 1 = launched, < 0 = -error
+int launch_tma_z(cudaStream_t s, const double2 *A, const double2 *B, double2 *C, int64_t M, int64_t N, int64_t K, int64_t sAm, int64_t sAk, int64_t sBn,
+                 int64_t sBk, int64_t sCm, int64_t sCn, const double alpha[2], const double beta[2], int conj_a, int conj_b) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return 0;
-    const double2 *A = (const double2 *)d.A.data, *B = (const double2 *)d.B.data;
-    const int64_t  M = p.m.tot, N = p.n.tot, K = p.k.tot;
-    const int64_t  sAm = p.m.s[ROLE_A][0], sAk = p.k.s[ROLE_A][0], sBn = p.n.s[ROLE_B][0], sBk = p.k.s[ROLE_B][0];
-    const bool     ak = (sAk == 1), bk = (sBk == 1);
+    const bool ak = (sAk == 1), bk = (sBk == 1);
     if (!ak && sAm != 1) return 0;
     if (!bk && sBn != 1) return 0;
     const int64_t lda = ak ? sAm : sAk, ldb = bk ? sBn : sBk;
@@ -393,8 +390,7 @@ int try_run_tma_z(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const d
     if ((ak ? K : M) > lda && (ak ? M : K) > 1) return 0;
     if ((bk ? K : N) > ldb && (bk ? N : K) > 1) return 0;
     const int64_t tm = (M + 127) / 128, tn = (N + 31) / 32;
-    // small outputs want split-K (the FMA kernel has it); the tensor-pipe kernel needs enough tiles to fill the machine
-    if (tm * tn > 0x7fffffffLL || tm * tn * 2 <= (int64_t)sm_count() * 2) return 0;
+    if (tm * tn > 0x7fffffffLL) return 0;
     auto make_map = [&](CUtensorMap *map, const double2 *base, int64_t inner, int64_t outer, int64_t ld, uint32_t box_outer) {
         cuuint64_t dims[2] = {(cuuint64_t)inner * 2, (cuuint64_t)outer};
         cuuint64_t strides[1] = {(cuuint64_t)ld * 16};
@@ -407,18 +403,98 @@ int try_run_tma_z(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const d
     if (!(bk ? make_map(&tmB, B, K, N, ldb, 32) : make_map(&tmB, B, N, K, ldb, 8))) return 0;
     TmaZGemmArgs a;
     a.M = M; a.N = N; a.K = K;
-    a.sCm = p.m.s[ROLE_C][0]; a.sCn = p.n.s[ROLE_C][0];
-    a.C = (double2 *)d.C.data;
-    a.alpha[0] = d.alpha[0]; a.alpha[1] = d.alpha[1];
-    a.beta[0] = beta_eff[0]; a.beta[1] = beta_eff[1];
+    a.sCm = sCm; a.sCn = sCn;
+    a.C = C;
+    a.alpha[0] = alpha[0]; a.alpha[1] = alpha[1];
+    a.beta[0] = beta[0]; a.beta[1] = beta[1];
     a.tiles_m = (int)tm; a.tiles_n = (int)tn;
-    a.conj_a = d.conj_a; a.conj_b = d.conj_b;
+    a.conj_a = conj_a; a.conj_b = conj_b;
     const size_t SMEM = 4 * (128 * 8 * 16 + 32 * 8 * 16) + 1024 + 64;
     int rc = k_launch_tma_z(s, tmA, tmB, a, dim3((unsigned)(tm * tn), 1, 1), SMEM, ak, bk);
-    if (rc) return -rc;
+    return rc ? -rc : 1;
+}
+
+int try_run_tma_z(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const double beta_eff[2]) {
+    if (!option(OPT_TMA) || d.force_kernel != 0 || d.split_k > 1 || p.swapped) return 0;
+    if (p.b.n != 0 || p.m.n != 1 || p.n.n != 1 || p.k.n != 1) return 0;
+    const int64_t tm = (p.m.tot + 127) / 128, tn = (p.n.tot + 31) / 32;
+    // small outputs want split-K (the FMA kernel has it); the tensor-pipe kernel needs enough tiles to fill the machine
+    if (tm * tn * 2 <= (int64_t)sm_count() * 2) return 0;
+    int r = launch_tma_z(s, (const double2 *)d.A.data, (const double2 *)d.B.data, (double2 *)d.C.data, p.m.tot, p.n.tot, p.k.tot, p.m.s[ROLE_A][0],
+                         p.k.s[ROLE_A][0], p.n.s[ROLE_B][0], p.k.s[ROLE_B][0], p.m.s[ROLE_C][0], p.n.s[ROLE_C][0], d.alpha, beta_eff, d.conj_a, d.conj_b);
+    if (r != 1) return r;
     d.launches++;
     d.split_k = 1;
     set_last_kernel("gemm_tma_z");
+    return 1;
+}
+
+// c128 contractions that are not a plain product (multi-index groups, batches, strided layouts): TTGT around gemm_tma_z. A and B are
+// gathered into K-major matrices by one strided copy each (alpha and the conjugations folded in), every batch member is one product on
+// the FP64 tensor pipe into a dense temporary, and one strided accumulate  C = beta C + T  scatters it. The copies move
+// O((M + N) K + M N) elements against 8 M N K flops; the FMA-pipe kernel they replace runs at two thirds of the tensor-pipe rate.
+int try_run_z_packed(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const double beta_eff[2]) {
+    const int mode = option(OPT_TMA_GENERIC); // 2: whenever legal (tests)
+    if (!option(OPT_TMA) || !mode || d.force_kernel != 0 || d.split_k > 1 || p.swapped) return 0;
+    if (p.m.n < 1 || p.n.n < 1 || p.k.n < 1) return 0;
+    if (p.b.n + p.m.n + p.k.n > EB200_MAX_RANK || p.b.n + p.n.n + p.k.n > EB200_MAX_RANK || p.b.n + p.m.n + p.n.n > EB200_MAX_RANK) return 0;
+    for (int i = 0; i < MAXG; i++) // broadcast / one-sided sums (stride 0) and negative strides stay on the gather kernel
+        if ((i < p.m.n && (p.m.s[ROLE_A][i] <= 0 || p.m.s[ROLE_C][i] <= 0)) || (i < p.n.n && (p.n.s[ROLE_B][i] <= 0 || p.n.s[ROLE_C][i] <= 0)) ||
+            (i < p.k.n && (p.k.s[ROLE_A][i] <= 0 || p.k.s[ROLE_B][i] <= 0)) ||
+            (i < p.b.n && (p.b.s[ROLE_A][i] <= 0 || p.b.s[ROLE_B][i] <= 0 || p.b.s[ROLE_C][i] <= 0)))
+            return 0;
+    const int64_t M = p.m.tot, N = p.n.tot, K = p.k.tot, NBt = p.b.tot;
+    const int64_t tm = (M + 127) / 128, tn = (N + 31) / 32;
+    if (NBt > 256) return 0; // one launch per batch member
+    if (mode != 2 && (tm * tn <= sm_count() || K < 32)) return 0;
+    void *Ap = nullptr, *Bp = nullptr, *Tp = nullptr;
+    int   rc;
+    if ((rc = scratch_alloc(&Ap, (size_t)NBt * M * K * 16, s)) || (rc = scratch_alloc(&Bp, (size_t)NBt * N * K * 16, s)) ||
+        (rc = scratch_alloc(&Tp, (size_t)NBt * M * N * 16, s))) {
+        if (Ap) cudaFreeAsync(Ap, s);
+        if (Bp) cudaFreeAsync(Bp, s);
+        return -rc;
+    }
+    auto release = [&]() {
+        cudaFreeAsync(Ap, s);
+        cudaFreeAsync(Bp, s);
+        cudaFreeAsync(Tp, s);
+    };
+    // strided copy between a tensor's own layout and the dense [batch][rows][cols] form (inner-first axis lists)
+    auto copy = [&](const Grp &rows, const Grp &cols, int role, const void *src, void *dst, bool to_dense, const double *al, const double *be, int conj) -> int {
+        int64_t dims[EB200_MAX_RANK], ss[EB200_MAX_RANK], ds[EB200_MAX_RANK];
+        int     perm[EB200_MAX_RANK], r = 0;
+        int64_t st = 1;
+        const Grp *gs[3] = {&cols, &rows, &p.b};
+        for (const Grp *g : gs)
+            for (int i = 0; i < g->n; i++, r++) {
+                dims[r] = g->ext[i];
+                (to_dense ? ss : ds)[r] = g->s[role][i];
+                (to_dense ? ds : ss)[r] = st;
+                st *= g->ext[i];
+            }
+        for (int i = 0; i < r; i++) perm[i] = i;
+        return eb200_zpermute((void *)s, r, dims, ss, perm, ds, al, (const double *)src, be, (double *)dst, conj);
+    };
+    const double  one[2] = {1.0, 0.0}, zero[2] = {0.0, 0.0};
+    const int64_t launches0 = launch_counter();
+    if ((rc = copy(p.m, p.k, ROLE_A, d.A.data, Ap, true, d.alpha, zero, d.conj_a)) || (rc = copy(p.n, p.k, ROLE_B, d.B.data, Bp, true, one, zero, d.conj_b))) {
+        release();
+        return -rc;
+    }
+    for (int64_t b = 0; b < NBt; b++) {
+        int r = launch_tma_z(s, (const double2 *)Ap + b * M * K, (const double2 *)Bp + b * N * K, (double2 *)Tp + b * M * N, M, N, K, K, 1, K, 1, N, 1, one, zero, 0, 0);
+        if (r != 1) { // nothing of C has been touched yet
+            release();
+            return r < 0 ? r : 0;
+        }
+    }
+    rc = copy(p.m, p.n, ROLE_C, Tp, d.C.data, false, one, beta_eff, 0);
+    release();
+    if (rc) return -rc;
+    d.launches += (int)(launch_counter() - launches0);
+    d.split_k = 1;
+    set_last_kernel("gemm_tma_z<packed>");
     return 1;
 }
 
@@ -693,6 +769,9 @@ template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract
     if constexpr (std::is_same_v<T, double2>) {
         if (!mma) {
             int r = try_run_tma_z(s, p, d, beta_eff);
+            if (r == 1) return EB200_OK;
+            if (r < 0) return -r;
+            r = try_run_z_packed(s, p, d, beta_eff);
             if (r == 1) return EB200_OK;
             if (r < 0) return -r;
         }

@@ -66,13 +66,14 @@ struct Options {
         v[OPT_TMA_DIST] = env("EB200_TMA_DIST", 0);
         v[OPT_PERMUTE_TMA] = env("EB200_PERMUTE_TMA", 1);
         v[OPT_TCGEN05_GENERIC] = env("EB200_TCGEN05_GENERIC", 1);
+        v[OPT_SCRATCH_KEEP_MB] = env("EB200_SCRATCH_KEEP_MB", 4096);
     }
 };
 Options &options() {
     static Options o;
     return o;
 }
-const char *const kOptionNames[OPT_COUNT] = {"tma", "tma_generic", "tma_tile", "tma_dist", "permute_tma", "tcgen05_generic"};
+const char *const kOptionNames[OPT_COUNT] = {"tma", "tma_generic", "tma_tile", "tma_dist", "permute_tma", "tcgen05_generic", "scratch_keep_mb"};
 thread_local const char *t_last_kernel = "";
 } // namespace
 int  option(int which) { return options().v[which].load(std::memory_order_relaxed); }
@@ -82,7 +83,9 @@ void set_last_kernel(const char *name) { t_last_kernel = name; }
 // Split-K partials, mixed-type widened copies and device-side scalars come from a PRIVATE memory pool per device. The
 // device's default pool (shared with the embedding application, e.g. torch) is never touched. Freed scratch up to
 // `keep` bytes stays cached across synchronisations (a release threshold of 0 would hand it back at every sync, ~1 ms
-// per split-K call); anything above is returned to the driver at the next synchronisation point.
+// per split-K call); anything above is returned to the driver at the next synchronisation point. `keep` is the option
+// "scratch_keep_mb" (default 4096 MB = 2 % of the B200's HBM: the packed complex paths hold three operand-sized buffers per call, and
+// re-acquiring 2 GB from the driver costs ~16 ms per call); eb200_set_option updates live pools, 0 returns everything at each sync.
 namespace {
 struct ScratchPools {
     std::mutex    mu;
@@ -110,7 +113,7 @@ int scratch_alloc(void **p, size_t bytes, cudaStream_t s) {
             props.location.type = cudaMemLocationTypeDevice;
             props.location.id = dev;
             EB_CUDA(cudaMemPoolCreate(&sp.pool[dev], &props));
-            uint64_t keep = 256ull << 20;
+            uint64_t keep = (uint64_t)std::max(0, option(OPT_SCRATCH_KEEP_MB)) << 20;
             EB_CUDA(cudaMemPoolSetAttribute(sp.pool[dev], cudaMemPoolAttrReleaseThreshold, &keep));
         }
         pool = sp.pool[dev];
@@ -389,6 +392,13 @@ int eb200_set_option(const char *name, int value) {
     for (int i = 0; i < OPT_COUNT; i++)
         if (!strcmp(name, kOptionNames[i])) {
             options().v[i].store(value, std::memory_order_relaxed);
+            if (i == OPT_SCRATCH_KEEP_MB) { // live pools follow the new threshold
+                ScratchPools &sp = scratch_pools();
+                std::lock_guard<std::mutex> lock(sp.mu);
+                uint64_t keep = (uint64_t)std::max(0, value) << 20;
+                for (cudaMemPool_t pool : sp.pool)
+                    if (pool) EB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+            }
             return EB200_OK;
         }
     return fail(EB200_ERR_INVALID_ARGUMENT, "eb200_set_option: unknown option '%s'", name);

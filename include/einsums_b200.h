@@ -318,7 +318,9 @@ const char *eb200_last_kernel_name(void);
  *   "tma_dist"     0 | n: automatic / issue the loads of step t + n while step t is consumed (1 <= n < stages)
  *   "permute_tma"  1 | 0: TMA-staged FP64 plane transpose whenever the layout has a tensor map / never (register-staged kernels)
  *   "tcgen05_generic" 1 | 0 | 2: multi-index FP32 contractions on the tcgen05 kernel by the padding / fill rules / never / whenever legal
- *                  (default from EB200_TCGEN05_GENERIC) */
+ *                  (default from EB200_TCGEN05_GENERIC)
+ *   "scratch_keep_mb" n: freed scratch (split-K partials, packed complex operands, widened copies) the library's PRIVATE memory pool
+ *                  keeps cached across synchronisations, in MB (default 4096, EB200_SCRATCH_KEEP_MB); the rest goes back to the driver */
 int eb200_set_option(const char *name, int value);
 int eb200_get_option(const char *name, int *value);
 

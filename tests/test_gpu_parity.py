@@ -1137,3 +1137,29 @@ def test_c64_tcgen05_default_routing_and_beta_zero(gpu, oracle):
     ref = np.zeros((1280, 640), np.complex64)
     oracle.einsum_generic("ij", ref, "ik", A, "kj", B, 1.0, 0.0)
     assert_close(Cd.cpu().numpy(), ref, np.complex64)
+
+
+@pytest.mark.parametrize("case", C64_TCGEN05, ids=lambda c: f"{c[0]}<-{c[1]},{c[2]}")
+def test_c128_packed_tensor_pipe_patterns(tma_generic_always, oracle, case):
+    """c128 contractions that are not a plain product: operands gathered to K-major matrices, gemm_tma_z per batch member into a dense
+    temporary, strided accumulate into C (TTGT around the FP64 tensor-pipe kernel); conj flags, complex alpha / beta."""
+    gpu = tma_generic_always
+    c_idx, a_idx, b_idx, ext = case
+    for (alpha, beta, ca, cb) in ((0.25, 1.0, False, False), (1.0 - 0.5j, 0.0, True, False), (-0.5 + 0.25j, 2.0 - 1.0j, False, True)):
+        run_case(gpu, oracle, c_idx, a_idx, b_idx, ext, np.complex128, alpha, beta, conj_a=ca, conj_b=cb, seed=53)
+        assert gpu.last_kernel() in ("gemm_tma_z<packed>", "gemm_tma_z"), (gpu.last_kernel(), case)
+
+
+def test_c128_packed_default_routing(gpu, oracle):
+    """A c128 Wmbej with more tiles than SMs takes the packed tensor-pipe path without any knob; beta = 0 never reads C."""
+    ext = dict(m=20, b=64, e=48, j=10, n=2, f=40)
+    run_case(gpu, oracle, "mbej", "jnfb", "mnef", ext, np.complex128, -0.5, 1.0, seed=11)
+    assert gpu.last_kernel() == "gemm_tma_z<packed>", gpu.last_kernel()
+    rng = np.random.default_rng(12)
+    t, g = rand(rng, (10, 2, 40, 64), np.complex128), rand(rng, (20, 2, 48, 40), np.complex128)
+    Wd = torch.full((20, 64, 48, 10), float("nan"), dtype=torch.complex128, device="cuda")
+    gpu.contract("mbej", Wd, "jnfb", dev(t), "mnef", dev(g), 1.0, 0.0)
+    assert gpu.last_kernel() == "gemm_tma_z<packed>"
+    ref = np.zeros((20, 64, 48, 10), np.complex128)
+    oracle.einsum_generic("mbej", ref, "jnfb", t, "mnef", g, 1.0, 0.0)
+    assert_close(Wd.cpu().numpy(), ref, np.complex128)
