@@ -606,19 +606,22 @@ int try_run_tf32x3_generic(cudaStream_t s, const Plan &p, eb200_contract_desc &d
 // plane's — 8 M N K real flops, exactly the complex product's count. Both operands are first PACKED (one strided-copy launch each: the
 // index permutation, conjugation and alpha are absorbed there), so every tile-family pattern becomes one batched K-major product whose
 // multi-index C is written by the generic epilogue as (re, im) pairs. Packing moves O((M + N) K) bytes against O(M N K) flops.
-int try_run_c64_tcgen05(cudaStream_t s, const Plan &p, eb200_contract_desc &d, double beta_eff[2]) {
+// CPLX = false is the FP32 variant of the same scheme (no planes, no expansion): it serves real contractions whose own layout has no
+// tensor map (strides that are not multiples of 16 bytes, no unit-stride index) and would otherwise run on the FMA pipe.
+template <bool CPLX> int try_run_packed_tcgen05(cudaStream_t s, const Plan &p, eb200_contract_desc &d, double beta_eff[2]) {
+    constexpr int64_t W = CPLX ? 2 : 1; // floats per element
     if (g_use_tcgen05 < 0) g_use_tcgen05 = env_int("EB200_USE_TCGEN05", 1);
     const int mode = option(OPT_TCGEN05_GENERIC);
     if (!g_use_tcgen05 || !mode || d.force_kernel != 0 || d.split_k > 1 || p.swapped) return 0;
-    if (p.m.n < 1 || p.n.n < 1 || p.k.n < 1 || p.m.n > 3 || p.n.n > 2 || p.b.n > 3) return 0;
+    if (p.m.n < 1 || p.n.n < 1 || p.k.n < 1 || p.m.n > 3 || p.n.n > (CPLX ? 2 : 3) || p.b.n > 3) return 0;
     if (p.b.n + p.m.n + p.k.n > EB200_MAX_RANK || p.b.n + p.n.n + p.k.n > EB200_MAX_RANK) return 0;
     if (!encode_tiled_fn()) return 0;
     for (int i = 0; i < MAXG; i++) // broadcast / one-sided sums (stride 0) and negative strides stay on the gather kernel
         if ((i < p.m.n && p.m.s[ROLE_A][i] <= 0) || (i < p.n.n && p.n.s[ROLE_B][i] <= 0) || (i < p.k.n && (p.k.s[ROLE_A][i] <= 0 || p.k.s[ROLE_B][i] <= 0)) ||
             (i < p.b.n && (p.b.s[ROLE_A][i] <= 0 || p.b.s[ROLE_B][i] <= 0)))
             return 0;
-    const int64_t M = p.m.tot, N = p.n.tot, K = p.k.tot, NBt = p.b.tot, Kp = (K + 1) & ~1LL;
-    if (2 * K >= (1LL << 31) || NBt >= (1LL << 31) || M >= (1LL << 40) || N >= (1LL << 40)) return 0;
+    const int64_t M = p.m.tot, N = p.n.tot, K = p.k.tot, NBt = p.b.tot, Kp = CPLX ? ((K + 1) & ~1LL) : ((K + 3) & ~3LL); // packed rows: multiples of 16 bytes
+    if (W * K >= (1LL << 31) || NBt >= (1LL << 31) || M >= (1LL << 40) || N >= (1LL << 40)) return 0;
     // enumeration order of the M and N groups: the index that pads least to a multiple of 32 goes innermost
     auto order = [](const Grp &g, int *ord) {
         int best = 0;
@@ -642,23 +645,23 @@ int try_run_c64_tcgen05(cudaStream_t s, const Plan &p, eb200_contract_desc &d, d
         a.en[i] = i < p.n.n ? (int32_t)p.n.ext[on[i]] : 1;
         a.ek[i] = 1;
         a.eb[i] = i < p.b.n ? (int32_t)p.b.ext[i] : 1;
-        a.gCm[i] = i < p.m.n ? 2 * p.m.s[ROLE_C][om[i]] : 0; // C strides in floats
-        a.gCn[i] = i < p.n.n ? 2 * p.n.s[ROLE_C][on[i]] : 0;
-        a.gCb[i] = i < p.b.n ? 2 * p.b.s[ROLE_C][i] : 0;
+        a.gCm[i] = i < p.m.n ? W * p.m.s[ROLE_C][om[i]] : 0; // C strides in floats
+        a.gCn[i] = i < p.n.n ? W * p.n.s[ROLE_C][on[i]] : 0;
+        a.gCb[i] = i < p.b.n ? W * p.b.s[ROLE_C][i] : 0;
         if ((i < p.m.n && p.m.ext[om[i]] >= (1LL << 31)) || (i < p.n.n && p.n.ext[on[i]] >= (1LL << 31))) return 0;
     }
-    a.ek[0] = (int32_t)(2 * K);
+    a.ek[0] = (int32_t)(W * K);
     a.mblk0 = (a.em[0] + 31) / 32; a.nblk0 = (a.en[0] + 31) / 32;
-    a.kstep0 = (int32_t)((2 * K + 31) / 32);
+    a.kstep0 = (int32_t)((W * K + 31) / 32);
     a.KT = a.kstep0;
     a.MB = (int64_t)a.mblk0 * a.em[1] * a.em[2];
     a.NB = (int64_t)a.nblk0 * a.en[1] * a.en[2];
-    const int64_t tm = (a.MB + 3) / 4, tn = (a.NB + 1) / 2; // 128 rows x 64 complex columns per tile
+    const int64_t NT = CPLX ? 64 : 128, tm = (a.MB + 3) / 4, tn = CPLX ? (a.NB + 1) / 2 : (a.NB + 3) / 4; // 128 rows x 64 complex (128 real) columns per tile
     if (tm * tn > 0x7fffffffLL || tm * tn * NBt > (1LL << 40)) return 0;
     if (mode != 2) {
-        const double waste = (double)(tm * 128) / (double)M * ((double)(tn * 64) / (double)N);
+        const double waste = (double)(tm * 128) / (double)M * ((double)(tn * NT) / (double)N);
         if (waste > 2.0) return 0;
-        if (tm * tn * NBt * 2 < sm_count()) return 0;      // too few tiles: the FMA-pipe kernel has split-K
+        if (tm * tn * NBt * (CPLX ? 2 : 4) < sm_count()) return 0;      // too few tiles: the FMA-pipe kernel has split-K
         if (std::min(M, N) < 128 || K < 16) return 0;       // packing would not pay
     }
     // ---- pack: A' [b][m composite][Kp] complex (alpha and conj folded in), Bc [b][n composite][K] complex, B' two planes of rows
@@ -674,38 +677,40 @@ int try_run_c64_tcgen05(cudaStream_t s, const Plan &p, eb200_contract_desc &d, d
         for (int i = 0; i < p.b.n; i++, r++) { dims[r] = p.b.ext[i]; ss[r] = p.b.s[role][i]; ds[r] = st; st *= p.b.ext[i]; }
         for (int i = 0; i < r; i++) perm[i] = i;
         const float zero[2] = {0.f, 0.f};
-        return eb200_cpermute((void *)s, r, dims, ss, perm, ds, al, (const float *)src, zero, (float *)dst, conj);
+        if constexpr (CPLX) return eb200_cpermute((void *)s, r, dims, ss, perm, ds, al, (const float *)src, zero, (float *)dst, conj);
+        else return eb200_spermute((void *)s, r, dims, ss, perm, ds, al, (const float *)src, zero, (float *)dst, 0);
     };
     const float alpha_c[2] = {(float)d.alpha[0], (float)d.alpha[1]}, one_c[2] = {1.f, 0.f};
-    const size_t bytesA = (size_t)NBt * M * Kp * 8, bytesBc = (size_t)NBt * N * K * 8, bytesBp = (size_t)NBt * 2 * N * Kp * 8;
-    if ((rc = scratch_alloc(&Ap, bytesA, s)) || (rc = scratch_alloc(&Bc, bytesBc, s)) || (rc = scratch_alloc(&Bp, bytesBp, s))) {
+    const size_t bytesA = (size_t)NBt * M * Kp * 4 * W, bytesBc = CPLX ? (size_t)NBt * N * K * 8 : 0, bytesBp = (size_t)NBt * W * N * Kp * 4 * W;
+    if ((rc = scratch_alloc(&Ap, bytesA, s)) || (CPLX && (rc = scratch_alloc(&Bc, bytesBc, s))) || (rc = scratch_alloc(&Bp, bytesBp, s))) {
         if (Ap) cudaFreeAsync(Ap, s);
         if (Bc) cudaFreeAsync(Bc, s);
         return -rc;
     }
     auto release = [&]() {
         cudaFreeAsync(Ap, s);
-        cudaFreeAsync(Bc, s);
+        if (Bc) cudaFreeAsync(Bc, s);
         cudaFreeAsync(Bp, s);
     };
     int64_t launches0 = launch_counter();
-    if ((rc = pack(p.m, om, ROLE_A, d.A.data, Ap, Kp, alpha_c, d.conj_a)) || (rc = pack(p.n, on, ROLE_B, d.B.data, Bc, K, one_c, d.conj_b)) ||
-        (rc = k_launch_c64_expand(s, Bc, Bp, NBt * N, N, K, Kp))) {
+    if ((rc = pack(p.m, om, ROLE_A, d.A.data, Ap, Kp, alpha_c, d.conj_a)) ||
+        (rc = CPLX ? pack(p.n, on, ROLE_B, d.B.data, Bc, K, one_c, d.conj_b) : pack(p.n, on, ROLE_B, d.B.data, Bp, Kp, one_c, 0)) ||
+        (CPLX && (rc = k_launch_c64_expand(s, Bc, Bp, NBt * N, N, K, Kp)))) {
         release();
         return -rc;
     }
     // ---- tensor maps over the packed operands (real view: rows of 2 Kp floats, 2 K of them valid — the rest is out of bounds = zero)
     Grp gk, gb, gm, gn;
     memset(&gk, 0, sizeof(gk)); memset(&gb, 0, sizeof(gb)); memset(&gm, 0, sizeof(gm)); memset(&gn, 0, sizeof(gn));
-    gk.n = 1; gk.ext[0] = 2 * K; gk.s[ROLE_A][0] = gk.s[ROLE_B][0] = 1;
-    int64_t st = 2 * Kp;
+    gk.n = 1; gk.ext[0] = W * K; gk.s[ROLE_A][0] = gk.s[ROLE_B][0] = 1;
+    int64_t st = W * Kp;
     gm.n = p.m.n;
     for (int i = 0; i < p.m.n; i++) { gm.ext[i] = a.em[i]; gm.s[ROLE_A][i] = st; st *= a.em[i]; }
     if (NBt > 1) { gb.n = 1; gb.ext[0] = NBt; gb.s[ROLE_A][0] = st; }
-    st = 2 * Kp;
-    gn.n = p.n.n + 1;
+    st = W * Kp;
+    gn.n = p.n.n + (CPLX ? 1 : 0);
     for (int i = 0; i < p.n.n; i++) { gn.ext[i] = a.en[i]; gn.s[ROLE_B][i] = st; st *= a.en[i]; }
-    gn.ext[p.n.n] = 2; gn.s[ROLE_B][p.n.n] = st; st *= 2; // the (real | imaginary)-output planes
+    if (CPLX) { gn.ext[p.n.n] = 2; gn.s[ROLE_B][p.n.n] = st; st *= 2; } // the (real | imaginary)-output planes
     if (NBt > 1) gb.s[ROLE_B][0] = st;
     CUtensorMap tmA, tmB;
     int32_t     dBn[3];
@@ -715,11 +720,11 @@ int try_run_c64_tcgen05(cudaStream_t s, const Plan &p, eb200_contract_desc &d, d
         return 0;
     }
     for (int i = 0; i < 3; i++) a.dBn[i] = i < p.n.n ? dBn[i] : -1;
-    a.dBc = dBn[p.n.n];
-    a.cplx = 1;
+    a.dBc = CPLX ? dBn[p.n.n] : -1;
+    a.cplx = CPLX ? 1 : 0;
     a.b_flat = 1;
     // the epilogue multiplies by a REAL beta per component; a beta with an imaginary part scales C beforehand
-    if (beta_eff[1] != 0.0) {
+    if (CPLX && beta_eff[1] != 0.0) {
         rc = launch_scale<float2>(s, p.t, d.C.data, beta_eff, d);
         if (rc) { release(); return -rc; }
         d.launches--; // counted below with the other launches of this call
@@ -727,7 +732,7 @@ int try_run_c64_tcgen05(cudaStream_t s, const Plan &p, eb200_contract_desc &d, d
     }
     a.tiles_m = (int)tm; a.tiles_n = (int)tn;
     a.batch = NBt;
-    a.M = M; a.N = 2 * N; a.K = 2 * K;
+    a.M = M; a.N = W * N; a.K = W * K;
     a.C = (float *)d.C.data;
     a.alpha = 1.f; a.beta = (float)beta_eff[0];
     a.c_n_unit = (p.n.s[ROLE_C][on[0]] == 1 && p.m.s[ROLE_C][om[0]] != 1) ? 1 : 0;
@@ -739,7 +744,7 @@ int try_run_c64_tcgen05(cudaStream_t s, const Plan &p, eb200_contract_desc &d, d
     d.launches += (int)(launch_counter() - launches0);
     d.split_k = 1;
     d.kernel_used = EB200_KF_TILE_TCGEN05;
-    set_last_kernel("gemm_tf32x3_tcgen05<c64>");
+    set_last_kernel(CPLX ? "gemm_tf32x3_tcgen05<c64>" : "gemm_tf32x3_tcgen05<packed>");
     return 1;
 }
 
@@ -779,7 +784,7 @@ template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract
     if constexpr (std::is_same_v<T, float2>) {
         if (!mma) {
             double be[2] = {beta_eff[0], beta_eff[1]};
-            int    r = try_run_c64_tcgen05(s, p, d, be);
+            int    r = try_run_packed_tcgen05<true>(s, p, d, be);
             if (r == 1) return EB200_OK;
             if (r < 0) return -r;
         }
@@ -790,6 +795,10 @@ template <typename T> int run_tile(cudaStream_t s, const Plan &p, eb200_contract
             if (r == 1) return EB200_OK;
             if (r < 0) return -r;
             r = try_run_tf32x3_generic(s, p, d, beta_eff);
+            if (r == 1) return EB200_OK;
+            if (r < 0) return -r;
+            double be[2] = {beta_eff[0], 0.0};
+            r = try_run_packed_tcgen05<false>(s, p, d, be);
             if (r == 1) return EB200_OK;
             if (r < 0) return -r;
         }

@@ -1163,3 +1163,21 @@ def test_c128_packed_default_routing(gpu, oracle):
     ref = np.zeros((20, 64, 48, 10), np.complex128)
     oracle.einsum_generic("mbej", ref, "jnfb", t, "mnef", g, 1.0, 0.0)
     assert_close(Wd.cpu().numpy(), ref, np.complex128)
+
+
+@pytest.mark.parametrize("case", TMA_GENERIC, ids=lambda c: f"{c[0]}<-{c[1]},{c[2]}")
+def test_f32_packed_tcgen05_patterns(tcgen05_generic_always, oracle, case):
+    """FP32 contractions whose own layout has no tensor map (strides that are not multiples of 16 bytes) are packed to K-major
+    matrices and run on the tcgen05 kernel as well; the aligned ones take it directly."""
+    from einsums_b200 import KF
+    gpu = tcgen05_generic_always
+    c_idx, a_idx, b_idx, ext = case
+    for (alpha, beta) in ((0.25, 1.0), (1.0, 0.0)):
+        d = run_case(gpu, oracle, c_idx, a_idx, b_idx, ext, np.float32, alpha, beta, seed=59)
+        assert d.kernel_used == KF["TILE_TCGEN05"], (d.kernel_used, gpu.last_kernel(), case)
+
+
+def test_f32_packed_default_routing(gpu, oracle):
+    """Odd extents (no 16-byte strides) at a size that fills the SMs: packed path without any knob."""
+    d = run_case(gpu, oracle, "mbej", "jnfb", "mnef", dict(m=13, b=67, e=61, j=11, n=3, f=45), np.float32, -0.5, 1.0, seed=13)
+    assert gpu.last_kernel() == "gemm_tf32x3_tcgen05<packed>", gpu.last_kernel()

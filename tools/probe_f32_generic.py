@@ -31,3 +31,5 @@ for (o, v) in ((40, 160), (60, 240)):
 o, v = 20, 200
 run("Wabef f32 o=20 v=200 (nmef order)", "abef", r(v, v, v, v), "nmef", r(o, o, v, v), "mnab", r(o, o, v, v), 0.25, 1.0, 2.0 * o**2 * v**4)
 run("batched 2 idx f32", "xyij", r(4, 6, 1024, 1024), "xyik", r(4, 6, 1024, 512), "yxkj", r(6, 4, 512, 1024), 1.0, 0.0, 2.0 * 24 * 1024 * 1024 * 512)
+o, v = 41, 163
+run(f"Wmbej f32 o={o} v={v} (odd extents: packed)", "mbej", r(o, v, v, o), "jnfb", r(o, o, v, v), "mnef", r(o, o, v, v), -0.5, 1.0, 2.0 * o**3 * v**3)
