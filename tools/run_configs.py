@@ -157,6 +157,43 @@ def cfg4(report, sizes=(64, 96, 128, 160), per_order=True):
     torch.cuda.empty_cache()
 
 
+def cfg_types(report):
+    """The other value types of the flat seam ({s,c,z}gemm and the generic contraction) on the tensor cores: FP32 / c64 on tcgen05 with
+    3xTF32 splitting (real flops against a third of the nominal dense TF32 rate, 1125 / 3 = 375 TFLOP/s), c128 on the FP64 tensor pipe."""
+    TF32X3 = 1125.0 / 3
+    o, v, n = 40, 160, 4096
+    def rt(dt, *s):
+        if dt.is_complex:
+            rd = torch.float32 if dt == torch.complex64 else torch.float64
+            return torch.complex(torch.rand(*s, dtype=rd, device="cuda") - 0.5, torch.rand(*s, dtype=rd, device="cuda") - 0.5)
+        return torch.rand(*s, dtype=dt, device="cuda") - 0.5
+    for dt, name, mul, tol in ((torch.float32, "f32", 2.0, 1e-5), (torch.complex64, "c64", 8.0, 1e-5), (torch.complex128, "c128", 8.0, 1e-12)):
+        peak, pname = (report.fp64, "frac_of_fp64_peak") if dt == torch.complex128 else (TF32X3, "frac_of_3xtf32_peak")
+        A, B, C = rt(dt, n, n), rt(dt, n, n), rt(dt, n, n)
+        C0 = C[:64].clone()
+        ops.contract("ij", C, "ik", A, "kj", B, 0.5, 1.0)
+        ref = C0.to(torch.complex128 if dt.is_complex else torch.float64) + 0.5 * (A[:64].to(torch.complex128 if dt.is_complex else torch.float64) @ B.to(torch.complex128 if dt.is_complex else torch.float64))
+        err = ((C[:64] - ref).abs().max() / ref.abs().max()).item()
+        assert err <= tol, (name, err)
+        ms = timeit(lambda: ops.contract("ij", C, "ik", A, "kj", B, 0.5, 1.0))
+        report.add({"config": f"types {name}", "op": f"gemm {n}^3 (ik,kj) beta=1", "ms": round(ms, 4), "real_tflops": round(mul * n**3 / ms / 1e9, 1),
+                    pname: round(mul * n**3 / ms / 1e9 / peak, 3), "kernel": ops.last_kernel(), "parity": err, "parity_tol": tol})
+        del A, B, C
+        t, g, W = rt(dt, o, o, v, v), rt(dt, o, o, v, v), rt(dt, o, v, v, o)
+        W0 = W[:1].clone()
+        d = ops.contract("mbej", W, "jnfb", t, "mnef", g, -0.5, 1.0)
+        wide = torch.complex128 if dt.is_complex else torch.float64
+        ref = W0.to(wide) - 0.5 * torch.einsum("jnfb,mnef->mbej", t.to(wide), g[:1].to(wide))
+        err = ((W[:1] - ref).abs().max() / ref.abs().max()).item()
+        assert err <= tol, (name, err)
+        ms = timeit(lambda: ops.contract("mbej", W, "jnfb", t, "mnef", g, -0.5, 1.0), 1, 3)
+        report.add({"config": f"types {name}", "op": f"Wmbej o={o} v={v} (generic)", "ms": round(ms, 4), "real_tflops": round(mul * o**3 * v**3 / ms / 1e9, 1),
+                    pname: round(mul * o**3 * v**3 / ms / 1e9 / peak, 3), "kernel": ops.last_kernel(), "launches": int(d.launches), "parity": err,
+                    "parity_tol": tol})
+        del t, g, W
+    torch.cuda.empty_cache()
+
+
 def run_all(which=("1", "2", "3", "4"), emit=None, wabef=True, permuted_k=True, per_order=True):
     hbm, hsrc, fp64, fsrc = peaks()
     report = Recorder(hbm, fp64, emit)
@@ -164,6 +201,11 @@ def run_all(which=("1", "2", "3", "4"), emit=None, wabef=True, permuted_k=True, 
     if "2" in which: cfg2(report, wabef)
     if "3" in which: cfg3(report, permuted_k)
     if "4" in which: cfg4(report, per_order=per_order)
+    if "T" in which:
+        try:
+            cfg_types(report)
+        except Exception as e:  # the headline line must still be printed
+            report.add({"config": "types", "error": repr(e)[:300]})
     return report.records, {"fp64_dmma_tflops": fp64, "fp64_source": fsrc, "hbm_copy_gbs": hbm, "hbm_source": hsrc}
 
 
