@@ -41,7 +41,7 @@ int                 sm_count();
 /// name of the tile kernel this thread launched last (eb200_last_kernel_name: tests and the benchmark report it)
 void        set_last_kernel(const char *name);
 /// tuning / testing knobs behind eb200_set_option
-enum { OPT_TMA = 0, OPT_TMA_GENERIC, OPT_TMA_TILE, OPT_TMA_DIST, OPT_PERMUTE_TMA, OPT_TCGEN05_GENERIC, OPT_SCRATCH_KEEP_MB, OPT_COUNT };
+enum { OPT_TMA = 0, OPT_TMA_GENERIC, OPT_TMA_TILE, OPT_TMA_DIST, OPT_PERMUTE_TMA, OPT_TCGEN05_GENERIC, OPT_SCRATCH_KEEP_MB, OPT_TCGEN05_PAIR, OPT_COUNT };
 int option(int which);
 /// stream-ordered scratch from the library's private memory pool (runtime.cu); release with cudaFreeAsync on the same stream
 int scratch_alloc(void **p, size_t bytes, cudaStream_t s);

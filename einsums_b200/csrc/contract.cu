@@ -351,27 +351,38 @@ int try_run_tf32x3(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const 
     if ((a_mn ? M : K) > lda || (b_mn ? N : K) > ldb) return 0;
     if (p.b.n && (sAb <= 0 || sBb <= 0 || (sAb & 3) || (sBb & 3) || NB >= (1LL << 31))) return 0; // shared (stride 0) operands: FMA kernel
     if (M * N * NB < 128 * 128 * 4) return 0; // tiny outputs: the FMA kernel (with split-K) is the better fit
+    // CTA pairs (cta_group::2, 256 x 128 tile pairs) when the 256-row granularity pads M by at most 5 % and there is work for every pair
+    const int64_t tm1 = (M + 127) / 128, tm2 = (M + 255) / 256, tn1 = (N + 127) / 128;
+    const int     pair_mode = option(OPT_TCGEN05_PAIR); // 0: never, 1: by the rule, 2: always
+    const bool    pair = pair_mode == 2 || (pair_mode == 1 && 2 * tm2 * 20 <= tm1 * 21 && tm2 * tn1 * NB >= sm_count() / 2);
     CUtensorMap tmA, tmB;
     if (!(a_mn ? make_operand_map_f32(&tmA, A, M, K, lda, NB, sAb, 32, 32, true) : make_operand_map_f32(&tmA, A, K, M, lda, NB, sAb, 32, 128))) return 0;
-    if (!(b_mn ? make_operand_map_f32(&tmB, B, N, K, ldb, NB, sBb, 32, 32, true) : make_operand_map_f32(&tmB, B, K, N, ldb, NB, sBb, 32, 128))) return 0;
+    if (!(b_mn ? make_operand_map_f32(&tmB, B, N, K, ldb, NB, sBb, 32, 32, true) : make_operand_map_f32(&tmB, B, K, N, ldb, NB, sBb, 32, pair ? 64 : 128)))
+        return 0;
     Tf32GemmArgs a;
     a.M = M; a.N = N; a.K = K;
     a.sCm = p.m.s[ROLE_C][0]; a.sCn = p.n.s[ROLE_C][0];
     a.C = (float *)d.C.data;
     a.alpha = (float)d.alpha[0]; a.beta = (float)beta_eff[0];
     a.batch = NB; a.sCb = sCb;
-    const int64_t tm = (M + 127) / 128, tn = (N + 127) / 128;
+    const int64_t tm = pair ? tm2 : tm1, tn = tn1; // PAIR: tiles_m counts 256-row tile pairs
     if (tm * tn > 0x7fffffffLL || tm * tn * NB > (1LL << 40)) return 0;
     a.tiles_m = (int)tm; a.tiles_n = (int)tn;
     constexpr size_t SMEM = 3 * 65536 + 4 * (32 * 33 * 4) + 1024 + 256;
     // persistent: one CTA per SM (the kernel needs all of shared memory and all 512 TMEM columns), each walking its share of the tiles
-    const unsigned grid = (unsigned)std::min<int64_t>(tm * tn * NB, sm_count());
-    int rc = k_launch_tf32x3(s, tmA, tmB, a, dim3(grid, 1, 1), SMEM, a_mn, b_mn);
+    int rc;
+    if (pair) {
+        const unsigned grid = 2u * (unsigned)std::min<int64_t>(tm * tn * NB, sm_count() / 2);
+        rc = k_launch_tf32x3_pair(s, tmA, tmB, a, dim3(grid, 1, 1), SMEM, a_mn, b_mn);
+    } else {
+        const unsigned grid = (unsigned)std::min<int64_t>(tm * tn * NB, sm_count());
+        rc = k_launch_tf32x3(s, tmA, tmB, a, dim3(grid, 1, 1), SMEM, a_mn, b_mn);
+    }
     if (rc) return -rc;
     d.launches++;
     d.split_k = 1;
     d.kernel_used = EB200_KF_TILE_TCGEN05;
-    set_last_kernel("gemm_tf32x3_tcgen05");
+    set_last_kernel(pair ? "gemm_tf32x3_tcgen05<pair>" : "gemm_tf32x3_tcgen05");
     return 1;
 }
 

@@ -75,19 +75,69 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-template <bool A_MN, bool B_MN, bool MULTI, bool GENERIC = false>
+// ---- CTA-pair (cta_group::2) variants: one thread of the LEADER CTA issues M = 256 MMAs over both CTAs' shared and tensor memory
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of all prior MMAs arrives on the barrier at the same shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
+// arrive on the barrier at this offset in the LEADER CTA (rank 0 of the cluster). Default (CTA-scope release) semantics, as CUTLASS's
+// ClusterBarrier::arrive(cta_id): a .release.cluster here costs a MEMBAR.ALL.GPU per arriving thread (17 % of the samples, ncu)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITC_LOOP:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAITC_DONE;\n"
+        "bra WAITC_LOOP;\n"
+        "WAITC_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// PAIR: two CTAs of a cluster share one 256 x 128 tile: each loads and splits its own 128 rows of A and its own 64-row HALF of B, the
+// leader's tcgen05.mma.cta_group::2 (M = 256) reads both halves of B, and each CTA ends up with its own 128 x 128 accumulators in its own
+// tensor memory (the epilogue is the single-CTA one). Per k-step a CTA then moves 24 KB (TMA) + 48 KB (splitters) + 72 KB (operand
+// reads) instead of 32 + 64 + 96 KB through shared memory, which is what bounds the single-CTA kernel; 4 stages of 48 KB.
+template <bool A_MN, bool B_MN, bool MULTI, bool GENERIC = false, bool PAIR = false>
 __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                              const __grid_constant__ Tf32GemmArgs args) {
-    constexpr int      BM = 128, BN = 128, BK = 32, STAGES = 3, NACC = 2;
-    constexpr uint32_t TILE_BYTES = BM * BK * 4;                 // 16 KB per operand tile
-    constexpr uint32_t RAW_BYTES = 2 * TILE_BYTES;               // A_raw | B_raw
+    static_assert(!(PAIR && GENERIC), "the pair kernel serves plain / batched products");
+    constexpr int      BM = 128, BN = 128, BK = 32, STAGES = PAIR ? 4 : 3, NACC = 2;
+    constexpr uint32_t TILE_BYTES = BM * BK * 4;                 // 16 KB per A tile
+    constexpr uint32_t TILE_B_BYTES = PAIR ? TILE_BYTES / 2 : TILE_BYTES; // PAIR: this CTA's 64-row half of the B tile
+    constexpr uint32_t RAW_BYTES = TILE_BYTES + TILE_B_BYTES;    // A_raw | B_raw
     constexpr uint32_t STAGE_BYTES = 2 * RAW_BYTES;              // + A_lo | B_lo
     constexpr uint32_t TMEM_COLS = 512;                          // two accumulator PAIRS (hi*hi | cross terms, 128 columns each): chunks and tiles alternate
     constexpr uint32_t PATCH_BYTES = 32 * 33 * 4;                // per epilogue warp: 32 x 32 transposition patch
     constexpr int      KCB = 16;                                 // k-blocks per accumulation chunk (512 k)
     // instruction descriptor: D=F32 (1<<4), A=TF32 (2<<7), B=TF32 (2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
-                               ((uint32_t)(BM >> 4) << 24);
+                               ((uint32_t)((PAIR ? 2 * BM : BM) >> 4) << 24);
 
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -106,34 +156,45 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
     const int nchunks = (nsteps + KCB - 1) / KCB;
     // static tile schedule: this CTA owns tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; tile_m runs fastest, so the CTAs that are
     // resident together share B panels (and, a little later, A panels) in L2
+    // PAIR: the schedule runs over CTA pairs and 256-row tile pairs (args.tiles_m counts those); rank r of the pair owns rows 128 r .. 128 r + 127
+    uint32_t rank = 0;
+    if constexpr (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int64_t sched_id = PAIR ? (blockIdx.x >> 1) : blockIdx.x, sched_n = PAIR ? (gridDim.x >> 1) : gridDim.x;
     const int64_t tiles_per_batch = (int64_t)args.tiles_m * args.tiles_n, total_tiles = tiles_per_batch * args.batch;
-    const int     my_tiles = (int)((total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const int     my_tiles = (int)((total_tiles - sched_id + sched_n - 1) / sched_n);
     auto decode = [&](int i, int &tile_m, int &tile_n, int &b) {
-        const int64_t t = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
+        const int64_t t = sched_id + (int64_t)i * sched_n;
         b = (int)(t / tiles_per_batch);
         const int in = (int)(t - (int64_t)b * tiles_per_batch);
         tile_n = in / args.tiles_m;
         tile_m = in - tile_n * args.tiles_m;
+        if constexpr (PAIR) tile_m = 2 * tile_m + (int)rank;
     };
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(full_raw(s), 1);
-            mbar_init(full_lo(s), 128);
+            mbar_init(full_lo(s), PAIR ? 8 : 128); // PAIR: the leader's barrier collects one arrival per splitter warp of both CTAs
             mbar_init(empty(s), 1);
         }
         for (int b = 0; b < NACC; b++) {
             mbar_init(chunk_full(b), 1);
-            mbar_init(chunk_drained(b), 128);
+            mbar_init(chunk_drained(b), PAIR ? 256 : 128);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) { // one warp of EACH CTA of the pair takes part
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); // the peer's barriers must be initialised before anything arrives on them
+    else __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -219,25 +280,28 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
 #pragma unroll
                         for (int q = 0; q < 4; q++) tma_load_3d(a_dst + q * 4096, &tmA, full_raw(s), tile_m * BM + 32 * q, it * BK, b);
                     } else tma_load_3d(a_dst, &tmA, full_raw(s), it * BK, tile_m * BM, b); // box {32 k, 128 m}
+                    const int n0 = tile_n * BN + (PAIR ? (int)rank * (BN / 2) : 0); // PAIR: this CTA's half of the tile's columns
                     if constexpr (B_MN) {
 #pragma unroll
-                        for (int q = 0; q < 4; q++) tma_load_3d(b_dst + q * 4096, &tmB, full_raw(s), tile_n * BN + 32 * q, it * BK, b);
-                    } else tma_load_3d(b_dst, &tmB, full_raw(s), it * BK, tile_n * BN, b);
+                        for (int q = 0; q < (PAIR ? 2 : 4); q++) tma_load_3d(b_dst + q * 4096, &tmB, full_raw(s), n0 + 32 * q, it * BK, b);
+                    } else tma_load_3d(b_dst, &tmB, full_raw(s), it * BK, n0, b); // box {32 k, 128 n} (PAIR: {32 k, 64 n})
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== tcgen05.mma issuer =====================
-        if (lane == 0) {
+        // ===================== tcgen05.mma issuer (PAIR: the leader CTA's only) =====================
+        if (lane == 0 && (!PAIR || rank == 0)) {
             int gs = 0, gc = 0; // global k-step and accumulation-chunk counters of this CTA
             for (int i = 0; i < my_tiles; i++) {
                 for (int it = 0; it < nsteps; it++, gs++) {
                     const int s = gs % STAGES, ab = gc & (NACC - 1);
                     if (it % KCB == 0 && gc >= NACC) { // the accumulator must have been drained (chunk gc - NACC)
-                        mbar_wait(chunk_drained(ab), ((gc / NACC) - 1) & 1);
+                        if constexpr (PAIR) mbar_wait_cluster(chunk_drained(ab), ((gc / NACC) - 1) & 1);
+                        else mbar_wait(chunk_drained(ab), ((gc / NACC) - 1) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
-                    mbar_wait(full_lo(s), (gs / STAGES) & 1); // splitters are done => the raw tile landed too
+                    if constexpr (PAIR) mbar_wait_cluster(full_lo(s), (gs / STAGES) & 1);
+                    else mbar_wait(full_lo(s), (gs / STAGES) & 1); // splitters are done => the raw tile landed too
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_base + s * STAGE_BYTES, b_hi = a_hi + TILE_BYTES, a_lo = a_hi + RAW_BYTES, b_lo = a_lo + TILE_BYTES;
                     // The hi*hi product and the two cross terms go to DIFFERENT accumulators: every accumulation step truncates the FP32
@@ -251,13 +315,21 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
                         const uint64_t dah = umma_smem_desc_sw128<A_MN>(a_hi + koa), dbh = umma_smem_desc_sw128<B_MN>(b_hi + kob);
                         const uint64_t dal = umma_smem_desc_sw128<A_MN>(a_lo + koa), dbl = umma_smem_desc_sw128<B_MN>(b_lo + kob);
                         const uint32_t first = ((it % KCB) | kk) == 0;
-                        umma_tf32(tacc_x, dal, dbh, IDESC, !first);
-                        umma_tf32(tacc_x, dah, dbl, IDESC, 1);
-                        umma_tf32(tacc_hi, dah, dbh, IDESC, !first);
+                        if constexpr (PAIR) {
+                            umma_tf32_pair(tacc_x, dal, dbh, IDESC, !first);
+                            umma_tf32_pair(tacc_x, dah, dbl, IDESC, 1);
+                            umma_tf32_pair(tacc_hi, dah, dbh, IDESC, !first);
+                        } else {
+                            umma_tf32(tacc_x, dal, dbh, IDESC, !first);
+                            umma_tf32(tacc_x, dah, dbl, IDESC, 1);
+                            umma_tf32(tacc_hi, dah, dbh, IDESC, !first);
+                        }
                     }
-                    umma_commit(empty(s));
+                    if constexpr (PAIR) umma_commit_pair(empty(s)); // frees the stage in both CTAs
+                    else umma_commit(empty(s));
                     if (it % KCB == KCB - 1 || it == nsteps - 1) {
-                        umma_commit(chunk_full(ab));
+                        if constexpr (PAIR) umma_commit_pair(chunk_full(ab));
+                        else umma_commit(chunk_full(ab));
                         gc++;
                     }
                 }
@@ -287,7 +359,10 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
                 lo[idx] = l;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy stores -> visible to the tensor core's async proxy
-            mbar_arrive(full_lo(s));
+            if constexpr (PAIR) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(full_lo(s));
+            } else mbar_arrive(full_lo(s));
         }
     } else {
         // ===================== epilogue warps (6..9): drain finished chunks, store finished tiles =====================
@@ -296,6 +371,10 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
         const int quad = warp & 3;                       // TMEM lane quadrant of this warp: warps 6,7,8,9 -> 2,3,0,1
         float    *patch = reinterpret_cast<float *>(smem_gen + STAGES * STAGE_BYTES) + (warp - 6) * (32 * 33);
         const float alpha = args.alpha, beta = args.beta;
+        auto arrive_drained = [&](int ab) {
+            if constexpr (PAIR) mbar_arrive_leader(chunk_drained(ab)); // the leader's issuer waits for both CTAs' epilogue warps
+            else mbar_arrive(chunk_drained(ab));
+        };
         auto tmem_ld32 = [&](uint32_t taddr, uint32_t(&r)[32]) {
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -423,7 +502,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
                         for (int j = 0; j < 32; j++) acc[c0 + j] += __uint_as_float(r[j]);
                     }
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(chunk_drained(ab));
+                    arrive_drained(ab);
                 }
 #pragma unroll
                 for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -554,7 +633,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
                         }
                         if (q == BN / 32 - 1) {
                             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                            mbar_arrive(chunk_drained(ab));
+                            arrive_drained(ab);
                         }
                         __syncwarp();
                         if (n < args.N) {
@@ -581,7 +660,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
                         tmem_ld32(taddr + 128u, x);
                         if (c0 == BN - 32) {
                             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                            mbar_arrive(chunk_drained(ab));
+                            arrive_drained(ab);
                         }
                         float v[32];
 #pragma unroll
@@ -615,7 +694,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
                         for (int j = 0; j < 32; j++) acc[c0 + j] += __uint_as_float(r[j]);
                     }
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(chunk_drained(ab));
+                    arrive_drained(ab);
                 }
 #pragma unroll
                 for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -628,10 +707,14 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
-    __syncthreads();
+    if constexpr (PAIR) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        cluster_sync_all(); // neither CTA may leave (or free tensor memory) while the other still arrives on its barriers
+    } else __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
 }
 

@@ -25,6 +25,42 @@ int k_launch_tf32x3(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &t
     EB_POST_LAUNCH("gemm_tf32x3_tcgen05");
     return EB200_OK;
 }
+// CTA-pair variant: clusters of two CTAs (cta_group::2), grid = an even number of CTAs
+int k_launch_tf32x3_pair(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB, const Tf32GemmArgs &a, dim3 grid, size_t smem, bool a_mn, bool b_mn) {
+    const bool multi = a.K > 512;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(320, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+#define EB_TF32_PAIR1(AM, BM_, MU)                                              \
+    {                                                                           \
+        auto kern = gemm_tf32x3_tcgen05<AM, BM_, MU, false, true>;              \
+        int  rc = set_smem_attr(kern, smem);                                    \
+        if (rc) return rc;                                                      \
+        EB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, a));                   \
+    }
+#define EB_TF32_PAIR(AM, BM_)                                                   \
+    {                                                                           \
+        if (multi) EB_TF32_PAIR1(AM, BM_, true) else EB_TF32_PAIR1(AM, BM_, false) \
+    }
+    if (a_mn && b_mn) EB_TF32_PAIR(true, true)
+    else if (a_mn && !b_mn) EB_TF32_PAIR(true, false)
+    else if (!a_mn && b_mn) EB_TF32_PAIR(false, true)
+    else EB_TF32_PAIR(false, false)
+#undef EB_TF32_PAIR
+#undef EB_TF32_PAIR1
+    EB_POST_LAUNCH("gemm_tf32x3_tcgen05<pair>");
+    return EB200_OK;
+}
 int k_launch_tf32x3_generic(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB, const Tf32GemmArgs &a, dim3 grid, size_t smem, bool a_mn, bool b_mn) {
 #define EB_TF32_GEN(AM, BM_)                                                    \
     {                                                                           \

@@ -26,6 +26,8 @@ int k_launch_tma_z(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tm
                    bool bk);                                                                     // k_tile_tma.cu
 int k_launch_tf32x3(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB, const Tf32GemmArgs &a, dim3 grid, size_t smem, bool a_mn,
                     bool b_mn); // k_tile_tf32.cu
+int k_launch_tf32x3_pair(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB, const Tf32GemmArgs &a, dim3 grid, size_t smem, bool a_mn,
+                         bool b_mn); // k_tile_tf32.cu
 int k_launch_tf32x3_generic(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB, const Tf32GemmArgs &a, dim3 grid, size_t smem,
                             bool a_mn, bool b_mn); // k_tile_tf32.cu
 int k_launch_c64_expand(cudaStream_t s, const void *Bc, void *Bp, int64_t rows, int64_t N, int64_t K, int64_t Kp); // k_tile_tf32.cu

@@ -67,13 +67,14 @@ struct Options {
         v[OPT_PERMUTE_TMA] = env("EB200_PERMUTE_TMA", 1);
         v[OPT_TCGEN05_GENERIC] = env("EB200_TCGEN05_GENERIC", 1);
         v[OPT_SCRATCH_KEEP_MB] = env("EB200_SCRATCH_KEEP_MB", 4096);
+        v[OPT_TCGEN05_PAIR] = env("EB200_TCGEN05_PAIR", 1);
     }
 };
 Options &options() {
     static Options o;
     return o;
 }
-const char *const kOptionNames[OPT_COUNT] = {"tma", "tma_generic", "tma_tile", "tma_dist", "permute_tma", "tcgen05_generic", "scratch_keep_mb"};
+const char *const kOptionNames[OPT_COUNT] = {"tma", "tma_generic", "tma_tile", "tma_dist", "permute_tma", "tcgen05_generic", "scratch_keep_mb", "tcgen05_pair"};
 thread_local const char *t_last_kernel = "";
 } // namespace
 int  option(int which) { return options().v[which].load(std::memory_order_relaxed); }

@@ -319,6 +319,8 @@ const char *eb200_last_kernel_name(void);
  *   "permute_tma"  1 | 0: TMA-staged FP64 plane transpose whenever the layout has a tensor map / never (register-staged kernels)
  *   "tcgen05_generic" 1 | 0 | 2: multi-index FP32 contractions on the tcgen05 kernel by the padding / fill rules / never / whenever legal
  *                  (default from EB200_TCGEN05_GENERIC)
+ *   "tcgen05_pair" 1 | 0 | 2: plain / batched FP32 products on CTA pairs (cta_group::2, 256 x 128 tile pairs) when M pads by <= 5 % and
+ *                  every pair has work / never / always (default from EB200_TCGEN05_PAIR)
  *   "scratch_keep_mb" n: freed scratch (split-K partials, packed complex operands, widened copies) the library's PRIVATE memory pool
  *                  keeps cached across synchronisations, in MB (default 4096, EB200_SCRATCH_KEEP_MB); the rest goes back to the driver */
 int eb200_set_option(const char *name, int value);

@@ -511,8 +511,16 @@ def test_gemm_strided_batched_and_copy_strided(gpu, oracle):
     assert np.array_equal(dst.cpu().numpy(), H)
 
 
+@pytest.fixture(params=[0, 2], ids=["single", "pair"])
+def tcgen05_pair_mode(request, gpu):
+    """Run a tcgen05 test on the single-CTA kernel and on CTA pairs (cta_group::2, 256 x 128 tile pairs) regardless of the size rule."""
+    gpu.set_option("tcgen05_pair", request.param)
+    yield request.param
+    gpu.set_option("tcgen05_pair", 1)
+
+
 @pytest.mark.parametrize("shape", [(256, 256, 64), (300, 260, 100), (1000, 520, 260), (513, 384, 768), (128, 1024, 36)])
-def test_sgemm_tcgen05_3xtf32(gpu, oracle, shape):
+def test_sgemm_tcgen05_3xtf32(gpu, oracle, shape, tcgen05_pair_mode):
     """FP32 plain GEMM with both operands K-major takes the tcgen05/TMEM kernel (3xTF32 split accumulation). 1e-5 relative against a
     float64 reference; ragged M/N/K edges (TMA zero fill), alpha/beta, transposed C."""
     from einsums_b200 import KF
@@ -540,7 +548,7 @@ def test_sgemm_tcgen05_3xtf32(gpu, oracle, shape):
 
 
 @pytest.mark.parametrize("a_idx,b_idx", [("ik", "jk"), ("ki", "jk"), ("ik", "kj"), ("ki", "kj")])
-def test_sgemm_tcgen05_layouts(gpu, a_idx, b_idx):
+def test_sgemm_tcgen05_layouts(gpu, a_idx, b_idx, tcgen05_pair_mode):
     """All four operand layouts of the tcgen05 kernel: K-major tiles (one TMA box, descriptor advance inside the swizzle row) and
     MN-major tiles (four 32x32 boxes, descriptor advance by 8-row atoms), incl. the FP32 Wabef pattern (both MN-major)."""
     from einsums_b200 import KF
@@ -565,7 +573,7 @@ def test_sgemm_tcgen05_layouts(gpu, a_idx, b_idx):
     assert rel_err(Wd.cpu().numpy().astype(np.float64), refW) <= 1e-5
 
 
-def test_sgemm_tcgen05_persistent_and_batched(gpu):
+def test_sgemm_tcgen05_persistent_and_batched(gpu, tcgen05_pair_mode):
     """The persistent tile loop (more tiles than SMs, so every CTA walks several tiles and the accumulators rotate) and the batched form
     (one batch index carried by all three tensors: 3-D tensor maps), against float64 matmul; 1e-5 relative (3xTF32 with truncated hi)."""
     from einsums_b200 import KF
@@ -578,6 +586,7 @@ def test_sgemm_tcgen05_persistent_and_batched(gpu):
     Cd = C0.clone()
     d = gpu.contract("ij", Cd, "ik", A, "jk", B, 0.5, 2.0)
     assert d.kernel_used == KF["TILE_TCGEN05"], d.kernel_used
+    assert gpu.last_kernel() == ("gemm_tf32x3_tcgen05<pair>" if tcgen05_pair_mode else "gemm_tf32x3_tcgen05"), gpu.last_kernel()
     ref = 0.5 * (A.double() @ B.double().T) + 2.0 * C0.double()
     assert ((Cd.double() - ref).abs().max() / ref.abs().max()).item() <= 1e-5
     # same-sign data: the truncation of hi and lo is a one-sided error; it must stay inside the tolerance
