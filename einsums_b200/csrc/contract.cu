@@ -590,9 +590,15 @@ int try_run_tf32x3_generic(cudaStream_t s, const Plan &p, eb200_contract_desc &d
     // of 2.5 is still a clear win
     const double waste = (double)a.MB * 32 / (double)p.m.tot * ((double)a.NB * 32 / (double)p.n.tot) * ((double)KT * 32 / (double)p.k.tot);
     if (waste > 2.5 && mode != 2) return 0;
-    const int64_t tm = (a.MB + 3) / 4, tn = (a.NB + 3) / 4;
+    int64_t       tm = (a.MB + 3) / 4;
+    const int64_t tn = (a.NB + 3) / 4;
     if (tm * tn > 0x7fffffffLL || tm * tn * p.b.tot > (1LL << 40)) return 0;
     if (tm * tn * p.b.tot * 4 < sm_count() && mode != 2) return 0; // too few tiles to fill the machine: the FMA kernel has split-K
+    // CTA pairs (256-row tile pairs) by the rule of the plain kernel
+    const int64_t tm2 = (a.MB + 7) / 8;
+    const int     pair_mode = option(OPT_TCGEN05_PAIR);
+    const bool    pair = pair_mode == 2 || (pair_mode == 1 && 2 * tm2 * 20 <= tm * 21 && tm2 * tn * p.b.tot >= sm_count() / 2);
+    if (pair) tm = tm2;
     a.tiles_m = (int)tm; a.tiles_n = (int)tn;
     a.batch = p.b.tot;
     a.M = p.m.tot; a.N = p.n.tot; a.K = p.k.tot;
@@ -600,13 +606,13 @@ int try_run_tf32x3_generic(cudaStream_t s, const Plan &p, eb200_contract_desc &d
     a.alpha = (float)d.alpha[0]; a.beta = (float)beta_eff[0];
     a.c_n_unit = (p.n.n > 0 && p.n.s[ROLE_C][0] == 1) ? 1 : 0;
     constexpr size_t SMEM = 3 * 65536 + 4 * (32 * 33 * 4) + 1024 + 256 + 2048;
-    const unsigned   grid = (unsigned)std::min<int64_t>(tm * tn * p.b.tot, sm_count());
-    int rc = k_launch_tf32x3_generic(s, tmA, tmB, a, dim3(grid, 1, 1), SMEM, !ak, !bk);
+    const unsigned   grid = pair ? 2u * (unsigned)std::min<int64_t>(tm * tn * p.b.tot, sm_count() / 2) : (unsigned)std::min<int64_t>(tm * tn * p.b.tot, sm_count());
+    int rc = k_launch_tf32x3_generic(s, tmA, tmB, a, dim3(grid, 1, 1), SMEM, !ak, !bk, pair);
     if (rc) return -rc;
     d.launches++;
     d.split_k = 1;
     d.kernel_used = EB200_KF_TILE_TCGEN05;
-    set_last_kernel("gemm_tf32x3_tcgen05<generic>");
+    set_last_kernel(pair ? "gemm_tf32x3_tcgen05<generic,pair>" : "gemm_tf32x3_tcgen05<generic>");
     return 1;
 }
 
@@ -741,15 +747,18 @@ template <bool CPLX> int try_run_packed_tcgen05(cudaStream_t s, const Plan &p, e
         d.launches--; // counted below with the other launches of this call
         beta_eff[0] = 1.0; beta_eff[1] = 0.0;
     }
-    a.tiles_m = (int)tm; a.tiles_n = (int)tn;
+    const int64_t tm2 = (a.MB + 7) / 8;
+    const int     pair_mode = option(OPT_TCGEN05_PAIR);
+    const bool    pair = pair_mode == 2 || (pair_mode == 1 && 2 * tm2 * 20 <= tm * 21 && tm2 * tn * NBt >= sm_count() / 2);
+    a.tiles_m = (int)(pair ? tm2 : tm); a.tiles_n = (int)tn;
     a.batch = NBt;
     a.M = M; a.N = W * N; a.K = W * K;
     a.C = (float *)d.C.data;
     a.alpha = 1.f; a.beta = (float)beta_eff[0];
     a.c_n_unit = (p.n.s[ROLE_C][on[0]] == 1 && p.m.s[ROLE_C][om[0]] != 1) ? 1 : 0;
     constexpr size_t SMEM = 3 * 65536 + 4 * (32 * 33 * 4) + 1024 + 256 + 2048;
-    const unsigned   grid = (unsigned)std::min<int64_t>(tm * tn * NBt, sm_count());
-    rc = k_launch_tf32x3_generic(s, tmA, tmB, a, dim3(grid, 1, 1), SMEM, false, false);
+    const unsigned   grid = pair ? 2u * (unsigned)std::min<int64_t>(tm2 * tn * NBt, sm_count() / 2) : (unsigned)std::min<int64_t>(tm * tn * NBt, sm_count());
+    rc = k_launch_tf32x3_generic(s, tmA, tmB, a, dim3(grid, 1, 1), SMEM, false, false, pair);
     release();
     if (rc) return -rc;
     d.launches += (int)(launch_counter() - launches0);

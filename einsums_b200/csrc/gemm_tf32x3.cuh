@@ -126,7 +126,6 @@ __device__ __forceinline__ void cluster_sync_all() {
 template <bool A_MN, bool B_MN, bool MULTI, bool GENERIC = false, bool PAIR = false>
 __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                              const __grid_constant__ Tf32GemmArgs args) {
-    static_assert(!(PAIR && GENERIC), "the pair kernel serves plain / batched products");
     constexpr int      BM = 128, BN = 128, BK = 32, STAGES = PAIR ? 4 : 3, NACC = 2;
     constexpr uint32_t TILE_BYTES = BM * BK * 4;                 // 16 KB per A tile
     constexpr uint32_t TILE_B_BYTES = PAIR ? TILE_BYTES / 2 : TILE_BYTES; // PAIR: this CTA's 64-row half of the B tile
@@ -205,15 +204,19 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
             // lanes 0..3 own the four 32-row M blocks of the tile, lanes 4..7 the four N blocks: per tile each lane decodes its block into
             // tensor-map coordinates, per k-step it adds the K coordinates and issues its box (one SIMT pass per step); lane 0 alone polls
             // the empty barrier and posts the transaction bytes
-            const bool is_a = lane < 4;
-            const int  blk = lane & 3;
+            // PAIR: lanes 4..5 own this CTA's TWO N blocks (its half of the tile's columns; complex mode: rank 0 = the real-output plane,
+            // rank 1 = the imaginary-output plane of the same 64 complex columns)
+            constexpr int NLANES = PAIR ? 6 : 8;
+            const bool    is_a = lane < 4;
+            const int     blk = lane & 3;
             int        gs = 0;
             for (int i = 0; i < my_tiles; i++) {
                 int tile_m, tile_n, b;
                 decode(i, tile_m, tile_n, b);
                 int c0[5] = {0, 0, 0, 0, 0};
-                if (lane < 8) {
-                    const int64_t  cb = is_a ? (int64_t)tile_m * 4 + blk : (args.cplx ? (int64_t)tile_n * 2 + (blk & 1) : (int64_t)tile_n * 4 + blk);
+                if (lane < NLANES) {
+                    const int64_t  cb = is_a ? (int64_t)tile_m * 4 + blk
+                                            : (args.cplx ? (int64_t)tile_n * 2 + (blk & 1) : (int64_t)tile_n * 4 + (PAIR ? 2 * (int)rank : 0) + blk);
                     const int32_t *ext = is_a ? args.em : args.en, *dt = is_a ? args.dAm : args.dBn, *db = is_a ? args.dAb : args.dBb;
                     const int      blk0n = is_a ? args.mblk0 : args.nblk0;
                     int            blk0 = blk0n, i1 = 0, i2 = 0; // out of range: an inner coordinate past the extent zero-fills the whole box
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
                     }
                     if (args.cplx && !is_a) {
 #pragma unroll
-                        for (int d = 0; d < 5; d++) c0[d] += (args.dBc == d ? (blk >> 1) : 0);
+                        for (int d = 0; d < 5; d++) c0[d] += (args.dBc == d ? (PAIR ? (int)rank : (blk >> 1)) : 0);
                     }
                 }
                 const int kd0 = is_a ? args.dAk[0] : args.dBk[0], kd1 = is_a ? args.dAk[1] : args.dBk[1], kd2 = is_a ? args.dAk[2] : args.dBk[2];
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
                         mbar_expect_tx(full_raw(s), RAW_BYTES);
                     }
                     __syncwarp();
-                    if (lane < 8) {
+                    if (lane < NLANES) {
                         int c[5];
 #pragma unroll
                         for (int d = 0; d < 5; d++) c[d] = c0[d] + (kd0 == d ? 32 * s0 : 0) + (kd1 == d ? k1 : 0) + (kd2 == d ? k2 : 0);

@@ -61,20 +61,41 @@ int k_launch_tf32x3_pair(cudaStream_t s, const CUtensorMap &tmA, const CUtensorM
     EB_POST_LAUNCH("gemm_tf32x3_tcgen05<pair>");
     return EB200_OK;
 }
-int k_launch_tf32x3_generic(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB, const Tf32GemmArgs &a, dim3 grid, size_t smem, bool a_mn, bool b_mn) {
+int k_launch_tf32x3_generic(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB, const Tf32GemmArgs &a, dim3 grid, size_t smem, bool a_mn, bool b_mn,
+                            bool pair) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(320, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
 #define EB_TF32_GEN(AM, BM_)                                                    \
     {                                                                           \
-        auto kern = gemm_tf32x3_tcgen05<AM, BM_, true, true>;                   \
-        int  rc = set_smem_attr(kern, smem);                                    \
-        if (rc) return rc;                                                      \
-        kern<<<grid, 320, smem, s>>>(tmA, tmB, a);                              \
+        if (pair) {                                                             \
+            auto kern = gemm_tf32x3_tcgen05<AM, BM_, true, true, true>;         \
+            int  rc = set_smem_attr(kern, smem);                                \
+            if (rc) return rc;                                                  \
+            EB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, a));               \
+        } else {                                                                \
+            auto kern = gemm_tf32x3_tcgen05<AM, BM_, true, true>;               \
+            int  rc = set_smem_attr(kern, smem);                                \
+            if (rc) return rc;                                                  \
+            kern<<<grid, 320, smem, s>>>(tmA, tmB, a);                          \
+        }                                                                       \
     }
     if (a_mn && b_mn) EB_TF32_GEN(true, true)
     else if (a_mn && !b_mn) EB_TF32_GEN(true, false)
     else if (!a_mn && b_mn) EB_TF32_GEN(false, true)
     else EB_TF32_GEN(false, false)
 #undef EB_TF32_GEN
-    EB_POST_LAUNCH("gemm_tf32x3_tcgen05<generic>");
+    EB_POST_LAUNCH(pair ? "gemm_tf32x3_tcgen05<generic,pair>" : "gemm_tf32x3_tcgen05<generic>");
     return EB200_OK;
 }
 

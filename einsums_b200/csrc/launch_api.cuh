@@ -29,7 +29,7 @@ int k_launch_tf32x3(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &t
 int k_launch_tf32x3_pair(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB, const Tf32GemmArgs &a, dim3 grid, size_t smem, bool a_mn,
                          bool b_mn); // k_tile_tf32.cu
 int k_launch_tf32x3_generic(cudaStream_t s, const CUtensorMap &tmA, const CUtensorMap &tmB, const Tf32GemmArgs &a, dim3 grid, size_t smem,
-                            bool a_mn, bool b_mn); // k_tile_tf32.cu
+                            bool a_mn, bool b_mn, bool pair); // k_tile_tf32.cu
 int k_launch_c64_expand(cudaStream_t s, const void *Bc, void *Bp, int64_t rows, int64_t N, int64_t K, int64_t Kp); // k_tile_tf32.cu
 int k_launch_reduce(int dtype, cudaStream_t s, bool row, ReduceArgs &a, dim3 grid);              // k_reduce_{real,cplx}.cu
 int k_launch_reduce_real(int dtype, cudaStream_t s, bool row, ReduceArgs &a, dim3 grid);

@@ -1048,7 +1048,7 @@ TCGEN05_GENERIC = [
 
 
 @pytest.mark.parametrize("case", TCGEN05_GENERIC, ids=lambda c: f"{c[0]}<-{c[1]},{c[2]}")
-def test_tcgen05_generic_patterns(tcgen05_generic_always, oracle, case):
+def test_tcgen05_generic_patterns(tcgen05_generic_always, oracle, case, tcgen05_pair_mode):
     """The index patterns of the FP64 multi-index TMA kernel, in FP32, against the oracle (1e-5: 3xTF32 keeps FP32 accuracy)."""
     from einsums_b200 import KF
     gpu = tcgen05_generic_always
@@ -1057,7 +1057,7 @@ def test_tcgen05_generic_patterns(tcgen05_generic_always, oracle, case):
         d = run_case(gpu, oracle, c_idx, a_idx, b_idx, ext, np.float32, alpha, beta, seed=43)
         assert d.kernel_used == KF["TILE_TCGEN05"], (d.kernel_used, gpu.last_kernel(), case)
         if len(ext) > 3:
-            assert gpu.last_kernel() == "gemm_tf32x3_tcgen05<generic>", (gpu.last_kernel(), case)
+            assert gpu.last_kernel() == ("gemm_tf32x3_tcgen05<generic,pair>" if tcgen05_pair_mode else "gemm_tf32x3_tcgen05<generic>"), (gpu.last_kernel(), case)
 
 
 def test_tcgen05_generic_default_routing_and_long_k(gpu, oracle):
@@ -1066,14 +1066,14 @@ def test_tcgen05_generic_default_routing_and_long_k(gpu, oracle):
     from einsums_b200 import KF
     ext = dict(m=14, b=64, e=64, j=12, n=2, f=544)
     d = run_case(gpu, oracle, "mbej", "jnfb", "mnef", ext, np.float32, -0.5, 1.0, seed=7)
-    assert d.kernel_used == KF["TILE_TCGEN05"] and gpu.last_kernel() == "gemm_tf32x3_tcgen05<generic>", gpu.last_kernel()
+    assert d.kernel_used == KF["TILE_TCGEN05"] and gpu.last_kernel().startswith("gemm_tf32x3_tcgen05<generic"), gpu.last_kernel()
     d = run_case(gpu, oracle, "mbej", "jnfb", "mnef", dict(m=3, b=32, e=32, j=3, n=2, f=40), np.float32, -0.5, 1.0, seed=8)
     assert d.kernel_used == KF["TILE_SIMT"], gpu.last_kernel()
     rng = np.random.default_rng(9)
     t, g = rand(rng, (12, 2, 96, 64), np.float32), rand(rng, (14, 2, 64, 96), np.float32)
     Wd = torch.full((14, 64, 64, 12), float("nan"), dtype=torch.float32, device="cuda")
     gpu.contract("mbej", Wd, "jnfb", dev(t), "mnef", dev(g), 1.0, 0.0)
-    assert gpu.last_kernel() == "gemm_tf32x3_tcgen05<generic>"
+    assert gpu.last_kernel().startswith("gemm_tf32x3_tcgen05<generic")
     ref = np.zeros((14, 64, 64, 12), np.float32)
     oracle.einsum_generic("mbej", ref, "jnfb", t, "mnef", g, 1.0, 0.0)
     assert_close(Wd.cpu().numpy(), ref, np.float32)
@@ -1121,7 +1121,7 @@ C64_TCGEN05 = [
 
 
 @pytest.mark.parametrize("case", C64_TCGEN05, ids=lambda c: f"{c[0]}<-{c[1]},{c[2]}")
-def test_c64_tcgen05_patterns(tcgen05_generic_always, oracle, case):
+def test_c64_tcgen05_patterns(tcgen05_generic_always, oracle, case, tcgen05_pair_mode):
     from einsums_b200 import KF
     gpu = tcgen05_generic_always
     c_idx, a_idx, b_idx, ext = case
@@ -1175,7 +1175,7 @@ def test_c128_packed_default_routing(gpu, oracle):
 
 
 @pytest.mark.parametrize("case", TMA_GENERIC, ids=lambda c: f"{c[0]}<-{c[1]},{c[2]}")
-def test_f32_packed_tcgen05_patterns(tcgen05_generic_always, oracle, case):
+def test_f32_packed_tcgen05_patterns(tcgen05_generic_always, oracle, case, tcgen05_pair_mode):
     """FP32 contractions whose own layout has no tensor map (strides that are not multiples of 16 bytes) are packed to K-major
     matrices and run on the tcgen05 kernel as well; the aligned ones take it directly."""
     from einsums_b200 import KF

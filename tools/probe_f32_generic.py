@@ -3,6 +3,7 @@ import json, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from einsums_b200 import ops, KF_NAMES
 ops.init(0)
+if len(sys.argv) > 1: ops.set_option('tcgen05_pair', int(sys.argv[1]))
 
 def run(name, c, C, a, A, b, B, alpha, beta, flops):
     rec = {"op": name}
