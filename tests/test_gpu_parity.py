@@ -1190,3 +1190,31 @@ def test_f32_packed_default_routing(gpu, oracle):
     """Odd extents (no 16-byte strides) at a size that fills the SMs: packed path without any knob."""
     d = run_case(gpu, oracle, "mbej", "jnfb", "mnef", dict(m=13, b=67, e=61, j=11, n=3, f=45), np.float32, -0.5, 1.0, seed=13)
     assert gpu.last_kernel() == "gemm_tf32x3_tcgen05<packed>", gpu.last_kernel()
+
+
+def test_f64_packed_tma_generic(tma_generic_always, oracle):
+    """FP64 contractions without a tensor map (odd strides) or with a badly padding index order: operands packed to dense K-major form,
+    multi-index TMA kernel on the copies (C written in place through its own strides); against the oracle, incl. batch indices and split-K."""
+    gpu = tma_generic_always
+    cases = [("mbej", "jnfb", "mnef", dict(m=6, b=21, e=19, j=7, n=5, f=23)),
+             ("ij", "iknl", "jnkl", dict(i=70, j=50, k=4, l=19, n=3)),
+             ("abef", "nmef", "mnab", dict(a=9, b=35, e=10, f=33, m=5, n=3)),
+             ("bij", "bik", "bkj", dict(i=65, j=33, k=41, b=5)),
+             ("xyabcd", "xyakb", "ykxcd", dict(x=2, y=3, a=5, b=15, c=3, d=21, k=37))]
+    for c_idx, a_idx, b_idx, ext in cases:
+        for (alpha, beta) in ((0.25, 1.0), (1.0, 0.0)):
+            run_case(gpu, oracle, c_idx, a_idx, b_idx, ext, np.float64, alpha, beta, seed=61)
+            assert gpu.last_kernel() == "contract_tma_f64<packed>", (gpu.last_kernel(), c_idx, a_idx, b_idx)
+    gpu.set_option("tma_generic", 1)
+    # default routing: large odd-extent Wmbej takes the packed path, and agrees with the gather kernel
+    rng = np.random.default_rng(62)
+    o, v = 13, 79
+    t, g, W0 = rand(rng, (o, o, v, v)), rand(rng, (o, o, v, v)), rand(rng, (o, v, v, o))
+    Wp, Wg = dev(W0), dev(W0)
+    gpu.contract("mbej", Wp, "jnfb", dev(t), "mnef", dev(g), -0.5, 1.0)
+    assert gpu.last_kernel() == "contract_tma_f64<packed>", gpu.last_kernel()
+    gpu.set_option("tma_generic", 0)
+    gpu.contract("mbej", Wg, "jnfb", dev(t), "mnef", dev(g), -0.5, 1.0)
+    assert gpu.last_kernel() == "tile_mma_f64", gpu.last_kernel()
+    ref = W0 - 0.5 * np.einsum("jnfb,mnef->mbej", t, g)
+    assert rel_err(Wp.cpu().numpy(), ref) <= 1e-12 and rel_err(Wg.cpu().numpy(), ref) <= 1e-12

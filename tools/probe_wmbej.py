@@ -3,6 +3,7 @@ import sys, torch
 sys.path.insert(0, ".")
 from einsums_b200 import ops
 ops.init(0)
+if len(sys.argv) > 3: ops.set_option('tma_generic', int(sys.argv[3]))
 o, v = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (40, 160)
 t = torch.rand(o, o, v, v, dtype=torch.float64, device="cuda") - 0.5
 g = torch.rand(o, o, v, v, dtype=torch.float64, device="cuda") - 0.5
@@ -15,4 +16,4 @@ e0.record()
 for _ in range(3): d = fn()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3
-print(f"Wmbej o={o} v={v}: {ms:.3f} ms  {2.0*o**3*v**3/ms/1e9:.2f} TFLOP/s  kernel={d.kernel_used}")
+print(f"Wmbej o={o} v={v}: {ms:.3f} ms  {2.0*o**3*v**3/ms/1e9:.2f} TFLOP/s  kernel={ops.last_kernel()} launches={d.launches}")
