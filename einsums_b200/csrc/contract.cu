@@ -388,7 +388,7 @@ int try_run_tma_generic_packed(cudaStream_t s, const Plan &p, eb200_contract_des
     if ((rc = pack(m_src, p2.m, ROLE_A, d.A.data, Ap)) || (rc = pack(n_src, p2.n, ROLE_B, d.B.data, Bp))) {
         cudaFreeAsync(Ap, s);
         cudaFreeAsync(Bp, s);
-        return -rc;
+        return rc == EB200_ERR_UNSUPPORTED ? 0 : -rc;
     }
     const int packs = (int)(launch_counter() - launches0);
     eb200_contract_desc d2 = d;
@@ -587,7 +587,7 @@ int try_run_z_packed(cudaStream_t s, const Plan &p, eb200_contract_desc &d, cons
     const int64_t launches0 = launch_counter();
     if ((rc = copy(p.m, p.k, ROLE_A, d.A.data, Ap, true, d.alpha, zero, d.conj_a)) || (rc = copy(p.n, p.k, ROLE_B, d.B.data, Bp, true, one, zero, d.conj_b))) {
         release();
-        return -rc;
+        return rc == EB200_ERR_UNSUPPORTED ? 0 : -rc; // C is untouched: the gather kernel runs
     }
     for (int64_t b = 0; b < NBt; b++) {
         int r = launch_tma_z(s, (const double2 *)Ap + b * M * K, (const double2 *)Bp + b * N * K, (double2 *)Tp + b * M * N, M, N, K, K, 1, K, 1, N, 1, one, zero, 0, 0);
@@ -598,7 +598,7 @@ int try_run_z_packed(cudaStream_t s, const Plan &p, eb200_contract_desc &d, cons
     }
     rc = copy(p.m, p.n, ROLE_C, Tp, d.C.data, false, one, beta_eff, 0);
     release();
-    if (rc) return -rc;
+    if (rc) return rc == EB200_ERR_UNSUPPORTED ? 0 : -rc; // refused before any launch: C is untouched
     d.launches += (int)(launch_counter() - launches0);
     d.split_k = 1;
     set_last_kernel("gemm_tma_z<packed>");
@@ -810,7 +810,7 @@ template <bool CPLX> int try_run_packed_tcgen05(cudaStream_t s, const Plan &p, e
         (rc = CPLX ? pack(p.n, on, ROLE_B, d.B.data, Bc, K, one_c, d.conj_b) : pack(p.n, on, ROLE_B, d.B.data, Bp, Kp, one_c, 0)) ||
         (CPLX && (rc = k_launch_c64_expand(s, Bc, Bp, NBt * N, N, K, Kp)))) {
         release();
-        return -rc;
+        return rc == EB200_ERR_UNSUPPORTED ? 0 : -rc; // a layout the strided copy does not take: C is untouched, the gather kernel runs
     }
     // ---- tensor maps over the packed operands (real view: rows of 2 Kp floats, 2 K of them valid — the rest is out of bounds = zero)
     Grp gk, gb, gm, gn;

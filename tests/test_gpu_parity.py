@@ -1218,3 +1218,50 @@ def test_f64_packed_tma_generic(tma_generic_always, oracle):
     assert gpu.last_kernel() == "tile_mma_f64", gpu.last_kernel()
     ref = W0 - 0.5 * np.einsum("jnfb,mnef->mbej", t, g)
     assert rel_err(Wp.cpu().numpy(), ref) <= 1e-12 and rel_err(Wg.cpu().numpy(), ref) <= 1e-12
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.complex64, torch.float64, torch.complex128])
+def test_default_routing_fuzz_mid_sizes(gpu, dtype):
+    """Random tile-family contractions at sizes where the default rules pick the tensor-core routes (direct maps, packed operands, CTA
+    pairs, TTGT for c128) — no knobs set. Too large for the CPU oracle's loops, so the checker is torch.einsum in the next wider
+    precision on the device (FP32 / c64: 1e-5, FP64 / c128: 1e-12 relative to the result's largest magnitude)."""
+    wide = {torch.float32: torch.float64, torch.complex64: torch.complex128, torch.float64: torch.float64, torch.complex128: torch.complex128}[dtype]
+    tol = 1e-5 if dtype in (torch.float32, torch.complex64) else 1e-12
+    rng = np.random.default_rng({torch.float32: 1, torch.complex64: 2, torch.float64: 3, torch.complex128: 4}[dtype])
+    gen = torch.Generator(device="cuda").manual_seed(int(rng.integers(1 << 30)))
+    def rnd(shape):
+        rd = {torch.complex64: torch.float32, torch.complex128: torch.float64}.get(dtype, dtype)
+        x = torch.rand(*shape, dtype=rd, device="cuda", generator=gen) * 2 - 1
+        if dtype.is_complex:
+            x = torch.complex(x, torch.rand(*shape, dtype=rd, device="cuda", generator=gen) * 2 - 1)
+        return x
+    seen = set()
+    for n in range(14):
+        nm, nn, nk, nb = int(rng.integers(1, 3)), int(rng.integers(1, 3)), int(rng.integers(1, 3)), int(rng.integers(0, 2))
+        letters = list("abcdefgh")
+        m, nl, k, bt = letters[:nm], letters[nm:nm + nn], letters[nm + nn:nm + nn + nk], letters[nm + nn + nk:nm + nn + nk + nb]
+        def split(total, parts):   # extents whose product is about `total`, odd and even mixed
+            if parts == 1:
+                return [int(total)]
+            a = int(rng.choice([3, 4, 5, 7, 8, 12, 16]))
+            return [a, max(2, int(total // a))]
+        ext = {}
+        for grp, total in ((m, rng.choice([640, 900, 1333, 2048])), (nl, rng.choice([512, 777, 1100, 1536])), (k, rng.choice([64, 150, 333, 640]))):
+            for ch, e in zip(grp, split(total, len(grp))):
+                ext[ch] = e
+        for ch in bt:
+            ext[ch] = int(rng.choice([2, 3]))
+        c, a, b = m + nl + bt, m + k + bt, nl + k + bt
+        for lst in (c, a, b):
+            rng.shuffle(lst)
+        c_idx, a_idx, b_idx = "".join(c), "".join(a), "".join(b)
+        alpha, beta = [(1.0, 0.0), (0.5, 2.0), (-1.0, 1.0)][int(rng.integers(0, 3))]
+        A, B, C0 = rnd([ext[x] for x in a_idx]), rnd([ext[x] for x in b_idx]), rnd([ext[x] for x in c_idx])
+        Cd = C0.clone()
+        gpu.contract(c_idx, Cd, a_idx, A, b_idx, B, alpha, beta)
+        seen.add(gpu.last_kernel())
+        ref = beta * C0.to(wide) + alpha * torch.einsum(f"{a_idx},{b_idx}->{c_idx}", A.to(wide), B.to(wide))
+        err = ((Cd.to(wide) - ref).abs().max() / ref.abs().max()).item()
+        assert err <= tol, (c_idx, a_idx, b_idx, ext, gpu.last_kernel(), err)
+    print("kernels seen:", sorted(seen))
+    assert any(("tcgen05" in s_ or "tma" in s_) for s_ in seen), seen
