@@ -653,13 +653,55 @@ bool make_generic_map_f32(CUtensorMap *map, const float *base, const Grp &tgt, c
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// ---- C layouts the tile epilogue cannot write in memory order. The epilogue's lanes run along the INNER index of the M (or N) group; when
+// neither is unit-stride in C (Wmbej: W[m,b,e,j] has j innermost, an OUTER index of the M group), every 4-byte access of a warp falls into its own
+// 32-byte sector. With beta = 0 the L2 merges the partial stores (188 TFLOP/s on Wmbej FP32 o=40 v=160); with beta != 0 the old-C loads cost 8 x
+// their bytes and throttle the kernel (129). Then the tile kernel writes a dense temporary in GEMM order (lanes along m, unit stride) with
+// beta = 0, and one strided accumulate  C = beta C + T  (the permute kernels: both sides coalesced through shared-memory tiles) finishes: 192.
+struct DenseOut {
+    void   *T = nullptr;
+    int     n = 0;
+    int64_t ext[EB200_MAX_RANK], ts[EB200_MAX_RANK], cs[EB200_MAX_RANK];
+};
+// fills strides of the dense temporary into gCm / gCn / gCb (in FLOATS, w floats per element) and records the index list for the accumulate
+int dense_out_begin(cudaStream_t s, DenseOut &o, int w, const int32_t em[3], int nm, const int32_t en[3], int nn, const int32_t eb[3], int nb, int64_t gCm[3],
+                    int64_t gCn[3], int64_t gCb[3]) {
+    int64_t st = 1;
+    o.n = 0;
+    auto add = [&](const int32_t *e, int cnt, int64_t *g) {
+        for (int i = 0; i < cnt; i++) {
+            o.ext[o.n] = e[i];
+            o.cs[o.n] = g[i] / w; // the caller's C strides, back in elements
+            o.ts[o.n] = st;
+            g[i] = st * w;
+            st *= e[i];
+            o.n++;
+        }
+    };
+    add(em, nm, gCm);
+    add(en, nn, gCn);
+    add(eb, nb, gCb);
+    int rc = scratch_alloc(&o.T, (size_t)st * 4 * w, s);
+    return rc;
+}
+int dense_out_finish(cudaStream_t s, DenseOut &o, bool cplx, void *C, const double beta[2]) {
+    int perm[EB200_MAX_RANK];
+    for (int i = 0; i < o.n; i++) perm[i] = i;
+    const float one[2] = {1.f, 0.f}, be[2] = {(float)beta[0], (float)beta[1]};
+    int rc = cplx ? eb200_cpermute((void *)s, o.n, o.ext, o.ts, perm, o.cs, one, (const float *)o.T, be, (float *)C, 0)
+                  : eb200_spermute((void *)s, o.n, o.ext, o.ts, perm, o.cs, one, (const float *)o.T, be, (float *)C, 0);
+    cudaFreeAsync(o.T, s);
+    o.T = nullptr;
+    return rc;
+}
+
 int try_run_tf32x3_generic(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const double beta_eff[2]) {
     if (g_use_tcgen05 < 0) {
         const char *e = getenv("EB200_USE_TCGEN05");
         g_use_tcgen05 = e ? atoi(e) : 1;
     }
-    const int mode = option(OPT_TCGEN05_GENERIC); // 1: by the rules below; 0: never; 2: whenever a tensor map exists (tests)
-    if (!g_use_tcgen05 || !mode || d.force_kernel != 0 || d.split_k > 1 || p.swapped) return 0;
+    const int mode = option(OPT_TCGEN05_GENERIC); // 1: by the rules below; 0: never; 2: whenever a tensor map exists (tests); 3: packed operands preferred
+    if (!g_use_tcgen05 || !mode || mode == 3 || d.force_kernel != 0 || d.split_k > 1 || p.swapped) return 0;
     const float *A = (const float *)d.A.data, *B = (const float *)d.B.data;
     const bool   ak = p.a_kmajor != 0, bk = p.b_kmajor != 0;
     Tf32GemmArgs a;
@@ -701,10 +743,33 @@ int try_run_tf32x3_generic(cudaStream_t s, const Plan &p, eb200_contract_desc &d
     a.C = (float *)d.C.data;
     a.alpha = (float)d.alpha[0]; a.beta = (float)beta_eff[0];
     a.c_n_unit = (p.n.n > 0 && p.n.s[ROLE_C][0] == 1) ? 1 : 0;
+    DenseOut dense;
+    if (beta_eff[0] != 0.0 && !a.c_n_unit && p.m.s[ROLE_C][0] != 1 && (mode == 2 || (double)p.m.tot * (double)p.n.tot * (double)p.b.tot >= (double)(1 << 22))) {
+        int rc = dense_out_begin(s, dense, 1, a.em, p.m.n, a.en, p.n.n, a.eb, p.b.n, a.gCm, a.gCn, a.gCb);
+        if (rc == EB200_OK) {
+            a.C = (float *)dense.T;
+            a.beta = 0.f;
+        } else if (rc != EB200_ERR_OUT_OF_MEMORY) return -rc;
+        else // no room: write C directly (slower, still correct)
+            for (int i = 0; i < 3; i++) {
+                a.gCm[i] = i < p.m.n ? p.m.s[ROLE_C][i] : 0;
+                a.gCn[i] = i < p.n.n ? p.n.s[ROLE_C][i] : 0;
+                a.gCb[i] = i < p.b.n ? p.b.s[ROLE_C][i] : 0;
+            }
+    }
     constexpr size_t SMEM = 3 * 65536 + 4 * (32 * 33 * 4) + 1024 + 256 + 2048;
     const unsigned   grid = pair ? 2u * (unsigned)std::min<int64_t>(tm * tn * p.b.tot, sm_count() / 2) : (unsigned)std::min<int64_t>(tm * tn * p.b.tot, sm_count());
     int rc = k_launch_tf32x3_generic(s, tmA, tmB, a, dim3(grid, 1, 1), SMEM, !ak, !bk, pair);
-    if (rc) return -rc;
+    if (rc) {
+        if (dense.T) cudaFreeAsync(dense.T, s);
+        return -rc;
+    }
+    if (dense.T) {
+        const int64_t l0 = launch_counter();
+        rc = dense_out_finish(s, dense, false, d.C.data, beta_eff);
+        if (rc) return -rc;
+        d.launches += (int)(launch_counter() - l0);
+    }
     d.launches++;
     d.split_k = 1;
     d.kernel_used = EB200_KF_TILE_TCGEN05;
@@ -836,8 +901,24 @@ template <bool CPLX> int try_run_packed_tcgen05(cudaStream_t s, const Plan &p, e
     a.dBc = CPLX ? dBn[p.n.n] : -1;
     a.cplx = CPLX ? 1 : 0;
     a.b_flat = 1;
+    // C layouts the epilogue cannot write in memory order, beta != 0: dense temporary + one strided accumulate (see DenseOut); this also
+    // takes a complex beta as it is
+    a.c_n_unit = (p.n.s[ROLE_C][on[0]] == 1 && p.m.s[ROLE_C][om[0]] != 1) ? 1 : 0;
+    DenseOut dense;
+    if ((beta_eff[0] != 0.0 || beta_eff[1] != 0.0) && !a.c_n_unit && p.m.s[ROLE_C][om[0]] != 1 && (mode == 2 || (double)M * (double)N * (double)NBt >= (double)(1 << 22))) {
+        rc = dense_out_begin(s, dense, (int)W, a.em, p.m.n, a.en, p.n.n, a.eb, p.b.n, a.gCm, a.gCn, a.gCb);
+        if (rc != EB200_OK && rc != EB200_ERR_OUT_OF_MEMORY) { release(); return -rc; }
+        if (rc == EB200_ERR_OUT_OF_MEMORY) { // no room: write C directly
+            dense.T = nullptr;
+            for (int i = 0; i < 3; i++) {
+                a.gCm[i] = i < p.m.n ? W * p.m.s[ROLE_C][om[i]] : 0;
+                a.gCn[i] = i < p.n.n ? W * p.n.s[ROLE_C][on[i]] : 0;
+                a.gCb[i] = i < p.b.n ? W * p.b.s[ROLE_C][i] : 0;
+            }
+        }
+    }
     // the epilogue multiplies by a REAL beta per component; a beta with an imaginary part scales C beforehand
-    if (CPLX && beta_eff[1] != 0.0) {
+    if (!dense.T && CPLX && beta_eff[1] != 0.0) {
         rc = launch_scale<float2>(s, p.t, d.C.data, beta_eff, d);
         if (rc) { release(); return -rc; }
         d.launches--; // counted below with the other launches of this call
@@ -849,14 +930,18 @@ template <bool CPLX> int try_run_packed_tcgen05(cudaStream_t s, const Plan &p, e
     a.tiles_m = (int)(pair ? tm2 : tm); a.tiles_n = (int)tn;
     a.batch = NBt;
     a.M = M; a.N = W * N; a.K = W * K;
-    a.C = (float *)d.C.data;
-    a.alpha = 1.f; a.beta = (float)beta_eff[0];
-    a.c_n_unit = (p.n.s[ROLE_C][on[0]] == 1 && p.m.s[ROLE_C][om[0]] != 1) ? 1 : 0;
+    a.C = dense.T ? (float *)dense.T : (float *)d.C.data;
+    a.alpha = 1.f; a.beta = dense.T ? 0.f : (float)beta_eff[0];
+    if (dense.T) a.c_n_unit = 0; // the temporary is unit-stride along the inner M index
     constexpr size_t SMEM = 3 * 65536 + 4 * (32 * 33 * 4) + 1024 + 256 + 2048;
     const unsigned   grid = pair ? 2u * (unsigned)std::min<int64_t>(tm2 * tn * NBt, sm_count() / 2) : (unsigned)std::min<int64_t>(tm * tn * NBt, sm_count());
     rc = k_launch_tf32x3_generic(s, tmA, tmB, a, dim3(grid, 1, 1), SMEM, false, false, pair);
     release();
-    if (rc) return -rc;
+    if (rc) {
+        if (dense.T) cudaFreeAsync(dense.T, s);
+        return -rc;
+    }
+    if (dense.T && (rc = dense_out_finish(s, dense, CPLX, d.C.data, beta_eff))) return -rc;
     d.launches += (int)(launch_counter() - launches0);
     d.split_k = 1;
     d.kernel_used = EB200_KF_TILE_TCGEN05;
