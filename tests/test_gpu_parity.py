@@ -1265,3 +1265,28 @@ def test_default_routing_fuzz_mid_sizes(gpu, dtype):
         assert err <= tol, (c_idx, a_idx, b_idx, ext, gpu.last_kernel(), err)
     print("kernels seen:", sorted(seen))
     assert any(("tcgen05" in s_ or "tma" in s_) for s_ in seen), seen
+
+
+def test_sgemm_tcgen05_pair_stress_against_single(gpu):
+    """CTA pairs hand tiles between two SMs (remote mbarrier arrivals, multicast commits): the same products on the single-CTA kernel and on
+    pairs must agree BITWISE (same MMA sequence per 128 x 128 accumulator, same chunking), every element, over repeated launches and several
+    tile / k-step counts — a stale `lo` tile or an accumulator handed over early would show up here long before it shows up in a tolerance."""
+    torch.manual_seed(23)
+    for (m, n, k, a_idx, b_idx) in ((2048, 2048, 1024, "ik", "jk"), (4096, 1536, 4096 + 96, "ik", "kj"), (5000, 1100, 300, "ki", "jk")):
+        ext = dict(i=m, j=n, k=k)
+        A = torch.rand(*[ext[c] for c in a_idx], dtype=torch.float32, device="cuda") * 2 - 1
+        B = torch.rand(*[ext[c] for c in b_idx], dtype=torch.float32, device="cuda") * 2 - 1
+        C0 = torch.rand(m, n, dtype=torch.float32, device="cuda")
+        gpu.set_option("tcgen05_pair", 0)
+        Cs = C0.clone()
+        gpu.contract("ij", Cs, a_idx, A, b_idx, B, 0.5, 2.0)
+        assert gpu.last_kernel() == "gemm_tf32x3_tcgen05"
+        gpu.set_option("tcgen05_pair", 2)
+        try:
+            for rep in range(6):
+                Cp = C0.clone()
+                gpu.contract("ij", Cp, a_idx, A, b_idx, B, 0.5, 2.0)
+                assert gpu.last_kernel() == "gemm_tf32x3_tcgen05<pair>"
+                assert torch.equal(Cp, Cs), (m, n, k, rep, (Cp - Cs).abs().max().item())
+        finally:
+            gpu.set_option("tcgen05_pair", 1)

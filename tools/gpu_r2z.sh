@@ -1,13 +1,15 @@
 #!/bin/bash
-# final validation at N = 2: bench both arms the way the driver launches them, K-split GPU tests
-N=2
+# round-2 closing validation on one GPU: smoke, the whole GPU suite, both bench arms the way the driver runs them
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/r2z_bench_n$N.json 2> gpurun_out/r2z_bench_n$N.err; echo "bench rc=$?"
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2z_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/r2z_smoke.log | cut -c1-400
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2z_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2z_pytest.log
+python bench.py --impl reference > gpurun_out/r2z_bench_reference.json 2> gpurun_out/r2z_bench_reference.err; echo "ref rc=$?"
+( time python bench.py ) > gpurun_out/r2z_bench.json 2> gpurun_out/r2z_bench.err; echo "bench rc=$?"; tail -3 gpurun_out/r2z_bench.err
 python - <<PY
 import json
-for l in open("gpurun_out/r2z_bench_n2.json"):
+for l in open("gpurun_out/r2z_bench.json"):
     if l.startswith("{"):
-        d=json.loads(l); print("value", d["value"], "e2e", d["e2e"]["value"], "sharded", d.get("sharded",{}).get("tflops_total"), d.get("sharded",{}).get("parity_rel_err"), "ksplit", json.dumps(d.get("ksplit",{}))[:300])
+        d=json.loads(l); print("value", d["value"], "frac", d["roofline"]["frac"], "e2e", d["e2e"]["value"], "sharded", d["sharded"]["tflops_total"], "cpu", d["cpu_baseline"]["value"])
+        for r in d["configs"]["records"]:
+            r.pop("all", None); print(json.dumps(r)[:260])
 PY
-tail -3 gpurun_out/r2z_bench_n$N.err
-timeout 300 python -m pytest tests -m gpu -q -x -k "ksplit" 2>&1 | tail -3
