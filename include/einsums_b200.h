@@ -307,9 +307,13 @@ int eb200_contract_host_release(void);
  * descriptor, written to desc->kernel_used. Lets CPU tests pin the planner. */
 int eb200_contract_plan(eb200_contract_desc *desc);
 
-/* Name of the tile kernel the calling thread's last contraction launched ("gemm_tma_f64", "contract_tma_f64<128x64>",
- * "contract_tma_f64<80x80>", "tile_mma_f64", "gemm_tf32x3_tcgen05", "tile_simt"; "" before the first one). The
- * descriptor's kernel_used names the family; this names the kernel inside the family. */
+/* Name of the tile kernel the calling thread's last contraction launched ("" before the first one). The descriptor's kernel_used
+ * names the family; this names the kernel inside the family:
+ *   FP64   "gemm_tma_f64", "contract_tma_f64<128x64>", "contract_tma_f64<80x80>", "contract_tma_f64<packed>", "tile_mma_f64"
+ *   FP32   "gemm_tf32x3_tcgen05", "gemm_tf32x3_tcgen05<pair>", "gemm_tf32x3_tcgen05<generic>", "gemm_tf32x3_tcgen05<generic,pair>",
+ *          "gemm_tf32x3_tcgen05<packed>", "tile_simt"
+ *   c64    "gemm_tf32x3_tcgen05<c64>", "tile_simt"
+ *   c128   "gemm_tma_z", "gemm_tma_z<packed>", "tile_simt" */
 const char *eb200_last_kernel_name(void);
 /* Tuning / testing knobs, process-wide (defaults from EB200_USE_TMA, EB200_USE_TMA_GENERIC, EB200_TMA_TILE, EB200_TMA_DIST, EB200_PERMUTE_TMA):
  *   "tma"          1 | 0: use / avoid both TMA kernels (0 = cp.async gather kernel everywhere)
