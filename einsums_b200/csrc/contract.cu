@@ -327,7 +327,7 @@ int try_run_tma_generic_packed(cudaStream_t s, const Plan &p, eb200_contract_des
     // the two copies cost about 45 (1/M + 1/N) of the product's time; the TMA kernel is 1.24 x the gather kernel on such layouts
     if (use_generic != 2 && (std::min(M, N) < 768 || K < 64)) return 0;
     Plan p2 = p;
-    auto reorder = [](Grp &g, int role_packed, int64_t row_len) { // least padding to a multiple of 16 innermost; packed strides for the operand
+    auto reorder = [](Grp &g) { // least padding to a multiple of 16 innermost (all three roles' strides move together)
         int best = 0;
         double bw = 1e30;
         for (int i = 0; i < g.n; i++) {
@@ -344,13 +344,11 @@ int try_run_tma_generic_packed(cudaStream_t s, const Plan &p, eb200_contract_des
         put(best);
         for (int i = 0; i < o.n; i++)
             if (i != best) put(i);
-        (void)role_packed; (void)row_len;
         grp_finalize(g);
         return bw;
     };
-    Grp m_src = p.m, n_src = p.n; // source strides follow the same reordering
-    const double wm = reorder(p2.m, ROLE_A, Kp), wn = reorder(p2.n, ROLE_B, Kp);
-    m_src = p2.m; n_src = p2.n;
+    const double wm = reorder(p2.m), wn = reorder(p2.n);
+    const Grp m_src = p2.m, n_src = p2.n; // the ORIGINAL operand strides in the new order (before the packed strides go in)
     // the gather kernel runs odd-stride layouts at 72-75 % of the DMMA peak (no paired loads), the TMA kernel packed operands at 93 %
     if (use_generic != 2 && wm * wn * ((double)((K + 15) / 16 * 16) / (double)K) > 1.25) return 0;
     // packed strides
@@ -383,7 +381,6 @@ int try_run_tma_generic_packed(cudaStream_t s, const Plan &p, eb200_contract_des
         const double one = 1.0, zero = 0.0;
         return eb200_dpermute((void *)s, r, dims, ss, perm, ds, &one, (const double *)from, &zero, (double *)to, 0);
     };
-    // m_src / n_src carry the ORIGINAL operand strides in the new order (reorder() moved all three roles together)
     const int64_t launches0 = launch_counter();
     if ((rc = pack(m_src, p2.m, ROLE_A, d.A.data, Ap)) || (rc = pack(n_src, p2.n, ROLE_B, d.B.data, Bp))) {
         cudaFreeAsync(Ap, s);

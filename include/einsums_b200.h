@@ -321,8 +321,9 @@ const char *eb200_last_kernel_name(void);
  *   "tma_tile"     -1 | 0 | 1: automatic / 128x64 / 80x80 tiles in the multi-index TMA kernel
  *   "tma_dist"     0 | n: automatic / issue the loads of step t + n while step t is consumed (1 <= n < stages)
  *   "permute_tma"  1 | 0: TMA-staged FP64 plane transpose whenever the layout has a tensor map / never (register-staged kernels)
- *   "tcgen05_generic" 1 | 0 | 2: multi-index FP32 contractions on the tcgen05 kernel by the padding / fill rules / never / whenever legal
- *                  (default from EB200_TCGEN05_GENERIC)
+ *   "tcgen05_generic" 1 | 0 | 2 | 3: multi-index FP32 / c64 contractions on the tcgen05 kernel by the padding / fill rules / never /
+ *                  whenever legal (tests) / FP32 through packed operands even when tensor maps exist (A/B experiments);
+ *                  default from EB200_TCGEN05_GENERIC
  *   "tcgen05_pair" 1 | 0 | 2: plain / batched FP32 products on CTA pairs (cta_group::2, 256 x 128 tile pairs) when M pads by <= 5 % and
  *                  every pair has work / never / always (default from EB200_TCGEN05_PAIR)
  *   "scratch_keep_mb" n: freed scratch (split-K partials, packed complex operands, widened copies) the library's PRIVATE memory pool
