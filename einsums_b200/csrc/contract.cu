@@ -95,6 +95,11 @@ bool make_operand_map(CUtensorMap *map, const double *base, int64_t inner, int64
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+inline int env_int_early(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 // ---- tile shape / split-K choice shared by both TMA kernels. mb, nb: 16-row block counts of the (padded) composite M and N.
 struct TmaChoice { int cfg; int64_t tm, tn; int splits; };
 TmaChoice choose_tma_tile(int64_t mb, int64_t nb, int64_t batches, int64_t KT, int forced_split) {
@@ -174,6 +179,8 @@ int try_run_tma(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const dou
         // the re-reads by four.
         static const int group_env = getenv("EB200_TMA_GROUP") ? atoi(getenv("EB200_TMA_GROUP")) : 0;
         a.group = group_env > 0 ? group_env : 32;
+        static const int prefetch_desc = env_int_early("EB200_TMA_PREFETCH_DESC", 0);
+        a.prefetch_desc = prefetch_desc;
     }
     d.split_k = 1;
     static const size_t smem_pad = getenv("EB200_TMA_SMEM_PAD") ? (size_t)atoi(getenv("EB200_TMA_SMEM_PAD")) : 0; // debugging: forces 1 CTA/SM

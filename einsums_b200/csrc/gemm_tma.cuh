@@ -30,6 +30,7 @@ struct TmaGemmArgs {
     int32_t tiles_m, tiles_n, vec_c;
     int32_t dist;          // prefetch distance in k steps (1 .. STAGES-1), see contract_tma.cuh
     int32_t group;         // tile rows per rasterisation group (B panels are re-read from DRAM once per group when they exceed L2)
+    int32_t prefetch_desc; // 1: prefetch.tensormap for both maps before the barrier set-up
 };
 
 template <bool A_KMAJOR, bool B_KMAJOR>
@@ -62,6 +63,11 @@ __global__ void __launch_bounds__(256, 2) gemm_tma_f64(const __grid_constant__ C
     const int ks0 = 0, nsteps = (int)((args.K + BK - 1) / BK);
 
     if (tid == 0) {
+        // the descriptor fetch of this CTA's first loads overlaps the barrier set-up (EB200_TMA_PREFETCH_DESC=1; measured: no effect, profiles/r2/experiment_prefetch_tensormap_no_effect.txt)
+        if (args.prefetch_desc) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        }
         for (int s = 0; s < STAGES; s++) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), NCONS);

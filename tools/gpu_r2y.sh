@@ -1,4 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -x -k "packed or tma_generic or fuzz" 2>&1 | tail -4 | cut -c1-400
-python tools/probe_wmbej.py 61 243 1
+for i in 1 2; do
+for p in 1 0; do echo "prefetch_desc=$p"; EB200_TMA_PREFETCH_DESC=$p python tools/probe.py wabef 2>&1 | tail -1; done
+done | tee gpurun_out/r2y_prefetch_desc.txt
