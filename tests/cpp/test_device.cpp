@@ -315,6 +315,34 @@ TEST_CASE(gpu_complex_and_float) {
     }
 }
 
+TEST_CASE(gpu_other_types_reach_tensor_cores) {
+    // The same einsum() call, sizes that fill the SMs: FP32 and c64 Wmbej land on the tcgen05 kernel (generic instantiation / packed
+    // operands), c128 on the FP64 tensor pipe (TTGT around gemm_tma_z) — eb200_last_kernel_name() says which; spot rows against host loops.
+    using namespace einsums::index;
+    const size_t o = 12, v = 64;
+    auto check = [&](auto zero, double tol, const char *want_prefix) {
+        using T = decltype(zero);
+        auto t = create_random_gpu_tensor<T>("t", o, o, v, v), g = create_random_gpu_tensor<T>("g", o + 2, o, v, v);
+        auto W = create_random_gpu_tensor<T>("W", o + 2, v, v, o);
+        auto hW0 = host(W);
+        AlgorithmChoice alg;
+        einsum(T(1.0), Indices{m, b, e, j}, &W, T(-0.5), Indices{j, n, f, b}, t, Indices{m, n, e, f}, g, &alg);
+        CHECK(alg == ta::GENERIC);
+        std::string kernel = eb200_last_kernel_name();
+        CHECK(kernel.rfind(want_prefix, 0) == 0);
+        auto ht = host(t), hg = host(g), hW = host(W);
+        for (size_t mm : {size_t(0), size_t(o + 1)}) for (size_t bb : {size_t(3), size_t(v - 1)}) for (size_t ee : {size_t(0), size_t(17)}) for (size_t jj : {size_t(5)}) {
+            std::complex<double> s = 0;
+            for (size_t nn = 0; nn < o; nn++) for (size_t ff = 0; ff < v; ff++) s += std::complex<double>(ht(jj, nn, ff, bb)) * std::complex<double>(hg(mm, nn, ee, ff));
+            std::complex<double> want = std::complex<double>(hW0(mm, bb, ee, jj)) - 0.5 * s;
+            CHECK(std::abs(std::complex<double>(hW(mm, bb, ee, jj)) - want) <= tol * std::max(1.0, std::abs(want)) * double(o * v));
+        }
+    };
+    check(float(0), 1e-6, "gemm_tf32x3_tcgen05");
+    check(std::complex<float>(0), 1e-6, "gemm_tf32x3_tcgen05<c64>");
+    check(std::complex<double>(0), 1e-14, "gemm_tma_z");
+}
+
 TEST_CASE(gpu_mixed_precision) { // GPUTensorAlgebra.hip:2301-2354: d-f-d, d-f-f, f-d-d, cd-cd-d (always GENERIC)
     using namespace einsums::index;
     auto run = [&](auto tc, auto ta, auto tb) {
