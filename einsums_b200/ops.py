@@ -265,7 +265,8 @@ def launch_count_reset():
 
 
 def set_option(name: str, value: int):
-    """Process-wide tuning / testing knob (eb200_set_option): "tma", "tma_generic", "tma_tile"."""
+    """Process-wide tuning / testing knob (eb200_set_option): "tma", "tma_generic", "tma_tile", "tma_dist", "permute_tma",
+    "tcgen05_generic", "tcgen05_pair", "scratch_keep_mb" (include/einsums_b200.h documents the values)."""
     check(lib().eb200_set_option(name.encode(), int(value)))
 
 

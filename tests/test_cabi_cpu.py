@@ -134,3 +134,16 @@ def test_memory_budget_accounting(eb):
     assert lib.eb200_memory_stats(C.byref(b), C.byref(u), C.byref(pk), C.byref(n)) == 0
     assert b.value == 1 << 20 and u.value == 0 and n.value == 0
     assert lib.eb200_set_memory_budget(0) == 0
+
+
+def test_options_round_trip_without_a_device(eb):
+    """eb200_set_option / eb200_get_option: every documented knob exists, keeps its value, and an unknown name is refused (no CUDA call)."""
+    defaults = {"tma": 1, "tma_generic": 1, "tma_tile": -1, "tma_dist": 0, "permute_tma": 1, "tcgen05_generic": 1, "tcgen05_pair": 1, "scratch_keep_mb": 4096}
+    for name, dflt in defaults.items():
+        old = ops.get_option(name)
+        assert old == dflt, (name, old)
+        ops.set_option(name, 7)
+        assert ops.get_option(name) == 7
+        ops.set_option(name, old)
+    with pytest.raises(Exception):
+        ops.set_option("no_such_option", 1)
