@@ -465,6 +465,7 @@ int try_run_tf32x3(cudaStream_t s, const Plan &p, eb200_contract_desc &d, const 
     a.C = (float *)d.C.data;
     a.alpha = (float)d.alpha[0]; a.beta = (float)beta_eff[0];
     a.batch = NB; a.sCb = sCb;
+    a.c_vec4 = (a.sCn == 1 && (a.sCm & 3) == 0 && (N & 3) == 0 && (sCb & 3) == 0 && ((uintptr_t)d.C.data % 16) == 0) ? 1 : 0;
     const int64_t tm = pair ? tm2 : tm1, tn = tn1; // PAIR: tiles_m counts 256-row tile pairs
     if (tm * tn > 0x7fffffffLL || tm * tn * NB > (1LL << 40)) return 0;
     a.tiles_m = (int)tm; a.tiles_n = (int)tn;

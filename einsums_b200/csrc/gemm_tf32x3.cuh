@@ -46,6 +46,7 @@ struct Tf32GemmArgs {
     int32_t cplx;                                       // 1: complex-interleaved C (strides given in floats), 64 complex columns per tile
     int32_t dBc;                                        // tensor-map dimension of B'-plane index
     int32_t b_flat;                                     // the operands carry ONE merged batch dimension (dAb[0] / dBb[0]); C keeps eb / gCb
+    int32_t c_vec4;                                     // plain kernel, sCn == 1: C rows, batch stride and N are multiples of 4 floats, C 16-byte aligned
 };
 
 #ifdef EB200_TF32_KERNEL_IMPL // the kernel itself is compiled by k_tile_tf32.cu only
@@ -394,6 +395,11 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
                            "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                          : "r"(taddr));
         };
+        auto tmem_ld8 = [&](uint32_t taddr, uint32_t(&r)[8]) { // no wait: the caller waits once for several loads
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                         : "r"(taddr));
+        };
         // store 32 columns [n0, n0 + 32) of this thread's row: out = alpha * v + beta * C
         auto store_block = [&](float *Cb, int tile_m, int64_t n0, const float(&v)[32]) {
             const int64_t m = (int64_t)tile_m * BM + quad * 32 + lane;
@@ -614,6 +620,63 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
                         if (i == 0) prefetch_tile(0);
                         if (i + 1 < my_tiles) prefetch_tile(i + 1);
                     }
+                    if (args.c_vec4) {
+                        // 16-byte accesses: lane = (row r0 = lane / 8, column group cg = lane % 8) handles rows r0 + 4 i (i = 0..7) x columns 4 cg .. 4 cg + 3
+                        // of a 32 x 32 block — a quarter of the load / store instructions and addresses of the scalar form
+                        const int     r0 = lane >> 3, cg = lane & 7;
+                        const int64_t ncol = (int64_t)tile_n * BN + 4 * cg;
+                        float4        oldA[8]; // old C values of the block (a second buffer for the next block spills at the 168-register cap: 130 vs 148 TFLOP/s)
+#define EB_LOAD_OLD(Q, O)                                                                                                                         \
+    {                                                                                                                                             \
+        const int64_t nq_ = ncol + 32 * (Q);                                                                                                      \
+        _Pragma("unroll") for (int i2 = 0; i2 < 8; i2++) {                                                                                        \
+            const int64_t mm_ = mrow0 + r0 + 4 * i2;                                                                                              \
+            O[i2] = (mm_ < args.M && nq_ < args.N) ? *reinterpret_cast<const float4 *>(Cb + mm_ * args.sCm + nq_) : make_float4(0.f, 0.f, 0.f, 0.f); \
+        }                                                                                                                                         \
+    }
+#define EB_BLOCK(Q, CUR, NXT, HAS_NEXT)                                                                                                           \
+    {                                                                                                                                             \
+        if (beta != 0.f) EB_LOAD_OLD((Q), CUR)                                                                                                    \
+        _Pragma("unroll") for (int h = 0; h < 4; h++) {                                                                                           \
+            uint32_t       r[8], x[8];                                                                                                            \
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * 256 + 32 * (Q) + 8 * h);                           \
+            tmem_ld8(taddr, r);                                                                                                                   \
+            tmem_ld8(taddr + 128u, x);                                                                                                            \
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");                                                                          \
+            _Pragma("unroll") for (int j = 0; j < 8; j++) patch[lane * 33 + 8 * h + j] = __uint_as_float(r[j]) + __uint_as_float(x[j]);           \
+        }                                                                                                                                         \
+        if ((Q) == BN / 32 - 1) {                                                                                                                 \
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");                                                                      \
+            arrive_drained(ab);                                                                                                                   \
+        }                                                                                                                                         \
+        __syncwarp();                                                                                                                             \
+        const int64_t n = ncol + 32 * (Q);                                                                                                        \
+        if (n < args.N) {                                                                                                                         \
+            _Pragma("unroll") for (int i2 = 0; i2 < 8; i2++) {                                                                                    \
+                const int     rr = r0 + 4 * i2;                                                                                                   \
+                const int64_t mm = mrow0 + rr;                                                                                                    \
+                if (mm < args.M) {                                                                                                                \
+                    const float *pp = patch + rr * 33 + 4 * cg;                                                                                   \
+                    float4       o = make_float4(alpha * pp[0], alpha * pp[1], alpha * pp[2], alpha * pp[3]);                                     \
+                    if (beta != 0.f) {                                                                                                            \
+                        const float4 c = CUR[i2];                                                                                                 \
+                        o.x = fmaf(beta, c.x, o.x); o.y = fmaf(beta, c.y, o.y); o.z = fmaf(beta, c.z, o.z); o.w = fmaf(beta, c.w, o.w);           \
+                    }                                                                                                                             \
+                    *reinterpret_cast<float4 *>(Cb + mm * args.sCm + n) = o;                                                                      \
+                }                                                                                                                                 \
+            }                                                                                                                                     \
+        }                                                                                                                                         \
+        __syncwarp();                                                                                                                             \
+    }
+                        mbar_wait(chunk_full(ab), (gc / NACC) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        EB_BLOCK(0, oldA, oldA, true)
+                        EB_BLOCK(1, oldA, oldA, true)
+                        EB_BLOCK(2, oldA, oldA, true)
+                        EB_BLOCK(3, oldA, oldA, false)
+#undef EB_BLOCK
+#undef EB_LOAD_OLD
+                    } else {
                     mbar_wait(chunk_full(ab), (gc / NACC) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -651,6 +714,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tf32x3_tcgen05(const __grid_const
                             }
                         }
                         __syncwarp();
+                    }
                     }
                 } else {
                     mbar_wait(chunk_full(ab), (gc / NACC) & 1);

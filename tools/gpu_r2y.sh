@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 bash tools/ncu_capture.sh r2_tf32_wabef_beta1 gemm_tf32x3 1 python tools/probe_wabef_f32_one.py 1.0
-timeout 300 bash tools/ncu_capture.sh r2_tf32_wabef_beta0 gemm_tf32x3 1 python tools/probe_wabef_f32_one.py 0.0
+timeout 300 python -m pytest tests -m gpu -q -x -k "tcgen05 or sgemm" 2>&1 | tail -4 | cut -c1-400
+(echo "pair=1"; timeout 120 python tools/probe_f32.py 1) 2>&1 | tee gpurun_out/r2y_probe_f32_vec4.txt
