@@ -45,6 +45,8 @@ enum { OPT_TMA = 0, OPT_TMA_GENERIC, OPT_TMA_TILE, OPT_TMA_DIST, OPT_PERMUTE_TMA
 int option(int which);
 /// stream-ordered scratch from the library's private memory pool (runtime.cu); release with cudaFreeAsync on the same stream
 int scratch_alloc(void **p, size_t bytes, cudaStream_t s);
+/// a call about to take `bytes` of scratch in total: lets the pool keep that much cached (bounded by 1/8 of the device memory)
+void scratch_expect(size_t bytes);
 
 // ---------------------------------------------------------------- scalar algebra
 // real types are float/double; complex are float2/double2 (interleaved re,im = the C ABI layout)

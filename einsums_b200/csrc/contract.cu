@@ -373,6 +373,7 @@ int try_run_tma_generic_packed(cudaStream_t s, const Plan &p, eb200_contract_des
     p2.a_kmajor = p2.b_kmajor = 1;
     void *Ap = nullptr, *Bp = nullptr;
     int   rc;
+    scratch_expect((size_t)(elemsA + elemsB) * 8);
     if ((rc = scratch_alloc(&Ap, (size_t)elemsA * 8, s)) || (rc = scratch_alloc(&Bp, (size_t)elemsB * 8, s))) {
         if (Ap) cudaFreeAsync(Ap, s);
         return rc == EB200_ERR_OUT_OF_MEMORY ? 0 : -rc;
@@ -561,6 +562,7 @@ int try_run_z_packed(cudaStream_t s, const Plan &p, eb200_contract_desc &d, cons
     if (mode != 2 && (tm * tn <= sm_count() || K < 32)) return 0;
     void *Ap = nullptr, *Bp = nullptr, *Tp = nullptr;
     int   rc;
+    scratch_expect(((size_t)NBt * M * K + (size_t)NBt * N * K + (size_t)NBt * M * N) * 16);
     if ((rc = scratch_alloc(&Ap, (size_t)NBt * M * K * 16, s)) || (rc = scratch_alloc(&Bp, (size_t)NBt * N * K * 16, s)) ||
         (rc = scratch_alloc(&Tp, (size_t)NBt * M * N * 16, s))) {
         if (Ap) cudaFreeAsync(Ap, s);
@@ -865,6 +867,7 @@ template <bool CPLX> int try_run_packed_tcgen05(cudaStream_t s, const Plan &p, e
     };
     const float alpha_c[2] = {(float)d.alpha[0], (float)d.alpha[1]}, one_c[2] = {1.f, 0.f};
     const size_t bytesA = (size_t)NBt * M * Kp * 4 * W, bytesBc = CPLX ? (size_t)NBt * N * K * 8 : 0, bytesBp = (size_t)NBt * W * N * Kp * 4 * W;
+    scratch_expect(bytesA + bytesBc + bytesBp + (size_t)NBt * M * N * 4 * W); // + the dense temporary some C layouts need
     if ((rc = scratch_alloc(&Ap, bytesA, s)) || (CPLX && (rc = scratch_alloc(&Bc, bytesBc, s))) || (rc = scratch_alloc(&Bp, bytesBp, s))) {
         if (Ap) cudaFreeAsync(Ap, s);
         if (Bc) cudaFreeAsync(Bc, s);

@@ -326,8 +326,10 @@ const char *eb200_last_kernel_name(void);
  *                  default from EB200_TCGEN05_GENERIC
  *   "tcgen05_pair" 1 | 0 | 2: plain / batched FP32 products on CTA pairs (cta_group::2, 256 x 128 tile pairs) when M pads by <= 5 % and
  *                  every pair has work / never / always (default from EB200_TCGEN05_PAIR)
- *   "scratch_keep_mb" n: freed scratch (split-K partials, packed complex operands, widened copies) the library's PRIVATE memory pool
- *                  keeps cached across synchronisations, in MB (default 4096, EB200_SCRATCH_KEEP_MB); the rest goes back to the driver */
+ *   "scratch_keep_mb" n: freed scratch (split-K partials, packed operands, widened copies) the library's PRIVATE memory pool keeps
+ *                  cached across synchronisations, in MB (default 4096, EB200_SCRATCH_KEEP_MB); the rest goes back to the driver. A
+ *                  contraction that needs more scratch than that in one call raises the threshold to its own demand, bounded by an
+ *                  eighth of the device memory, so that repeated calls do not re-acquire it; 0 switches caching and growth off */
 int eb200_set_option(const char *name, int value);
 int eb200_get_option(const char *name, int *value);
 
